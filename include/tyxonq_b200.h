@@ -1,0 +1,174 @@
+/*
+ * tyxonq_b200 -- C ABI of the B200-native statevector engine (libtyxonq_b200.so).
+ *
+ * The reference (QureGenAI-Biotech/TyxonQ) is pure Python and has no FFI of its own; the
+ * drop-in seams are Python.  This header is the boundary BELOW those
+ * seams: plain pointers and sizes, no torch types.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference's src/tyxonq/).
+ *
+ * Conventions
+ *   - A state is `batch` consecutive arrays of 2^n complex amplitudes in device memory,
+ *     complex64 (TQB_C64: float re,im) or complex128 (TQB_C128: double re,im).
+ *   - "bit p" is bit p of the flat amplitude index.  TyxonQ qubit q of an n-qubit register is
+ *     bit n-1-q (big-endian, libs/quantum_library/kernels/statevector.py:28-42).
+ *   - For a sharded state the local array holds 2^n amplitudes and `global_base` carries the
+ *     rank's high-order index bits (rank << n); diagonal tables and parity masks see
+ *     global_base | local_index.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  No entry
+ *     point synchronises, allocates or frees device memory except tqb_init/tqb_shutdown,
+ *     so everything else can be captured into a CUDA graph.
+ *   - Return value: 0 on success, negative on error; tqb_last_error() gives the message.
+ */
+#ifndef TYXONQ_B200_H
+#define TYXONQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQB_ABI_VERSION 1
+
+#define TQB_C64 0
+#define TQB_C128 1
+
+#define TQB_GATE_DENSE 0 /* dense 2^k x 2^k matrix, k <= 4, row-major, row = output index      */
+#define TQB_GATE_DIAG 1  /* diagonal: table of 2^k entries indexed by k GLOBAL index bits       */
+#define TQB_GATE_PAIR 2  /* 2x2 matrix on the pair (pattern A, pattern B) of k target bits,     */
+                         /* all other patterns untouched (cx, swap, controlled-U, UCC Givens)  */
+
+#define TQB_MAX_DENSE_K 4
+#define TQB_MAX_GATE_BITS 8
+#define TQB_MAX_TILE_HIGH 16
+
+/* One gate of a pass.  Matrix-index bit j (j = 0 least significant) lives on bits[j].
+ * DENSE/PAIR: bits[] are TILE-LOCAL positions (see tqb_pass); DIAG: GLOBAL index bits.      */
+typedef struct tqb_gate {
+  int32_t kind;
+  int32_t k;
+  int8_t bits[TQB_MAX_GATE_BITS];
+  int8_t sbits[TQB_MAX_GATE_BITS]; /* DENSE/PAIR: bits[] sorted ascending                    */
+  uint32_t off_a, off_b;           /* PAIR: tile-local offsets of patterns A and B            */
+  uint32_t mat_off;                /* offset (complex elements) into the matrix buffer        */
+  uint32_t mat_bstride;            /* per-batch-member stride (complex elements), 0 = shared  */
+  uint64_t zmask;                  /* PAIR: parity of popc(global_index & zmask) picks the     */
+                                   /* 2x2 at mat_off (even) or mat_off+4 (odd); 0 = no parity */
+} tqb_gate;                        /* 48 bytes */
+
+/* One pass = one read-modify-write sweep over the whole state.  Every CTA stages tiles of 2^m
+ * amplitudes in shared memory: the L lowest index bits (contiguous runs of 2^L amplitudes)
+ * plus the m-L high bits hb[] (ascending, each >= L).  Tile-local bit j is index bit j for
+ * j < L and index bit hb[j-L] otherwise.  All gates[gate_begin .. gate_begin+n_gates) are
+ * applied to the tile before it is written back.                                             */
+typedef struct tqb_pass {
+  int32_t m;
+  int32_t L;
+  int32_t gate_begin;
+  int32_t n_gates;
+  int32_t max_dense_k; /* largest k of a DENSE gate in the pass (selects the kernel variant)  */
+  int8_t hb[TQB_MAX_TILE_HIGH];
+} tqb_pass; /* 36 bytes */
+
+/* ---- library ------------------------------------------------------------------------- */
+int tqb_abi_version(void);
+const char *tqb_last_error(void);
+/* Allocates the per-device reduction workspace (call once per device before anything else). */
+int tqb_init(int device);
+int tqb_shutdown(int device);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches).         */
+int64_t tqb_launch_count(void);
+/* max dynamic shared memory per CTA (bytes) and SM count of `device`.                        */
+int tqb_device_info(int device, int *sm_count, int *max_smem_optin);
+
+/* ---- state construction -------------------------------------------------------------- */
+/* replaces init_statevector (libs/quantum_library/kernels/statevector.py:19-25): every batch
+ * member becomes the basis state |basis_index> (amplitude 1 at local index basis_index if it
+ * lies in this shard: basis_index - global_base in [0, 2^n)).                                */
+int tqb_init_basis(void *state, int n, int64_t batch, int dtype, uint64_t global_base,
+                   uint64_t basis_index, void *stream);
+
+/* ---- gate application ---------------------------------------------------------------- */
+/* replaces apply_1q_statevector / apply_2q_statevector / apply_kqubit_unitary
+ * (statevector.py:28-129) and the per-op loop of StatevectorEngine.run/state
+ * (devices/simulators/statevector/engine.py:52-374, 914-1038): runs n_passes fused passes in
+ * place.  passes: HOST array; gates, mats: DEVICE arrays (mats in the state's dtype).
+ * threads: CTA size (multiple of 32, <= 1024).  ctas_per_sm: 0 = auto.                      */
+int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global_base,
+                   const tqb_pass *passes, int n_passes, const tqb_gate *gates_dev,
+                   const void *mats_dev, int threads, int ctas_per_sm, void *stream);
+
+/* ---- reductions ---------------------------------------------------------------------- */
+/* out_dev[b] = sum_i |psi_b,i|^2 (float64).                                                  */
+int tqb_norm2(const void *state, int n, int64_t batch, int dtype, double *out_dev, void *stream);
+/* replaces expect_z_statevector called once per qubit (statevector.py:62-68, engine.py:467-473):
+ * out_dev[b*n + p] = sum_i |psi_i|^2 (1 - 2 bit_p(i)) for every LOCAL bit p in one read.     */
+int tqb_expect_z_bits(const void *state, int n, int64_t batch, int dtype, double *out_dev,
+                      void *stream);
+/* replaces the per-term Python loops of postprocessing/counts_expval.py:55-84 and
+ * examples/vqetfim_benchmark.py:96-102: out_dev[b*n_masks + t] = sum_i |psi_i|^2
+ * (-1)^popc((global_base|i) & masks_dev[t]).                                                  */
+int tqb_expect_zmasks(const void *state, int n, int64_t batch, int dtype, uint64_t global_base,
+                      const uint64_t *masks_dev, int n_masks, double *out_dev, void *stream);
+/* replaces pauli_string_sum_dense + dynamics.expectation (kernels/pauli.py:74-87,
+ * dynamics.py:117-126), matrix free.  Term t is coef[t] * i^ny * X^xmask Z^zmask with the
+ * i^ny phase already folded into the complex coef (re,im pairs, float64).  Terms must be
+ * grouped by xmask: group g covers terms [group_ptr[g], group_ptr[g+1]) and has xmask
+ * group_x[g].  out_dev[b] (2 doubles: re, im) = <psi_b| H |psi_b>.  All arrays on device.
+ * Local xmasks only (xmask < 2^n).                                                            */
+int tqb_expect_pauli_sum(const void *state, int n, int64_t batch, int dtype, uint64_t global_base,
+                         const uint64_t *group_x, const int32_t *group_ptr, int n_groups,
+                         const uint64_t *term_z, const double *term_coef, double *out_dev,
+                         void *stream);
+/* replaces apply_op (applications/chem/chem_libs/hamiltonians_chem_library/
+ * hamiltonian_builders.py:283-318) without densifying H: out = H psi, same term layout.    */
+int tqb_apply_pauli_sum(const void *state, void *out, int n, int64_t batch, int dtype,
+                        uint64_t global_base, const uint64_t *group_x, const int32_t *group_ptr,
+                        int n_groups, const uint64_t *term_z, const double *term_coef,
+                        void *stream);
+/* out_dev[b] (re,im float64) = <a_b|b_b> = sum_i conj(a_i) b_i.                              */
+int tqb_inner(const void *a, const void *b, int n, int64_t batch, int dtype, double *out_dev,
+              void *stream);
+/* Gradient reductions of the adjoint sweep (model: civector_ops.py:141-200).
+ * PAIR generator: out_dev[slot] += scale * Re sum_groups s(i) (conj(bra_A) ket_B - conj(bra_B) ket_A)
+ * with s = (-1)^popc(index & zmask); bits/off as in a PAIR gate with m = n (whole state).   */
+int tqb_grad_pair(const void *bra, const void *ket, int n, int dtype, const tqb_gate *gate_host,
+                  double scale, double *out_dev, int slot, void *stream);
+/* DENSE generator D (2^k x 2^k, float64 re,im pairs on HOST, k <= 2):
+ * out_dev[slot] += scale * Re <bra| D_bits |ket>.                                            */
+int tqb_grad_dense(const void *bra, const void *ket, int n, int dtype, int k, const int *bits,
+                   const double *gen_host, double scale, double *out_dev, int slot, void *stream);
+
+/* ---- measurement --------------------------------------------------------------------- */
+/* replaces StatevectorEngine._project_z (engine.py:1075-1087): zero the half with
+ * bit != keep, then scale by 1/sqrt(sum |psi|^2) when that sum is > 0.                      */
+int tqb_project_z(void *state, int n, int64_t batch, int dtype, int bit, int keep, void *stream);
+/* state *= factor (host scalar).                                                             */
+int tqb_scale(void *state, int n, int64_t batch, int dtype, double factor, void *stream);
+/* out_dev[b*2^n + i] = |psi_i|^2 as float64 (re*re + im*im, no FMA).                         */
+int tqb_probabilities(const void *state, int n, int64_t batch, int dtype, double *out_dev,
+                      void *stream);
+
+/* Sampler: replaces numpy Generator.choice + bincount in StatevectorEngine.run
+ * (engine.py:377-418).  The CDF is the documented blocked prefix sum (oracle/sv_oracle.py
+ * blocked_cdf): sequential float64 sums inside chunks of TQB_SCAN_BLOCK amplitudes, then a
+ * sequential sum of the chunk totals.                                                        */
+#define TQB_SCAN_BLOCK 4096
+/* chunk_prefix_dev: batch * (n_chunks + 1) doubles, n_chunks = max(1, 2^n / TQB_SCAN_BLOCK);
+ * entry [c] = sum of chunks < c, entry [n_chunks] = total.                                   */
+int tqb_cdf_chunks(const void *state, int n, int64_t batch, int dtype, double *chunk_prefix_dev,
+                   void *stream);
+/* idx_dev[b*shots + s] = #{ i : cdf_i / cdf_last <= uniforms_dev[b*shots + s] }  (int64).    */
+int tqb_sample(const void *state, int n, int64_t batch, int dtype, const double *chunk_prefix_dev,
+               const double *uniforms_dev, int64_t shots, int64_t *idx_dev, void *stream);
+
+/* ---- sharded states ------------------------------------------------------------------ */
+/* Local half of a global<->local qubit exchange: dst/src are chunk views; copies `count`
+ * complex elements (used to unpack received blocks back into the shard).                     */
+int tqb_copy(void *dst, const void *src, int64_t count, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TYXONQ_B200_H */

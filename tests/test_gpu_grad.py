@@ -1,0 +1,120 @@
+"""Gradients on the device: torch.autograd.Function (adjoint sweep) and the UCC energy+gradient path.
+
+Energies within 1e-10 of the oracle; UCC energy + gradient within 1e-8 (BASELINE.json north_star)."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import sv_oracle as O
+from oracle import ucc_oracle as U
+from tests.conftest import FakeCircuit
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_circuit(n, thetas):
+    """rx/ry/rz/rxx/ryy/rzz/cx circuit with torch angles (the gate set of the reference's
+    tests_core_module/test_all_gates_gradient.py:16-127 and test_circuit_state_autograd.py)."""
+    t = thetas
+    ops = [("h", 0), ("rx", 0, t[0]), ("ry", 1, t[1]), ("rz", 2, t[2]), ("cx", 0, 1), ("rxx", 1, 2, t[3]),
+           ("ryy", 0, 2, t[4]), ("rzz", 0, 1, t[5]), ("cz", 1, 2), ("rx", 2, t[0] * 2.0), ("s", 1), ("swap", 0, 2)]
+    return FakeCircuit(n, ops)
+
+
+def _loss_np(theta):
+    t = [float(x) for x in theta]
+    ops = [("h", 0), ("rx", 0, t[0]), ("ry", 1, t[1]), ("rz", 2, t[2]), ("cx", 0, 1), ("rxx", 1, 2, t[3]),
+           ("ryy", 0, 2, t[4]), ("rzz", 0, 1, t[5]), ("cz", 1, 2), ("rx", 2, t[0] * 2.0), ("s", 1), ("swap", 0, 2)]
+    psi, _ = O.evolve_ops(3, ops)
+    w = np.arange(1, 9, dtype=np.float64)
+    return float(np.sum(w * np.abs(psi) ** 2) + np.real(psi[1] * np.conj(psi[6])))
+
+
+@pytest.mark.parametrize("pdtype", ["float64", "float32"])
+def test_state_autograd_matches_finite_differences(cuda_device, pdtype):
+    import torch
+    from tyxonq_b200 import StatevectorEngine
+    theta0 = np.array([0.3, -0.7, 1.1, 0.5, -0.2, 0.9])
+    td = torch.float64 if pdtype == "float64" else torch.float32
+    theta = torch.tensor(theta0, dtype=td, requires_grad=True)
+    eng = StatevectorEngine("pytorch", device=cuda_device)
+    psi = eng.state(_torch_circuit(3, theta))
+    assert isinstance(psi, torch.Tensor) and psi.dtype == torch.complex128 and not psi.is_cuda and psi.requires_grad
+    w = torch.arange(1, 9, dtype=torch.float64)
+    loss = torch.sum(w * psi.abs() ** 2) + torch.real(psi[1] * torch.conj(psi[6]))
+    loss.backward()
+    th_used = theta.detach().double().numpy()
+    assert abs(float(loss) - _loss_np(th_used)) < 1e-10
+    fd = O.central_fd_gradient(_loss_np, th_used, 1e-6)
+    tol = 1e-7 if pdtype == "float64" else 1e-5
+    assert theta.grad.dtype == td
+    assert np.abs(theta.grad.double().numpy() - fd).max() < tol
+
+
+def test_state_autograd_kat(cuda_device):
+    # test_circuit_state_autograd.py: <Z> = cos(0.5) after rx(0.5); d<Z>/dtheta = -sin(theta)
+    import torch
+    from tyxonq_b200 import StatevectorEngine
+    th = torch.tensor(0.5, dtype=torch.float64, requires_grad=True)
+    psi = StatevectorEngine("pytorch", device=cuda_device).state(FakeCircuit(1, [("rx", 0, th)]))
+    z = psi[0].abs() ** 2 - psi[1].abs() ** 2
+    z.backward()
+    assert abs(float(z) - np.cos(0.5)) < 1e-12 and abs(float(th.grad) + np.sin(0.5)) < 1e-10
+
+
+def _ucc_problem(nao, ne):
+    from tyxonq_b200 import ucc
+    n = 2 * nao
+    no, nv = ne // 2, nao - ne // 2
+    ex_ops, param_ids = ucc.uccsd_ex_ops(no, nv)
+    assert (ex_ops, param_ids) == U.uccsd_ex_ops(no, nv)
+    i1, i2 = ucc.random_integral(nao, 2077)
+    o1, o2 = U.random_integral(nao, 2077)
+    assert np.array_equal(i1, o1) and np.array_equal(i2, o2)
+    return n, (ne // 2, ne // 2), ex_ops, param_ids, i1, i2
+
+
+def test_ucc_small_energy_grad(cuda_device):
+    import torch
+    from tyxonq_b200 import ucc
+    n, nes, ex_ops, pids, i1, i2 = _ucc_problem(4, 4)
+    ham = ucc.hamiltonian_from_integral(i1, i2)
+    Hs = U.hamiltonian_from_integral(i1, i2)
+    # the Pauli-sum H equals the fermionic sparse H on a random vector
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    assert np.abs(ham.apply(torch.from_numpy(v).to(cuda_device)).cpu().numpy() - Hs @ v).max() < 1e-10
+    np.random.seed(2077)
+    params = np.random.rand(max(pids) + 1) - 0.5
+    sv = ucc.UCCStatevector(n, nes, ex_ops, pids, ham, device=cuda_device)
+    psi = sv.statevector(params).cpu().numpy()
+    assert np.abs(psi - U.get_statevector(params, n, nes, ex_ops, pids)).max() < 1e-10
+    e_ref, g_ref = U.energy_and_grad_adjoint(params, Hs, n, nes, ex_ops, pids)
+    assert abs(sv.energy(params) - e_ref) < 1e-10
+    e, g = sv.energy_and_grad(params)
+    assert abs(e - e_ref) < 1e-10 and np.abs(g - g_ref).max() < 1e-8
+    fd = O.central_fd_gradient(lambda p: U.energy(p, Hs, n, nes, ex_ops, pids), params, 1e-6)
+    assert np.abs(g - fd).max() < 1e-6
+
+
+def test_ucc_h2o_shape_energy_grad(cuda_device):
+    """Config 2 of BASELINE.json: 14 qubits, (5,5) electrons, 140 excitations / 75 parameters,
+    synthetic integrals random_integral(7, 2077) (PySCF is not installable: parity with the real
+    molecule is unpinned)."""
+    from tyxonq_b200 import ucc
+    n, nes, ex_ops, pids, i1, i2 = _ucc_problem(7, 10)
+    assert n == 14 and len(ex_ops) == 140 and max(pids) + 1 == 75
+    ham = ucc.hamiltonian_from_integral(i1, i2)
+    Hs = U.hamiltonian_from_integral(i1, i2)
+    np.random.seed(2077)
+    params = np.random.rand(75) - 0.5
+    sv = ucc.UCCStatevector(n, nes, ex_ops, pids, ham, device=cuda_device)
+    e_ref, g_ref = U.energy_and_grad_adjoint(params, Hs, n, nes, ex_ops, pids)
+    e, g = sv.energy_and_grad(params)
+    assert abs(e - e_ref) < 1e-8
+    assert np.abs(g - g_ref).max() < 1e-8
+    # second call with other parameters reuses the compiled programs
+    e2, g2 = sv.energy_and_grad(params * 0.5)
+    e2_ref, g2_ref = U.energy_and_grad_adjoint(params * 0.5, Hs, n, nes, ex_ops, pids)
+    assert abs(e2 - e2_ref) < 1e-8 and np.abs(g2 - g2_ref).max() < 1e-8

@@ -1,0 +1,36 @@
+"""tyxonq_b200 -- B200-native (sm_100a) statevector engine behind TyxonQ's device/numerics API.
+
+Scope: the one data-parallel hot path of QureGenAI-Biotech/TyxonQ -- gate application on the
+2^n-amplitude state, Pauli-sum expectation, shot sampling and VQE parameter gradients.  Python
+host code (this package) drives hand-written CUDA kernels through the C ABI declared in
+``include/tyxonq_b200.h``; there is no CPU fallback.
+
+Public surface (mirrors the reference's names):
+  StatevectorEngine           devices/simulators/statevector/engine.py
+  kernels.*                   libs/quantum_library/kernels/statevector.py
+  PauliSum                    libs/quantum_library/kernels/pauli.py + dynamics.expectation
+  install()                   route ``device="statevector"`` of a live TyxonQ install to this engine
+"""
+from __future__ import annotations
+
+from ._lib import TqbError, launch_count, load  # noqa: F401
+
+__version__ = "0.1.0"
+
+_LAZY = {
+    "StatevectorEngine": ("engine", "StatevectorEngine"),
+    "PauliSum": ("pauli", "PauliSum"),
+    "install": ("install", "install"),
+    "uninstall": ("install", "uninstall"),
+}
+
+
+def __getattr__(name: str):
+    if name in _LAZY:
+        import importlib
+        mod, attr = _LAZY[name]
+        return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
+    if name in ("kernels", "engine", "pauli", "program", "planner", "gates", "autograd", "ucc", "vqe", "sharded", "circuits"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

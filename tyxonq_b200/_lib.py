@@ -1,0 +1,132 @@
+"""ctypes binding of libtyxonq_b200.so (the C ABI declared in include/tyxonq_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a CUDA device is not
+available, every compute entry point raises.  Loading the library itself needs only
+libcudart, so symbol checks work on a box without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libtyxonq_b200.so"
+
+TQB_C64, TQB_C128 = 0, 1
+GATE_DENSE, GATE_DIAG, GATE_PAIR = 0, 1, 2
+MAX_GATE_BITS = 8
+MAX_TILE_HIGH = 16
+SCAN_BLOCK = 4096
+
+# numpy mirrors of the ABI structs (layout checked against ctypes.sizeof below)
+GATE_DTYPE = np.dtype([
+    ("kind", "<i4"), ("k", "<i4"),
+    ("bits", "i1", (MAX_GATE_BITS,)), ("sbits", "i1", (MAX_GATE_BITS,)),
+    ("off_a", "<u4"), ("off_b", "<u4"), ("mat_off", "<u4"), ("mat_bstride", "<u4"),
+    ("zmask", "<u8"),
+], align=True)
+PASS_DTYPE = np.dtype([
+    ("m", "<i4"), ("L", "<i4"), ("gate_begin", "<i4"), ("n_gates", "<i4"), ("max_dense_k", "<i4"),
+    ("hb", "i1", (MAX_TILE_HIGH,)),
+], align=True)
+assert GATE_DTYPE.itemsize == 48, GATE_DTYPE.itemsize
+assert PASS_DTYPE.itemsize == 36, PASS_DTYPE.itemsize
+
+_vp = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_u64 = C.c_uint64
+_d = C.c_double
+
+# name -> (restype, argtypes); must list every symbol include/tyxonq_b200.h declares
+SIGNATURES = {
+    "tqb_abi_version": (_i, []),
+    "tqb_last_error": (C.c_char_p, []),
+    "tqb_init": (_i, [_i]),
+    "tqb_shutdown": (_i, [_i]),
+    "tqb_launch_count": (_i64, []),
+    "tqb_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i)]),
+    "tqb_init_basis": (_i, [_vp, _i, _i64, _i, _u64, _u64, _vp]),
+    "tqb_run_passes": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "tqb_norm2": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "tqb_expect_z_bits": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "tqb_expect_zmasks": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp]),
+    "tqb_expect_pauli_sum": (_i, [_vp, _i, _i64, _i, _u64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "tqb_apply_pauli_sum": (_i, [_vp, _vp, _i, _i64, _i, _u64, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tqb_inner": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp]),
+    "tqb_grad_pair": (_i, [_vp, _vp, _i, _i, _vp, _d, _vp, _i, _vp]),
+    "tqb_grad_dense": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _d, _vp, _i, _vp]),
+    "tqb_project_z": (_i, [_vp, _i, _i64, _i, _i, _i, _vp]),
+    "tqb_scale": (_i, [_vp, _i, _i64, _i, _d, _vp]),
+    "tqb_probabilities": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "tqb_cdf_chunks": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
+    "tqb_sample": (_i, [_vp, _i, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
+    "tqb_copy": (_i, [_vp, _vp, _i64, _i, _vp]),
+}
+
+
+class TqbError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+_inited_devices: set = set()
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no GPU needed) and bind every ABI symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise TqbError(
+            f"{LIB_PATH} is missing: build it with `python -m tyxonq_b200.build` "
+            "(tyxonq_b200 has no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header drift apart
+        fn.restype = res
+        fn.argtypes = args
+    if lib.tqb_abi_version() != 1:
+        raise TqbError("libtyxonq_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().tqb_last_error()
+        raise TqbError(msg.decode() if msg else f"tqb error {rc}")
+
+
+def ensure_device(device_index: int) -> None:
+    """tqb_init for a CUDA device (allocates the reduction workspace once)."""
+    if device_index in _inited_devices:
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise TqbError("tyxonq_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    check(load().tqb_init(int(device_index)))
+    _inited_devices.add(device_index)
+
+
+def launch_count() -> int:
+    return int(load().tqb_launch_count())
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+    if torch_dtype == torch.complex128:
+        return TQB_C128
+    if torch_dtype == torch.complex64:
+        return TQB_C64
+    raise TqbError(f"unsupported state dtype {torch_dtype}")
+
+
+def current_stream_ptr(device) -> int:
+    import torch
+    return int(torch.cuda.current_stream(device).cuda_stream)

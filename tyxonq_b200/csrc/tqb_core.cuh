@@ -1,0 +1,229 @@
+// tqb_core.cuh -- index arithmetic and per-thread tile phases of the fused gate pass.
+//
+// Everything here is __host__ __device__: the CUDA kernel in tqb_tile.cu calls these
+// functions from every thread with __syncthreads() between phases, and the host-side
+// emulator in tests/emu/ (test tooling, never shipped or loaded by the package) calls
+// the very same functions from nested loops, so the index logic can be checked against
+// the oracle on a box without a GPU.
+//
+// Reference semantics implemented (paths relative to the reference's src/tyxonq/):
+//   apply_1q_statevector / apply_2q_statevector   libs/quantum_library/kernels/statevector.py:28-59
+//   apply_kqubit_unitary                          libs/quantum_library/kernels/statevector.py:71-129
+#pragma once
+#include <stdint.h>
+
+#include "../../include/tyxonq_b200.h"
+
+#if defined(__CUDACC__)
+#define TQB_HD __host__ __device__ __forceinline__
+#else
+#define TQB_HD inline
+#endif
+
+namespace tqb {
+
+template <typename T>
+struct alignas(2 * sizeof(T)) cplx {
+  T x, y;
+};
+
+// V consecutive amplitudes moved as one 16-byte access (V = 1 for complex128, 2 for complex64).
+template <typename T, int V>
+struct alignas(sizeof(cplx<T>) * V) cvec {
+  cplx<T> e[V];
+};
+
+template <typename T>
+TQB_HD cplx<T> cmul(cplx<T> a, cplx<T> b) {
+  return cplx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T>
+TQB_HD void cmac(cplx<T> &acc, cplx<T> a, cplx<T> b) {
+  acc.x += a.x * b.x;
+  acc.x -= a.y * b.y;
+  acc.y += a.x * b.y;
+  acc.y += a.y * b.x;
+}
+
+TQB_HD int popc64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(v);
+#else
+  return __builtin_popcountll(v);
+#endif
+}
+
+// Geometry of one pass, passed to the kernel by value.
+struct TileGeom {
+  int n;                 // local index bits of one batch member
+  int m;                 // tile bits
+  int L;                 // low contiguous bits
+  int h;                 // m - L
+  uint64_t global_base;  // high-order bits of a sharded state (rank << n), else 0
+  int8_t hb[TQB_MAX_TILE_HIGH];
+};
+
+// Insert a zero bit at each of the k ascending positions sb[].
+TQB_HD uint32_t insert_zeros32(uint32_t g, const int8_t *sb, int k) {
+  for (int j = 0; j < k; ++j) {
+    const uint32_t p = (uint32_t)sb[j];
+    g = ((g >> p) << (p + 1)) | (g & ((1u << p) - 1u));
+  }
+  return g;
+}
+TQB_HD uint64_t insert_zeros64(uint64_t g, const int8_t *sb, int k) {
+  for (int j = 0; j < k; ++j) {
+    const uint64_t p = (uint64_t)sb[j];
+    g = ((g >> p) << (p + 1)) | (g & ((1ull << p) - 1ull));
+  }
+  return g;
+}
+
+// Index (within one batch member) of element 0 of tile t: t's bits deposited into the
+// index bits that are NOT tile bits.
+TQB_HD uint64_t tile_base(const TileGeom &g, uint64_t t) {
+  return insert_zeros64(t << g.L, g.hb, g.h);
+}
+// Offset of contiguous run j (j < 2^h) inside a tile.
+TQB_HD uint64_t run_offset(const TileGeom &g, uint32_t j) {
+  uint64_t o = 0;
+  for (int i = 0; i < g.h; ++i) o |= (uint64_t)((j >> i) & 1u) << g.hb[i];
+  return o;
+}
+// State index of tile-local element `local` (roff = table of run_offset for all j).
+TQB_HD uint64_t local_to_index(const TileGeom &g, const uint64_t *roff, uint64_t base, uint32_t local) {
+  return base | roff[local >> g.L] | (uint64_t)(local & ((1u << g.L) - 1u));
+}
+
+// ---- phase 1/3: stage a tile in shared memory, write it back ------------------------------
+template <typename T, int V>
+TQB_HD void tile_load(cplx<T> *tile, const cplx<T> *state, const TileGeom &g, const uint64_t *roff,
+                      uint64_t base, int tid, int nthreads) {
+  const uint32_t nvec = (1u << g.m) / V;
+  for (uint32_t i = tid; i < nvec; i += nthreads) {
+    const uint32_t local = i * V;
+    const uint64_t idx = local_to_index(g, roff, base, local);
+    *reinterpret_cast<cvec<T, V> *>(tile + local) = *reinterpret_cast<const cvec<T, V> *>(state + idx);
+  }
+}
+template <typename T, int V>
+TQB_HD void tile_store(const cplx<T> *tile, cplx<T> *state, const TileGeom &g, const uint64_t *roff,
+                       uint64_t base, int tid, int nthreads) {
+  const uint32_t nvec = (1u << g.m) / V;
+  for (uint32_t i = tid; i < nvec; i += nthreads) {
+    const uint32_t local = i * V;
+    const uint64_t idx = local_to_index(g, roff, base, local);
+    *reinterpret_cast<cvec<T, V> *>(state + idx) = *reinterpret_cast<const cvec<T, V> *>(tile + local);
+  }
+}
+
+// ---- phase 2: one gate on the staged tile ---------------------------------------------------
+template <typename T, int K>
+TQB_HD void gate_dense(cplx<T> *tile, int m, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  constexpr int D = 1 << K;
+  uint32_t off[D];
+#pragma unroll
+  for (int s = 0; s < D; ++s) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) o |= (uint32_t)((s >> j) & 1) << g.bits[j];
+    off[s] = o;
+  }
+  const uint32_t ngroups = 1u << (m - K);
+  if (sizeof(cplx<T>) * D * D <= 128) {  // matrix small enough to live in registers
+    cplx<T> Mr[D * D];
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) Mr[i] = M[i];
+    for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
+      const uint32_t base = insert_zeros32(gi, g.sbits, K);
+      cplx<T> v[D];
+#pragma unroll
+      for (int s = 0; s < D; ++s) v[s] = tile[base + off[s]];
+#pragma unroll
+      for (int r = 0; r < D; ++r) {
+        cplx<T> acc{0, 0};
+#pragma unroll
+        for (int c = 0; c < D; ++c) cmac(acc, Mr[r * D + c], v[c]);
+        tile[base + off[r]] = acc;
+      }
+    }
+  } else {
+    for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
+      const uint32_t base = insert_zeros32(gi, g.sbits, K);
+      cplx<T> v[D];
+#pragma unroll
+      for (int s = 0; s < D; ++s) v[s] = tile[base + off[s]];
+#pragma unroll 2
+      for (int r = 0; r < D; ++r) {
+        cplx<T> acc{0, 0};
+#pragma unroll
+        for (int c = 0; c < D; ++c) cmac(acc, M[r * D + c], v[c]);
+        tile[base + off[r]] = acc;
+      }
+    }
+  }
+}
+
+template <typename T>
+TQB_HD void gate_pair(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, uint64_t gbase,
+                      const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  const uint32_t ngroups = 1u << (geo.m - g.k);
+  cplx<T> M0[4], M1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) M0[i] = M[i];
+  if (g.zmask) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) M1[i] = M[4 + i];
+  }
+  for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
+    const uint32_t base = insert_zeros32(gi, g.sbits, g.k);
+    const uint32_t ia = base + g.off_a, ib = base + g.off_b;
+    const cplx<T> a = tile[ia], b = tile[ib];
+    bool odd = false;
+    if (g.zmask) odd = popc64(local_to_index(geo, roff, gbase, base) & g.zmask) & 1;
+    cplx<T> ra{0, 0}, rb{0, 0};
+    if (odd) {
+      cmac(ra, M1[0], a); cmac(ra, M1[1], b); cmac(rb, M1[2], a); cmac(rb, M1[3], b);
+    } else {
+      cmac(ra, M0[0], a); cmac(ra, M0[1], b); cmac(rb, M0[2], a); cmac(rb, M0[3], b);
+    }
+    tile[ia] = ra;
+    tile[ib] = rb;
+  }
+}
+
+template <typename T>
+TQB_HD void gate_diag(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, uint64_t gbase,
+                      const tqb_gate &g, const cplx<T> *tab, int tid, int nthreads) {
+  const uint32_t nel = 1u << geo.m;
+  for (uint32_t e = tid; e < nel; e += nthreads) {
+    const uint64_t idx = local_to_index(geo, roff, gbase, e);
+    uint32_t t = 0;
+    for (int j = 0; j < g.k; ++j) t |= (uint32_t)((idx >> g.bits[j]) & 1ull) << j;
+    tile[e] = cmul(tile[e], tab[t]);
+  }
+}
+
+// gbase = global_base | tile base: the state index of tile element 0, high shard bits included.
+// MAXK bounds the dense gate size this instantiation can execute (2 = light, few registers;
+// 4 = heavy): the host picks the variant per pass.
+template <typename T, int MAXK>
+TQB_HD void tile_apply_gate(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, uint64_t gbase,
+                            const tqb_gate &g, const cplx<T> *mat, int tid, int nthreads) {
+  switch (g.kind) {
+    case TQB_GATE_DENSE:
+      switch (g.k) {
+        case 1: gate_dense<T, 1>(tile, geo.m, g, mat, tid, nthreads); break;
+        case 2: gate_dense<T, 2>(tile, geo.m, g, mat, tid, nthreads); break;
+        case 3: if (MAXK >= 3) gate_dense<T, 3>(tile, geo.m, g, mat, tid, nthreads); break;
+        case 4: if (MAXK >= 4) gate_dense<T, 4>(tile, geo.m, g, mat, tid, nthreads); break;
+        default: break;
+      }
+      break;
+    case TQB_GATE_DIAG: gate_diag<T>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
+    case TQB_GATE_PAIR: gate_pair<T>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
+    default: break;
+  }
+}
+
+}  // namespace tqb

@@ -1,0 +1,722 @@
+// tqb_reduce.cu -- read-only passes over the state: norms, <Z> expectations, matrix-free
+// Pauli sums, inner products, adjoint-gradient reductions, projection, and the blocked-CDF
+// sampler.  All sums are float64 and two-stage (per-CTA partials in the library workspace,
+// then one CTA per batch member adds them in a fixed order), so results are deterministic.
+//
+// Replaces (reference paths relative to src/tyxonq/):
+//   expect_z_statevector                    libs/quantum_library/kernels/statevector.py:62-68
+//   pauli_string_sum_dense + expectation    libs/quantum_library/kernels/pauli.py:74-87, dynamics.py:117-126
+//   apply_op (densified sparse H)           applications/chem/chem_libs/hamiltonians_chem_library/hamiltonian_builders.py:283-318
+//   _project_z                              devices/simulators/statevector/engine.py:1075-1087
+//   sampling (Generator.choice + bincount)  devices/simulators/statevector/engine.py:377-418
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "tqb_core.cuh"
+#include "tqb_host.h"
+
+namespace tqb {
+
+constexpr int RT = 256;         // threads per reduction CTA
+constexpr int MAX_ACC = 40;     // values reduced per CTA at most (n bits or masks per launch)
+constexpr int MASKS_PER_LAUNCH = 32;
+
+// ---- block reduction of NV doubles per thread -> sm_out[0..NV) valid in thread 0 ----------
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double *sm /* [RT/32][NV] */, double *out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[warp * NV + i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int w = 0; w < RT / 32; ++w) s += sm[w * NV + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// grid = (nbx, batch); block x handles the contiguous segment [x*seg, (x+1)*seg) of member y.
+struct Seg {
+  int n;
+  int seg_bits;  // log2(segment length)
+};
+
+template <typename T>
+__device__ __forceinline__ double prob_of(const cplx<T> a) {
+  const double re = (double)a.x, im = (double)a.y;
+  return __dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im));
+}
+
+// partial[(y*nbx + x)*nv + j]
+template <typename T>
+__global__ void __launch_bounds__(RT) norm2_kernel(const cplx<T> *__restrict__ state, Seg sg, double *partial) {
+  __shared__ double sm[RT / 32];
+  const cplx<T> *s = state + ((size_t)blockIdx.y << sg.n) + ((size_t)blockIdx.x << sg.seg_bits);
+  const size_t len = (size_t)1 << sg.seg_bits;
+  double v[1] = {0.0};
+  for (size_t i = threadIdx.x; i < len; i += RT) v[0] += prob_of(s[i]);
+  block_reduce<1>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x));
+}
+
+// <Z> on every local bit.  Elements visited by one thread are i = it*RT + tid, so bits below
+// log2(RT) are fixed per thread, bits in [8, seg_bits) vary with `it`, bits >= seg_bits are
+// fixed per CTA.
+template <typename T>
+__global__ void __launch_bounds__(RT) expect_z_bits_kernel(const cplx<T> *__restrict__ state, Seg sg, double *partial) {
+  __shared__ double sm[(RT / 32) * MAX_ACC];
+  const cplx<T> *s = state + ((size_t)blockIdx.y << sg.n) + ((size_t)blockIdx.x << sg.seg_bits);
+  const size_t len = (size_t)1 << sg.seg_bits;
+  constexpr int LT = 8;  // log2(RT)
+  constexpr int MID = 16;
+  double tot = 0.0;
+  double ones[MID];  // probability mass with bit (LT + j) set
+#pragma unroll
+  for (int j = 0; j < MID; ++j) ones[j] = 0.0;
+  const int nmid = sg.seg_bits > LT ? sg.seg_bits - LT : 0;
+  for (size_t it = 0; it * RT + threadIdx.x < len; ++it) {
+    const double p = prob_of(s[it * RT + threadIdx.x]);
+    tot += p;
+#pragma unroll
+    for (int j = 0; j < MID; ++j)
+      if (j < nmid && ((it >> j) & 1)) ones[j] += p;
+  }
+  // combine into per-bit contributions, MAX_ACC at most
+  double v[MAX_ACC];
+#pragma unroll
+  for (int b = 0; b < MAX_ACC; ++b) {
+    double c = 0.0;
+    if (b < sg.n) {
+      if (b < LT && b < sg.seg_bits) c = ((threadIdx.x >> b) & 1) ? -tot : tot;
+      else if (b < sg.seg_bits) c = tot - 2.0 * ones[b - LT > 0 ? (b - LT < MID ? b - LT : MID - 1) : 0];
+      else c = ((blockIdx.x >> (b - sg.seg_bits)) & 1) ? -tot : tot;
+    }
+    v[b] = c;
+  }
+  block_reduce<MAX_ACC>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MAX_ACC);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RT) expect_zmasks_kernel(const cplx<T> *__restrict__ state, Seg sg, uint64_t global_base,
+                                                           const uint64_t *__restrict__ masks, int n_masks, double *partial) {
+  __shared__ double sm[(RT / 32) * MASKS_PER_LAUNCH];
+  __shared__ uint64_t smask[MASKS_PER_LAUNCH];
+  if (threadIdx.x < MASKS_PER_LAUNCH) smask[threadIdx.x] = threadIdx.x < n_masks ? masks[threadIdx.x] : 0ull;
+  __syncthreads();
+  const size_t off = (size_t)blockIdx.x << sg.seg_bits;
+  const cplx<T> *s = state + ((size_t)blockIdx.y << sg.n) + off;
+  const size_t len = (size_t)1 << sg.seg_bits;
+  double v[MASKS_PER_LAUNCH];
+#pragma unroll
+  for (int t = 0; t < MASKS_PER_LAUNCH; ++t) v[t] = 0.0;
+  for (size_t i = threadIdx.x; i < len; i += RT) {
+    const double p = prob_of(s[i]);
+    const uint64_t idx = global_base | (off + i);
+#pragma unroll
+    for (int t = 0; t < MASKS_PER_LAUNCH; ++t)
+      if (t < n_masks) v[t] += (__popcll(idx & smask[t]) & 1) ? -p : p;
+  }
+  block_reduce<MASKS_PER_LAUNCH>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MASKS_PER_LAUNCH);
+}
+
+// out[y*out_stride + j] = sum_x partial[(y*nbx + x)*nv + j], fixed order.  grid = batch.
+__global__ void finish_kernel(const double *partial, int nbx, int nv, int n_out, double *out, int out_stride) {
+  for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
+    double s = 0.0;
+    for (int x = 0; x < nbx; ++x) s += partial[((size_t)blockIdx.x * nbx + x) * nv + j];
+    out[(size_t)blockIdx.x * out_stride + j] = s;
+  }
+}
+
+// ---- Pauli sums -------------------------------------------------------------------------
+// sign-sum of a group's terms at index j: sum_t coef_t (-1)^popc(j & z_t)
+__device__ __forceinline__ void group_phase(const uint64_t *__restrict__ term_z, const double *__restrict__ term_coef,
+                                            int t0, int t1, uint64_t j, double &re, double &im) {
+  re = 0.0; im = 0.0;
+  for (int t = t0; t < t1; ++t) {
+    const double sgn = (__popcll(j & term_z[t]) & 1) ? -1.0 : 1.0;
+    re += sgn * term_coef[2 * t];
+    im += sgn * term_coef[2 * t + 1];
+  }
+}
+
+// <psi|H|psi> = sum_j sum_g conj(psi_{j^x_g}) * phase_g(j) * psi_j     (P|j> = phase(j)|j^x>)
+template <typename T>
+__global__ void __launch_bounds__(RT) expect_pauli_kernel(const cplx<T> *__restrict__ state, Seg sg, uint64_t global_base,
+                                                          const uint64_t *__restrict__ group_x, const int *__restrict__ group_ptr,
+                                                          int n_groups, const uint64_t *__restrict__ term_z,
+                                                          const double *__restrict__ term_coef, double *partial) {
+  __shared__ double sm[(RT / 32) * 2];
+  const cplx<T> *sb = state + ((size_t)blockIdx.y << sg.n);
+  const size_t off = (size_t)blockIdx.x << sg.seg_bits;
+  const size_t len = (size_t)1 << sg.seg_bits;
+  double v[2] = {0.0, 0.0};
+  for (size_t i = threadIdx.x; i < len; i += RT) {
+    const uint64_t j = off + i;
+    const cplx<T> a = sb[j];
+    const double ar = a.x, ai = a.y;
+    double hr = 0.0, hi = 0.0;  // sum_g conj(psi_{j^x}) * phase_g(j)
+    for (int g = 0; g < n_groups; ++g) {
+      double pr, pi;
+      group_phase(term_z, term_coef, group_ptr[g], group_ptr[g + 1], global_base | j, pr, pi);
+      const cplx<T> b = sb[j ^ group_x[g]];
+      const double br = b.x, bi = -(double)b.y;
+      hr += br * pr - bi * pi;
+      hi += br * pi + bi * pr;
+    }
+    v[0] += hr * ar - hi * ai;
+    v[1] += hr * ai + hi * ar;
+  }
+  block_reduce<2>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2);
+}
+
+// out_j = sum_g phase_g(j ^ x_g) * psi_{j ^ x_g}
+template <typename T>
+__global__ void __launch_bounds__(RT) apply_pauli_kernel(const cplx<T> *__restrict__ state, cplx<T> *__restrict__ out, int n,
+                                                         uint64_t global_base, const uint64_t *__restrict__ group_x,
+                                                         const int *__restrict__ group_ptr, int n_groups,
+                                                         const uint64_t *__restrict__ term_z,
+                                                         const double *__restrict__ term_coef) {
+  const cplx<T> *sb = state + ((size_t)blockIdx.y << n);
+  cplx<T> *ob = out + ((size_t)blockIdx.y << n);
+  const size_t dim = (size_t)1 << n;
+  for (size_t j = (size_t)blockIdx.x * RT + threadIdx.x; j < dim; j += (size_t)gridDim.x * RT) {
+    double hr = 0.0, hi = 0.0;
+    for (int g = 0; g < n_groups; ++g) {
+      const uint64_t src = j ^ group_x[g];
+      double pr, pi;
+      group_phase(term_z, term_coef, group_ptr[g], group_ptr[g + 1], global_base | src, pr, pi);
+      const cplx<T> b = sb[src];
+      const double br = b.x, bi = b.y;
+      hr += br * pr - bi * pi;
+      hi += br * pi + bi * pr;
+    }
+    ob[j] = cplx<T>{(T)hr, (T)hi};
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RT) inner_kernel(const cplx<T> *__restrict__ a, const cplx<T> *__restrict__ b, Seg sg,
+                                                   double *partial) {
+  __shared__ double sm[(RT / 32) * 2];
+  const size_t base = ((size_t)blockIdx.y << sg.n) + ((size_t)blockIdx.x << sg.seg_bits);
+  const size_t len = (size_t)1 << sg.seg_bits;
+  double v[2] = {0.0, 0.0};
+  for (size_t i = threadIdx.x; i < len; i += RT) {
+    const cplx<T> x = a[base + i], y = b[base + i];
+    const double xr = x.x, xi = x.y, yr = y.x, yi = y.y;
+    v[0] += xr * yr + xi * yi;
+    v[1] += xr * yi - xi * yr;
+  }
+  block_reduce<2>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2);
+}
+
+// ---- adjoint-gradient reductions ------------------------------------------------------------
+struct PairGen {
+  int n, k;
+  int8_t sbits[TQB_MAX_GATE_BITS];
+  uint64_t off_a, off_b, zmask;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(RT) grad_pair_kernel(const cplx<T> *__restrict__ bra, const cplx<T> *__restrict__ ket,
+                                                       PairGen pg, double scale, double *out) {
+  __shared__ double sm[RT / 32];
+  const uint64_t ngroups = 1ull << (pg.n - pg.k);
+  double v[1] = {0.0};
+  for (uint64_t g = (uint64_t)blockIdx.x * RT + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * RT) {
+    const uint64_t base = insert_zeros64(g, pg.sbits, pg.k);
+    const cplx<T> ba = bra[base + pg.off_a], bb = bra[base + pg.off_b];
+    const cplx<T> ka = ket[base + pg.off_a], kb = ket[base + pg.off_b];
+    // Re( conj(bra_A) ket_B - conj(bra_B) ket_A )
+    double r = ((double)ba.x * kb.x + (double)ba.y * kb.y) - ((double)bb.x * ka.x + (double)bb.y * ka.y);
+    if (__popcll(base & pg.zmask) & 1) r = -r;
+    v[0] += r;
+  }
+  double tot[1];
+  block_reduce<1>(v, sm, tot);
+  if (threadIdx.x == 0) atomicAdd(out, scale * tot[0]);
+}
+
+struct DenseGen {
+  int n, k;
+  int8_t bits[2], sbits[2];
+  double gen[32];  // 2^k x 2^k complex, row-major, (re, im)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(RT) grad_dense_kernel(const cplx<T> *__restrict__ bra, const cplx<T> *__restrict__ ket,
+                                                        DenseGen dg, double scale, double *out) {
+  __shared__ double sm[RT / 32];
+  const int D = 1 << dg.k;
+  const uint64_t ngroups = 1ull << (dg.n - dg.k);
+  double v[1] = {0.0};
+  for (uint64_t g = (uint64_t)blockIdx.x * RT + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * RT) {
+    const uint64_t base = insert_zeros64(g, dg.sbits, dg.k);
+    double kr[4], ki[4];
+    uint64_t off[4];
+    for (int s = 0; s < D; ++s) {
+      uint64_t o = 0;
+      for (int j = 0; j < dg.k; ++j) o |= (uint64_t)((s >> j) & 1) << dg.bits[j];
+      off[s] = o;
+      const cplx<T> kk = ket[base + o];
+      kr[s] = kk.x; ki[s] = kk.y;
+    }
+    double acc = 0.0;
+    for (int r = 0; r < D; ++r) {
+      double dr = 0.0, di = 0.0;  // (D ket)_r
+      for (int c = 0; c < D; ++c) {
+        const double gr = dg.gen[2 * (r * D + c)], gi = dg.gen[2 * (r * D + c) + 1];
+        dr += gr * kr[c] - gi * ki[c];
+        di += gr * ki[c] + gi * kr[c];
+      }
+      const cplx<T> bb = bra[base + off[r]];
+      acc += (double)bb.x * dr + (double)bb.y * di;  // Re(conj(bra) * (D ket))
+    }
+    v[0] += acc;
+  }
+  double tot[1];
+  block_reduce<1>(v, sm, tot);
+  if (threadIdx.x == 0) atomicAdd(out, scale * tot[0]);
+}
+
+// ---- projection / scaling / probabilities ----------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(RT) project_kernel(cplx<T> *state, Seg sg, int bit, int keep, double *partial) {
+  __shared__ double sm[RT / 32];
+  const size_t off = (size_t)blockIdx.x << sg.seg_bits;
+  cplx<T> *s = state + ((size_t)blockIdx.y << sg.n) + off;
+  const size_t len = (size_t)1 << sg.seg_bits;
+  double v[1] = {0.0};
+  for (size_t i = threadIdx.x; i < len; i += RT) {
+    const int b = (int)(((off + i) >> bit) & 1);
+    if (b == keep) v[0] += prob_of(s[i]);
+    else s[i] = cplx<T>{0, 0};
+  }
+  block_reduce<1>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x));
+}
+
+// state_b *= 1/sqrt(norm2[b]) when norm2[b] > 0
+template <typename T>
+__global__ void __launch_bounds__(RT) renorm_kernel(cplx<T> *state, int n, const double *norm2) {
+  const double nn = norm2[blockIdx.y];
+  if (!(nn > 0.0)) return;
+  const double f = 1.0 / sqrt(nn);
+  cplx<T> *s = state + ((size_t)blockIdx.y << n);
+  const size_t dim = (size_t)1 << n;
+  for (size_t i = (size_t)blockIdx.x * RT + threadIdx.x; i < dim; i += (size_t)gridDim.x * RT) {
+    cplx<T> a = s[i];
+    a.x = (T)((double)a.x * f);
+    a.y = (T)((double)a.y * f);
+    s[i] = a;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RT) scale_kernel(cplx<T> *state, size_t total, double f) {
+  for (size_t i = (size_t)blockIdx.x * RT + threadIdx.x; i < total; i += (size_t)gridDim.x * RT) {
+    cplx<T> a = state[i];
+    a.x = (T)((double)a.x * f);
+    a.y = (T)((double)a.y * f);
+    state[i] = a;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RT) probs_kernel(const cplx<T> *__restrict__ state, size_t total, double *out) {
+  for (size_t i = (size_t)blockIdx.x * RT + threadIdx.x; i < total; i += (size_t)gridDim.x * RT) out[i] = prob_of(state[i]);
+}
+
+// ---- sampler ---------------------------------------------------------------------------------
+// Chunk totals in the documented order: strictly sequential float64 sum of p_i over the chunk.
+// One warp owns 32 consecutive chunks; global loads are coalesced (32 consecutive amplitudes of
+// one chunk per instruction) and transposed through shared memory so that lane l adds the
+// elements of chunk l in index order.
+constexpr int CW = 4;  // warps per CTA
+template <typename T>
+__global__ void __launch_bounds__(CW * 32) chunk_totals_kernel(const cplx<T> *__restrict__ state, int n, int chunk_bits,
+                                                               long long n_chunks_total, double *totals) {
+  __shared__ double buf[CW][32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long group = (long long)blockIdx.x * CW + w;  // 32 chunks per group
+  const long long c0 = group * 32;
+  if (c0 >= n_chunks_total) return;
+  const size_t clen = (size_t)1 << chunk_bits;
+  double acc = 0.0;
+  for (size_t s0 = 0; s0 < clen; s0 += 32) {
+    const int width = (clen - s0) < 32 ? (int)(clen - s0) : 32;
+    for (int c = 0; c < 32; ++c) {
+      double p = 0.0;
+      if (c0 + c < n_chunks_total && lane < width) p = prob_of(state[((size_t)(c0 + c) << chunk_bits) + s0 + lane]);
+      buf[w][c][lane] = p;
+    }
+    __syncwarp();
+    for (int e = 0; e < width; ++e) acc = __dadd_rn(acc, buf[w][lane][e]);
+    __syncwarp();
+  }
+  if (c0 + lane < n_chunks_total) totals[c0 + lane] = acc;
+}
+
+// prefix[b*(nc+1) + c] = sum of totals of chunks < c (sequential), one CTA per batch member.
+__global__ void __launch_bounds__(RT) chunk_prefix_kernel(const double *totals, long long nc, double *prefix) {
+  __shared__ double sm[2048];
+  const double *t = totals + (size_t)blockIdx.x * nc;
+  double *p = prefix + (size_t)blockIdx.x * (nc + 1);
+  __shared__ double carry;
+  if (threadIdx.x == 0) { carry = 0.0; p[0] = 0.0; }
+  __syncthreads();
+  for (long long c0 = 0; c0 < nc; c0 += 2048) {
+    const int cnt = (nc - c0) < 2048 ? (int)(nc - c0) : 2048;
+    for (int i = threadIdx.x; i < cnt; i += RT) sm[i] = t[c0 + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double run = carry;
+      for (int i = 0; i < cnt; ++i) { run = __dadd_rn(run, sm[i]); sm[i] = run; }
+      carry = run;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += RT) p[c0 + i + 1] = sm[i];
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) sample_kernel(const cplx<T> *__restrict__ state, int n, int chunk_bits, long long nc,
+                                                     const double *__restrict__ prefix, const double *__restrict__ uniforms,
+                                                     long long shots, long long *idx_out) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= shots) return;
+  const long long b = blockIdx.y;
+  const double *p = prefix + (size_t)b * (nc + 1);
+  const double total = p[nc];
+  const double u = uniforms[(size_t)b * shots + s];
+  // c = #{ c : cdf_end(c) / total <= u },  cdf_end(c) = p[c+1]
+  long long lo = 0, hi = nc;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (__ddiv_rn(p[mid + 1], total) <= u) lo = mid + 1; else hi = mid;
+  }
+  long long idx;
+  if (lo >= nc) {
+    idx = (long long)1 << n;
+  } else {
+    const size_t clen = (size_t)1 << chunk_bits;
+    const cplx<T> *sc = state + ((size_t)b << n) + ((size_t)lo << chunk_bits);
+    const double pre = p[lo];
+    double run = 0.0;
+    size_t cnt = 0;
+    for (; cnt < clen; ++cnt) {
+      run = __dadd_rn(run, prob_of(sc[cnt]));
+      if (!(__ddiv_rn(__dadd_rn(pre, run), total) <= u)) break;
+    }
+    idx = (lo << chunk_bits) + (long long)cnt;
+  }
+  idx_out[(size_t)b * shots + s] = idx;
+}
+
+// ---- host helpers ----------------------------------------------------------------------------
+static int pick_seg(const Workspace &ws, int n, int64_t batch, int nv, int max_seg_bits, Seg *sg, int *nbx) {
+  // power-of-two number of segments per batch member, ~8 CTAs per SM overall
+  long long want = ((long long)ws.sm_count * 8 + batch - 1) / batch;
+  int lb = 0;
+  while ((1ll << lb) < want) ++lb;
+  int min_seg = n < 10 ? n : 10;  // at least 1024 amplitudes per CTA (or the whole state)
+  if (lb > n - min_seg) lb = n - min_seg;
+  if (lb < 0) lb = 0;
+  if (n - lb > max_seg_bits) lb = n - max_seg_bits;
+  if ((size_t)batch * ((size_t)1 << lb) * nv * sizeof(double) > ws.bytes / 2) return fail("reduction workspace too small");
+  if (batch > 65535) return fail("batch > 65535 not supported by the reduction kernels");
+  sg->n = n;
+  sg->seg_bits = n - lb;
+  *nbx = 1 << lb;
+  return 0;
+}
+
+template <typename F64, typename F32>
+static int by_dtype(int dtype, F64 f64, F32 f32) {
+  if (dtype == TQB_C128) { f64(); return 0; }
+  if (dtype == TQB_C64) { f32(); return 0; }
+  return fail("bad dtype");
+}
+
+}  // namespace tqb
+
+using namespace tqb;
+
+#define CD(p) reinterpret_cast<const cplx<double> *>(p)
+#define CF(p) reinterpret_cast<const cplx<float> *>(p)
+#define MD(p) reinterpret_cast<cplx<double> *>(p)
+#define MF(p) reinterpret_cast<cplx<float> *>(p)
+
+extern "C" {
+
+int tqb_norm2(const void *state, int n, int64_t batch, int dtype, double *out_dev, void *stream) {
+  TQB_REQUIRE(state && out_dev && n >= 0 && n < 48 && batch >= 1, "tqb_norm2: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  Seg sg; int nbx;
+  if (pick_seg(*ws, n, batch, 1, 40, &sg, &nbx)) return -1;
+  double *partial = (double *)ws->ptr;
+  dim3 grid(nbx, (unsigned)batch);
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { norm2_kernel<double><<<grid, RT, 0, st>>>(CD(state), sg, partial); },
+               [&] { norm2_kernel<float><<<grid, RT, 0, st>>>(CF(state), sg, partial); })) return -1;
+  TQB_CHECK_LAUNCH("norm2_kernel");
+  finish_kernel<<<(unsigned)batch, 32, 0, st>>>(partial, nbx, 1, 1, out_dev, 1);
+  TQB_CHECK_LAUNCH("finish_kernel");
+  return 0;
+}
+
+int tqb_expect_z_bits(const void *state, int n, int64_t batch, int dtype, double *out_dev, void *stream) {
+  TQB_REQUIRE(state && out_dev && n >= 1 && n <= MAX_ACC && batch >= 1, "tqb_expect_z_bits: bad arguments (1 <= n <= 40)");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  Seg sg; int nbx;
+  if (pick_seg(*ws, n, batch, MAX_ACC, 24, &sg, &nbx)) return -1;
+  double *partial = (double *)ws->ptr;
+  dim3 grid(nbx, (unsigned)batch);
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { expect_z_bits_kernel<double><<<grid, RT, 0, st>>>(CD(state), sg, partial); },
+               [&] { expect_z_bits_kernel<float><<<grid, RT, 0, st>>>(CF(state), sg, partial); })) return -1;
+  TQB_CHECK_LAUNCH("expect_z_bits_kernel");
+  finish_kernel<<<(unsigned)batch, 64, 0, st>>>(partial, nbx, MAX_ACC, n, out_dev, n);
+  TQB_CHECK_LAUNCH("finish_kernel");
+  return 0;
+}
+
+int tqb_expect_zmasks(const void *state, int n, int64_t batch, int dtype, uint64_t global_base, const uint64_t *masks_dev,
+                      int n_masks, double *out_dev, void *stream) {
+  TQB_REQUIRE(state && out_dev && masks_dev && n >= 0 && n < 48 && batch >= 1 && n_masks >= 1, "tqb_expect_zmasks: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  Seg sg; int nbx;
+  if (pick_seg(*ws, n, batch, MASKS_PER_LAUNCH, 40, &sg, &nbx)) return -1;
+  double *partial = (double *)ws->ptr;
+  dim3 grid(nbx, (unsigned)batch);
+  cudaStream_t st = as_stream(stream);
+  for (int m0 = 0; m0 < n_masks; m0 += MASKS_PER_LAUNCH) {
+    const int cnt = n_masks - m0 < MASKS_PER_LAUNCH ? n_masks - m0 : MASKS_PER_LAUNCH;
+    if (by_dtype(dtype,
+                 [&] { expect_zmasks_kernel<double><<<grid, RT, 0, st>>>(CD(state), sg, global_base, masks_dev + m0, cnt, partial); },
+                 [&] { expect_zmasks_kernel<float><<<grid, RT, 0, st>>>(CF(state), sg, global_base, masks_dev + m0, cnt, partial); }))
+      return -1;
+    TQB_CHECK_LAUNCH("expect_zmasks_kernel");
+    finish_kernel<<<(unsigned)batch, 32, 0, st>>>(partial, nbx, MASKS_PER_LAUNCH, cnt, out_dev + m0, n_masks);
+    TQB_CHECK_LAUNCH("finish_kernel");
+  }
+  return 0;
+}
+
+int tqb_expect_pauli_sum(const void *state, int n, int64_t batch, int dtype, uint64_t global_base, const uint64_t *group_x,
+                         const int32_t *group_ptr, int n_groups, const uint64_t *term_z, const double *term_coef,
+                         double *out_dev, void *stream) {
+  TQB_REQUIRE(state && out_dev && group_x && group_ptr && term_z && term_coef && n >= 0 && n < 48 && batch >= 1 && n_groups >= 0,
+              "tqb_expect_pauli_sum: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  Seg sg; int nbx;
+  if (pick_seg(*ws, n, batch, 2, 40, &sg, &nbx)) return -1;
+  double *partial = (double *)ws->ptr;
+  dim3 grid(nbx, (unsigned)batch);
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype,
+               [&] { expect_pauli_kernel<double><<<grid, RT, 0, st>>>(CD(state), sg, global_base, group_x, group_ptr, n_groups, term_z, term_coef, partial); },
+               [&] { expect_pauli_kernel<float><<<grid, RT, 0, st>>>(CF(state), sg, global_base, group_x, group_ptr, n_groups, term_z, term_coef, partial); }))
+    return -1;
+  TQB_CHECK_LAUNCH("expect_pauli_kernel");
+  finish_kernel<<<(unsigned)batch, 32, 0, st>>>(partial, nbx, 2, 2, out_dev, 2);
+  TQB_CHECK_LAUNCH("finish_kernel");
+  return 0;
+}
+
+int tqb_apply_pauli_sum(const void *state, void *out, int n, int64_t batch, int dtype, uint64_t global_base,
+                        const uint64_t *group_x, const int32_t *group_ptr, int n_groups, const uint64_t *term_z,
+                        const double *term_coef, void *stream) {
+  TQB_REQUIRE(state && out && state != out && group_x && group_ptr && term_z && term_coef && n >= 0 && n < 48 && batch >= 1,
+              "tqb_apply_pauli_sum: bad arguments (out must not alias state)");
+  TQB_REQUIRE(batch <= 65535, "tqb_apply_pauli_sum: batch > 65535");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  const size_t dim = (size_t)1 << n;
+  size_t bx = (dim + RT - 1) / RT;
+  const size_t cap = (size_t)ws->sm_count * 16;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)batch);
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype,
+               [&] { apply_pauli_kernel<double><<<grid, RT, 0, st>>>(CD(state), MD(out), n, global_base, group_x, group_ptr, n_groups, term_z, term_coef); },
+               [&] { apply_pauli_kernel<float><<<grid, RT, 0, st>>>(CF(state), MF(out), n, global_base, group_x, group_ptr, n_groups, term_z, term_coef); }))
+    return -1;
+  TQB_CHECK_LAUNCH("apply_pauli_kernel");
+  return 0;
+}
+
+int tqb_inner(const void *a, const void *b, int n, int64_t batch, int dtype, double *out_dev, void *stream) {
+  TQB_REQUIRE(a && b && out_dev && n >= 0 && n < 48 && batch >= 1, "tqb_inner: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  Seg sg; int nbx;
+  if (pick_seg(*ws, n, batch, 2, 40, &sg, &nbx)) return -1;
+  double *partial = (double *)ws->ptr;
+  dim3 grid(nbx, (unsigned)batch);
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { inner_kernel<double><<<grid, RT, 0, st>>>(CD(a), CD(b), sg, partial); },
+               [&] { inner_kernel<float><<<grid, RT, 0, st>>>(CF(a), CF(b), sg, partial); })) return -1;
+  TQB_CHECK_LAUNCH("inner_kernel");
+  finish_kernel<<<(unsigned)batch, 32, 0, st>>>(partial, nbx, 2, 2, out_dev, 2);
+  TQB_CHECK_LAUNCH("finish_kernel");
+  return 0;
+}
+
+int tqb_grad_pair(const void *bra, const void *ket, int n, int dtype, const tqb_gate *gate_host, double scale,
+                  double *out_dev, int slot, void *stream) {
+  TQB_REQUIRE(bra && ket && gate_host && out_dev && n >= 1 && n < 48 && slot >= 0, "tqb_grad_pair: bad arguments");
+  TQB_REQUIRE(gate_host->kind == TQB_GATE_PAIR && gate_host->k >= 1 && gate_host->k <= TQB_MAX_GATE_BITS && gate_host->k <= n,
+              "tqb_grad_pair: gate must be a PAIR gate with m = n");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  PairGen pg;
+  pg.n = n; pg.k = gate_host->k; pg.off_a = gate_host->off_a; pg.off_b = gate_host->off_b; pg.zmask = gate_host->zmask;
+  for (int i = 0; i < TQB_MAX_GATE_BITS; ++i) pg.sbits[i] = gate_host->sbits[i];
+  const uint64_t ngroups = 1ull << (n - pg.k);
+  uint64_t bx = (ngroups + RT - 1) / RT;
+  const uint64_t cap = (uint64_t)ws->sm_count * 8;
+  if (bx > cap) bx = cap;
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { grad_pair_kernel<double><<<(unsigned)bx, RT, 0, st>>>(CD(bra), CD(ket), pg, scale, out_dev + slot); },
+               [&] { grad_pair_kernel<float><<<(unsigned)bx, RT, 0, st>>>(CF(bra), CF(ket), pg, scale, out_dev + slot); })) return -1;
+  TQB_CHECK_LAUNCH("grad_pair_kernel");
+  return 0;
+}
+
+int tqb_grad_dense(const void *bra, const void *ket, int n, int dtype, int k, const int *bits, const double *gen_host,
+                   double scale, double *out_dev, int slot, void *stream) {
+  TQB_REQUIRE(bra && ket && bits && gen_host && out_dev && n >= 1 && n < 48 && k >= 1 && k <= 2 && k <= n && slot >= 0,
+              "tqb_grad_dense: bad arguments (k <= 2)");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  DenseGen dg;
+  dg.n = n; dg.k = k;
+  for (int j = 0; j < 2; ++j) dg.bits[j] = dg.sbits[j] = 0;
+  for (int j = 0; j < k; ++j) {
+    TQB_REQUIRE(bits[j] >= 0 && bits[j] < n, "tqb_grad_dense: bit out of range");
+    dg.bits[j] = (int8_t)bits[j];
+    dg.sbits[j] = (int8_t)bits[j];
+  }
+  if (k == 2) {
+    TQB_REQUIRE(bits[0] != bits[1], "tqb_grad_dense: repeated bit");
+    if (dg.sbits[0] > dg.sbits[1]) { int8_t t = dg.sbits[0]; dg.sbits[0] = dg.sbits[1]; dg.sbits[1] = t; }
+  }
+  const int D = 1 << k;
+  for (int i = 0; i < 32; ++i) dg.gen[i] = i < 2 * D * D ? gen_host[i] : 0.0;
+  const uint64_t ngroups = 1ull << (n - k);
+  uint64_t bx = (ngroups + RT - 1) / RT;
+  const uint64_t cap = (uint64_t)ws->sm_count * 8;
+  if (bx > cap) bx = cap;
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { grad_dense_kernel<double><<<(unsigned)bx, RT, 0, st>>>(CD(bra), CD(ket), dg, scale, out_dev + slot); },
+               [&] { grad_dense_kernel<float><<<(unsigned)bx, RT, 0, st>>>(CF(bra), CF(ket), dg, scale, out_dev + slot); })) return -1;
+  TQB_CHECK_LAUNCH("grad_dense_kernel");
+  return 0;
+}
+
+int tqb_project_z(void *state, int n, int64_t batch, int dtype, int bit, int keep, void *stream) {
+  TQB_REQUIRE(state && n >= 1 && n < 48 && batch >= 1 && bit >= 0 && bit < n, "tqb_project_z: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  Seg sg; int nbx;
+  if (pick_seg(*ws, n, batch, 1, 40, &sg, &nbx)) return -1;
+  double *partial = (double *)ws->ptr;
+  double *norms = (double *)((char *)ws->ptr + ws->bytes / 2);  // batch doubles
+  dim3 grid(nbx, (unsigned)batch);
+  cudaStream_t st = as_stream(stream);
+  const int kp = keep ? 1 : 0;
+  if (by_dtype(dtype, [&] { project_kernel<double><<<grid, RT, 0, st>>>(MD(state), sg, bit, kp, partial); },
+               [&] { project_kernel<float><<<grid, RT, 0, st>>>(MF(state), sg, bit, kp, partial); })) return -1;
+  TQB_CHECK_LAUNCH("project_kernel");
+  finish_kernel<<<(unsigned)batch, 32, 0, st>>>(partial, nbx, 1, 1, norms, 1);
+  TQB_CHECK_LAUNCH("finish_kernel");
+  const size_t dim = (size_t)1 << n;
+  size_t bx = (dim + RT - 1) / RT;
+  const size_t cap = (size_t)ws->sm_count * 16;
+  if (bx > cap) bx = cap;
+  dim3 g2((unsigned)bx, (unsigned)batch);
+  if (by_dtype(dtype, [&] { renorm_kernel<double><<<g2, RT, 0, st>>>(MD(state), n, norms); },
+               [&] { renorm_kernel<float><<<g2, RT, 0, st>>>(MF(state), n, norms); })) return -1;
+  TQB_CHECK_LAUNCH("renorm_kernel");
+  return 0;
+}
+
+int tqb_scale(void *state, int n, int64_t batch, int dtype, double factor, void *stream) {
+  TQB_REQUIRE(state && n >= 0 && n < 48 && batch >= 1, "tqb_scale: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  const size_t total = (size_t)batch << n;
+  size_t bx = (total + RT - 1) / RT;
+  const size_t cap = (size_t)ws->sm_count * 16;
+  if (bx > cap) bx = cap;
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { scale_kernel<double><<<(unsigned)bx, RT, 0, st>>>(MD(state), total, factor); },
+               [&] { scale_kernel<float><<<(unsigned)bx, RT, 0, st>>>(MF(state), total, factor); })) return -1;
+  TQB_CHECK_LAUNCH("scale_kernel");
+  return 0;
+}
+
+int tqb_probabilities(const void *state, int n, int64_t batch, int dtype, double *out_dev, void *stream) {
+  TQB_REQUIRE(state && out_dev && n >= 0 && n < 48 && batch >= 1, "tqb_probabilities: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  const size_t total = (size_t)batch << n;
+  size_t bx = (total + RT - 1) / RT;
+  const size_t cap = (size_t)ws->sm_count * 16;
+  if (bx > cap) bx = cap;
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { probs_kernel<double><<<(unsigned)bx, RT, 0, st>>>(CD(state), total, out_dev); },
+               [&] { probs_kernel<float><<<(unsigned)bx, RT, 0, st>>>(CF(state), total, out_dev); })) return -1;
+  TQB_CHECK_LAUNCH("probs_kernel");
+  return 0;
+}
+
+int tqb_cdf_chunks(const void *state, int n, int64_t batch, int dtype, double *chunk_prefix_dev, void *stream) {
+  TQB_REQUIRE(state && chunk_prefix_dev && n >= 0 && n < 48 && batch >= 1, "tqb_cdf_chunks: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  const int chunk_bits = n < 12 ? n : 12;  // TQB_SCAN_BLOCK = 4096
+  const long long nc = 1ll << (n - chunk_bits);
+  const long long nct = nc * batch;
+  TQB_REQUIRE((size_t)nct * sizeof(double) <= ws->bytes, "tqb_cdf_chunks: workspace too small for the chunk totals");
+  double *totals = (double *)ws->ptr;
+  const long long groups = (nct + 31) / 32;
+  const long long blocks = (groups + CW - 1) / CW;
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { chunk_totals_kernel<double><<<(unsigned)blocks, CW * 32, 0, st>>>(CD(state), n, chunk_bits, nct, totals); },
+               [&] { chunk_totals_kernel<float><<<(unsigned)blocks, CW * 32, 0, st>>>(CF(state), n, chunk_bits, nct, totals); })) return -1;
+  TQB_CHECK_LAUNCH("chunk_totals_kernel");
+  chunk_prefix_kernel<<<(unsigned)batch, RT, 0, st>>>(totals, nc, chunk_prefix_dev);
+  TQB_CHECK_LAUNCH("chunk_prefix_kernel");
+  return 0;
+}
+
+int tqb_sample(const void *state, int n, int64_t batch, int dtype, const double *chunk_prefix_dev, const double *uniforms_dev,
+               int64_t shots, int64_t *idx_dev, void *stream) {
+  TQB_REQUIRE(state && chunk_prefix_dev && uniforms_dev && idx_dev && n >= 0 && n < 48 && batch >= 1 && batch <= 65535 && shots >= 1,
+              "tqb_sample: bad arguments");
+  const int chunk_bits = n < 12 ? n : 12;
+  const long long nc = 1ll << (n - chunk_bits);
+  dim3 grid((unsigned)((shots + 127) / 128), (unsigned)batch);
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype,
+               [&] { sample_kernel<double><<<grid, 128, 0, st>>>(CD(state), n, chunk_bits, nc, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
+               [&] { sample_kernel<float><<<grid, 128, 0, st>>>(CF(state), n, chunk_bits, nc, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
+    return -1;
+  TQB_CHECK_LAUNCH("sample_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+"""Host-side gate definitions: the parity contract of the reference's gate constructors.
+
+Every matrix here equals the reference's ``libs/quantum_library/kernels/gates.py`` output
+(complex128) for the same angle; tests/test_gates_parity.py pins that against golden
+fixtures generated from the live reference.  Matrices are built on the host with numpy
+(2x2 / 4x4, a few hundred bytes per gate) and shipped to the device in one buffer per
+circuit; the 2^n-sized work happens only in the CUDA kernels.
+
+A gate is lowered to one of three device kinds (include/tyxonq_b200.h):
+  DENSE  full 2^k x 2^k matrix (h, rx, ry, rxx, ryy, user unitaries)
+  DIAG   2^k-entry table       (rz, s, sdg, phase, cz, rzz) -- needs no qubit to be tile-local
+  PAIR   2x2 block on two basis patterns, identity elsewhere (x, cx, cry, swap, iswap, UCC
+         excitation rotations) -- touches only 2/2^k of the amplitudes
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+C128 = np.complex128
+_SQ2 = 1.0 / math.sqrt(2.0)
+
+# ---------------------------------------------------------------------------------------
+# matrices (reference gates.py line numbers in comments)
+# ---------------------------------------------------------------------------------------
+H_MAT = np.array([[1, 1], [1, -1]], dtype=C128) * C128(1.0 / np.sqrt(np.float64(2.0)))  # :11-16
+X_MAT = np.array([[0, 1], [1, 0]], dtype=C128)       # :163-170
+Y_MAT = np.array([[0, -1j], [1j, 0]], dtype=C128)    # :173-177
+Z_MAT = np.array([[1, 0], [0, -1]], dtype=C128)      # :180-184
+CX_MAT = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=C128)   # :82-90
+CZ_MAT = np.diag(np.array([1, 1, 1, -1], dtype=C128))                                      # :98-107
+ISWAP_MAT = np.array([[1, 0, 0, 0], [0, 0, 1j, 0], [0, 1j, 0, 0], [0, 0, 0, 1]], dtype=C128)  # :110-133
+SWAP_MAT = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=C128)     # :136-160
+
+
+def _cs(theta: float) -> Tuple[float, float]:
+    t = float(theta) * 0.5
+    return math.cos(t), math.sin(t)
+
+
+def rz_diag(theta: float) -> np.ndarray:      # :19-35  c*I - i s Z
+    c, s = _cs(theta)
+    return np.array([complex(c, -s), complex(c, s)], dtype=C128)
+
+
+def rx_mat(theta: float) -> np.ndarray:       # :38-48  c*I - i s X
+    c, s = _cs(theta)
+    return np.array([[c, -1j * s], [-1j * s, c]], dtype=C128)
+
+
+def ry_mat(theta: float) -> np.ndarray:       # :51-65
+    c, s = _cs(theta)
+    return np.array([[c, -s], [s, c]], dtype=C128)
+
+
+def phase_diag(theta: float) -> np.ndarray:   # :68-79  diag(1, e^{i theta})
+    return np.array([1.0, np.exp(1j * np.float64(theta))], dtype=C128)
+
+
+S_DIAG = phase_diag(np.pi / 2.0)     # :187-188
+SD_DIAG = phase_diag(-np.pi / 2.0)   # :191-192
+
+
+def rzz_diag(theta: float) -> np.ndarray:     # :236-252  c*I4 - i s Z(x)Z
+    c, s = _cs(theta)
+    a, b = complex(c, -s), complex(c, s)
+    return np.array([a, b, b, a], dtype=C128)
+
+
+def rxx_mat(theta: float) -> np.ndarray:      # :203-214
+    c, s = _cs(theta)
+    m = np.zeros((4, 4), dtype=C128)
+    for i in range(4):
+        m[i, i] = c
+        m[i, 3 - i] = -1j * s
+    return m
+
+
+def ryy_mat(theta: float) -> np.ndarray:      # :217-233  Y(x)Y = antidiag(-1, 1, 1, -1)
+    c, s = _cs(theta)
+    m = np.zeros((4, 4), dtype=C128)
+    yy = (-1.0, 1.0, 1.0, -1.0)
+    for i in range(4):
+        m[i, i] = c
+        m[i, 3 - i] = -1j * s * yy[i]
+    return m
+
+
+# generators d/dtheta U = G U for the parametrised gates (used by the adjoint sweep)
+def _gen_rot(P: np.ndarray) -> np.ndarray:
+    return (-0.5j) * P
+
+
+GEN = {
+    "rx": _gen_rot(X_MAT), "ry": _gen_rot(Y_MAT), "rz": _gen_rot(Z_MAT),
+    "rxx": _gen_rot(np.kron(X_MAT, X_MAT)), "ryy": _gen_rot(np.kron(Y_MAT, Y_MAT)),
+    "rzz": _gen_rot(np.kron(Z_MAT, Z_MAT)),
+    # cry: |1><1| (x) (-i/2) Y
+    "cry": np.kron(np.array([[0, 0], [0, 1]], dtype=C128), _gen_rot(Y_MAT)),
+}
+
+# ---------------------------------------------------------------------------------------
+# lowered gates
+# ---------------------------------------------------------------------------------------
+DENSE, DIAG, PAIR = 0, 1, 2
+
+
+@dataclass
+class LGate:
+    """A gate lowered to index-bit space.
+
+    bits[j] is the index bit carrying matrix-index bit j (j = 0 least significant), i.e. for
+    reference qubits (q0, .., qk-1) on n qubits: bits[j] = n-1-q_{k-1-j}.
+    data: DENSE (2^k,2^k) | DIAG (2^k,) | PAIR (4,) or (8,) [even-parity 2x2, odd-parity 2x2].
+    """
+    kind: int
+    bits: Tuple[int, ...]
+    data: np.ndarray
+    pat_a: int = 0
+    pat_b: int = 0
+    zmask: int = 0
+    # bookkeeping for gradients: (parameter slot, op name) of a parametrised gate
+    param: Optional[int] = None
+    name: str = ""
+    mask: int = field(default=0, init=False)
+
+    def __post_init__(self) -> None:
+        m = 0
+        for b in self.bits:
+            m |= 1 << int(b)
+        self.mask = m
+
+    @property
+    def k(self) -> int:
+        return len(self.bits)
+
+
+def _bits_of(qubits: Sequence[int], n: int) -> Tuple[int, ...]:
+    return tuple(n - 1 - int(q) for q in reversed(list(qubits)))
+
+
+def dense_gate(mat: np.ndarray, qubits: Sequence[int], n: int, **kw: Any) -> LGate:
+    k = len(qubits)
+    d = 1 << k
+    m = np.asarray(mat, dtype=C128)
+    m = m.reshape(d, d) if m.size == d * d else m.reshape(-1, d * d)  # leading axis = batch of matrices
+    return LGate(DENSE, _bits_of(qubits, n), m, **kw)
+
+
+def diag_gate(tab: np.ndarray, qubits: Sequence[int], n: int, **kw: Any) -> LGate:
+    return LGate(DIAG, _bits_of(qubits, n), np.asarray(tab, dtype=C128).reshape(-1), **kw)
+
+
+def pair_gate(m2: np.ndarray, qubits: Sequence[int], n: int, pat_a: int, pat_b: int, *,
+              m2_odd: Optional[np.ndarray] = None, zmask: int = 0, **kw: Any) -> LGate:
+    d = np.asarray(m2, dtype=C128).reshape(4)
+    if zmask:
+        d = np.concatenate([d, np.asarray(m2_odd, dtype=C128).reshape(4)])
+    return LGate(PAIR, _bits_of(qubits, n), d, pat_a=int(pat_a), pat_b=int(pat_b), zmask=int(zmask), **kw)
+
+
+def classify_unitary(mat: np.ndarray, qubits: Sequence[int], n: int) -> LGate:
+    """Lower a user-supplied matrix (``unitary`` op / apply_kqubit_unitary) structurally."""
+    k = len(qubits)
+    d = 1 << k
+    M = np.asarray(mat, dtype=C128).reshape(d, d)
+    off = M - np.diag(np.diag(M))
+    if not np.any(off):
+        return diag_gate(np.diag(M).copy(), qubits, n)
+    if k >= 2:
+        rows = [i for i in range(d) if np.any(off[i]) or np.any(off[:, i]) or M[i, i] != 1.0]
+        if len(rows) == 2:
+            a, b = rows
+            return pair_gate(M[np.ix_([a, b], [a, b])], qubits, n, a, b)
+    return dense_gate(M, qubits, n)
+
+
+def lower_op(op: Sequence[Any], n: int, *, mode: str, unitary_cache: Optional[Dict[str, Any]] = None,
+             param: Optional[int] = None) -> Optional[LGate]:
+    """Lower one op tuple.  Returns None for ops that are not gates or that the reference
+    engine silently skips (engine.py:372-374; ``cry`` is skipped by state(), engine.py:918-949)."""
+    nm = op[0]
+    if nm == "h":
+        return dense_gate(H_MAT, [op[1]], n, name=nm)
+    if nm == "x":
+        return dense_gate(X_MAT, [op[1]], n, name=nm)
+    if nm == "rx":
+        return dense_gate(rx_mat(op[2]), [op[1]], n, name=nm, param=param)
+    if nm == "ry":
+        return dense_gate(ry_mat(op[2]), [op[1]], n, name=nm, param=param)
+    if nm == "rz":
+        return diag_gate(rz_diag(op[2]), [op[1]], n, name=nm, param=param)
+    if nm == "s":
+        return diag_gate(S_DIAG, [op[1]], n, name=nm)
+    if nm == "sdg":
+        return diag_gate(SD_DIAG, [op[1]], n, name=nm)
+    if nm in ("cx", "cz", "iswap", "swap", "rxx", "ryy", "rzz", "cry"):
+        q0, q1 = int(op[1]), int(op[2])
+        if q0 == q1:  # apply_2q_statevector returns the input unchanged (statevector.py:46-47)
+            return None
+        if nm == "cx":
+            return pair_gate(X_MAT, [q0, q1], n, 0b10, 0b11, name=nm)
+        if nm == "cz":
+            return diag_gate(np.array([1, 1, 1, -1], dtype=C128), [q0, q1], n, name=nm)
+        if nm == "swap":
+            return pair_gate(X_MAT, [q0, q1], n, 0b01, 0b10, name=nm)
+        if nm == "iswap":
+            return pair_gate(np.array([[0, 1j], [1j, 0]], dtype=C128), [q0, q1], n, 0b01, 0b10, name=nm)
+        if nm == "rzz":
+            return diag_gate(rzz_diag(op[3]), [q0, q1], n, name=nm, param=param)
+        if nm == "rxx":
+            return dense_gate(rxx_mat(op[3]), [q0, q1], n, name=nm, param=param)
+        if nm == "ryy":
+            return dense_gate(ryy_mat(op[3]), [q0, q1], n, name=nm, param=param)
+        if nm == "cry":
+            if mode != "run":
+                return None
+            return pair_gate(ry_mat(op[3]), [q0, q1], n, 0b10, 0b11, name=nm, param=param)
+    if nm == "unitary":
+        cache = unitary_cache or {}
+        if len(op) == 3:
+            mat = cache.get(str(op[2]))
+            return None if mat is None else classify_unitary(_to_np(mat), [int(op[1])], n)
+        if len(op) == 4:
+            mat = cache.get(str(op[3]))
+            q0, q1 = int(op[1]), int(op[2])
+            if mat is None:
+                return None
+            if q0 == q1:
+                raise ValueError("unitary on a repeated qubit")
+            return classify_unitary(_to_np(mat), [q0, q1], n)
+    return None
+
+
+def _to_np(x: Any) -> np.ndarray:
+    if hasattr(x, "detach"):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, dtype=C128)

@@ -1,0 +1,58 @@
+"""Route a live TyxonQ install to the B200 engine (seams B1/B2 of SURVEY.md section 8b).
+
+``install()`` rebinds, inside an importable ``tyxonq`` package:
+  * ``devices.simulators.driver._select_engine``  -> returns our ``StatevectorEngine`` for
+    "statevector" (reference driver.py:20-30, 96-97: the engine is constructed with no args)
+  * ``devices.simulators.statevector.engine.StatevectorEngine`` -> our class (used by
+    ``Circuit.state``, core/ir/circuit.py:492-494)
+  * the kernel functions of ``libs.quantum_library.kernels.statevector`` (looked up lazily by
+    ``Circuit._expectation_statevector`` and the chem numerics)
+TyxonQ itself is not a dependency of this package; ``install()`` raises ImportError without it.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict
+
+_saved: Dict[str, Any] = {}
+
+
+def install() -> None:
+    import importlib
+    drv = importlib.import_module("tyxonq.devices.simulators.driver")
+    eng_mod = importlib.import_module("tyxonq.devices.simulators.statevector.engine")
+    ker_mod = importlib.import_module("tyxonq.libs.quantum_library.kernels.statevector")
+    from . import kernels as K
+    from .engine import StatevectorEngine
+
+    if _saved:
+        return
+    _saved["select"] = drv._select_engine
+    _saved["engine"] = eng_mod.StatevectorEngine
+    _saved["kernels"] = {k: getattr(ker_mod, k) for k in K.__all__}
+
+    ref_select = drv._select_engine
+
+    def _select_engine(device: str):
+        name = device.split("::")[-1] if "::" in device else device
+        if name in ("simulator:statevector", "statevector"):
+            return StatevectorEngine
+        return ref_select(device)
+
+    drv._select_engine = _select_engine
+    eng_mod.StatevectorEngine = StatevectorEngine
+    for k in K.__all__:
+        setattr(ker_mod, k, getattr(K, k))
+
+
+def uninstall() -> None:
+    if not _saved:
+        return
+    import importlib
+    drv = importlib.import_module("tyxonq.devices.simulators.driver")
+    eng_mod = importlib.import_module("tyxonq.devices.simulators.statevector.engine")
+    ker_mod = importlib.import_module("tyxonq.libs.quantum_library.kernels.statevector")
+    drv._select_engine = _saved["select"]
+    eng_mod.StatevectorEngine = _saved["engine"]
+    for k, v in _saved["kernels"].items():
+        setattr(ker_mod, k, v)
+    _saved.clear()

@@ -1,0 +1,207 @@
+"""Host planner: lowered gates -> fused passes (tqb_pass / tqb_gate / matrix buffer).
+
+The reference interprets one op at a time and allocates a new 2^n array per gate
+(devices/simulators/statevector/engine.py:52-374).  Here a circuit is compiled into a short
+list of *passes*; each pass streams the state through shared-memory tiles once and applies
+every gate whose target bits are tile-local.  Diagonal gates never need locality (their
+table is indexed by the global amplitude index), so they ride along with any pass.
+
+Scheduling is a greedy list scheduler over the gate dependency order: gates that share no
+index bit commute, so a gate may join the current pass when (a) none of its bits is blocked
+by an earlier gate that could not be scheduled and (b) its target bits fit into the tile's
+budget of high bits.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .gates import DENSE, DIAG, PAIR, LGate
+
+C128 = np.complex128
+
+
+@dataclass
+class TileConfig:
+    m: int          # tile bits
+    L: int          # low contiguous bits
+    threads: int = 256
+    ctas_per_sm: int = 0
+    max_gates: int = 384
+
+    @property
+    def h(self) -> int:
+        return self.m - self.L
+
+
+def default_tile(n: int, itemsize: int, batch: int = 1) -> TileConfig:
+    """itemsize = 8 (complex64) or 16 (complex128).  Streaming regime: 32 KiB tiles (several CTAs
+    per SM overlap their load / compute / store phases), 512-byte contiguous runs.  Small states
+    use one big tile so that whole layers stay in shared memory."""
+    big = 13 if itemsize == 16 else 14           # 128 KiB tile
+    stream_m = 11 if itemsize == 16 else 12      # 32 KiB tile
+    stream_L = 5 if itemsize == 16 else 6        # 512 B runs
+    m = int(os.environ.get("TQB_TILE_M", 0)) or (min(n, big) if (n <= big + 3 and batch <= 64) else stream_m)
+    m = min(m, n)
+    L = int(os.environ.get("TQB_TILE_L", 0)) or stream_L
+    L = min(L, m)
+    if m - L > 12:
+        L = m - 12
+    threads = int(os.environ.get("TQB_THREADS", 0)) or (256 if m <= 12 else 512)
+    cps = int(os.environ.get("TQB_CTAS_PER_SM", 0))
+    return TileConfig(m=m, L=L, threads=threads, ctas_per_sm=cps)
+
+
+@dataclass
+class Program:
+    """A compiled circuit: host copies of the ABI arrays (uploaded by program.DeviceProgram)."""
+    n: int
+    passes: np.ndarray          # _lib.PASS_DTYPE
+    gates: np.ndarray           # _lib.GATE_DTYPE
+    mats: np.ndarray            # complex128, flat
+    n_gates_in: int             # gates before planning (for gates/s accounting)
+    tile: TileConfig
+    order: List[int]            # order[i] = index (into the input list) of the i-th scheduled gate
+
+    @property
+    def n_passes(self) -> int:
+        return int(self.passes.shape[0])
+
+
+def _low_mask(L: int) -> int:
+    return (1 << L) - 1
+
+
+def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[List[int], List[int]]]:
+    """Return [(high_bits, [gate indices in execution order]), ...]."""
+    N = len(gates)
+    done = [False] * N
+    remaining = N
+    first = 0
+    all_bits = (1 << n) - 1
+    low = _low_mask(tile.L)
+    h = tile.h
+    out: List[Tuple[List[int], List[int]]] = []
+    masks = [g.mask for g in gates]
+    needs = [0 if g.kind == DIAG else (g.mask & ~low) for g in gates]
+    is_diag = [g.kind == DIAG for g in gates]
+    while remaining:
+        while done[first]:
+            first += 1
+        H = 0
+        nH = 0
+        blocked = 0      # bits of skipped gates
+        blocked_nd = 0   # ... of skipped non-diagonal gates only
+        chosen: List[int] = []
+        i = first
+        seen = 0
+        while i < N and seen < 4096:
+            if not done[i]:
+                seen += 1
+                mk = masks[i]
+                if is_diag[i]:
+                    if mk & blocked_nd:
+                        blocked |= mk
+                    else:
+                        chosen.append(i)
+                elif mk & blocked:
+                    blocked |= mk
+                    blocked_nd |= mk
+                else:
+                    need = needs[i] & ~H
+                    cnt = bin(need).count("1")
+                    if nH + cnt <= h:
+                        H |= need
+                        nH += cnt
+                        chosen.append(i)
+                    else:
+                        blocked |= mk
+                        blocked_nd |= mk
+                if blocked_nd == all_bits or len(chosen) >= tile.max_gates:
+                    break
+            i += 1
+        for c in chosen:
+            done[c] = True
+        remaining -= len(chosen)
+        # fill the tile with the lowest free bits (longer contiguous runs)
+        b = tile.L
+        while nH < h and b < n:
+            if not (H >> b) & 1:
+                H |= 1 << b
+                nH += 1
+            b += 1
+        out.append(([p for p in range(n) if (H >> p) & 1], chosen))
+    return out
+
+
+def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_mats: int = 1) -> Program:
+    """Pack scheduled gates into the ABI arrays.  ``batch_mats`` > 1: every gate's ``data`` has a
+    leading batch axis (one matrix per batch member)."""
+    m_eff = min(tile.m, n)
+    tile = TileConfig(m=m_eff, L=min(tile.L, m_eff), threads=tile.threads, ctas_per_sm=tile.ctas_per_sm,
+                      max_gates=tile.max_gates)
+    sched = schedule(gates, n, tile)
+    ng = sum(len(c) for _, c in sched)
+    passes = np.zeros(len(sched), dtype=_lib.PASS_DTYPE)
+    garr = np.zeros(ng, dtype=_lib.GATE_DTYPE)
+    mats: List[np.ndarray] = []
+    mat_off = 0
+    gi = 0
+    order: List[int] = []
+    for pi, (hb, chosen) in enumerate(sched):
+        L = tile.L
+        assert len(hb) == m_eff - L, (hb, m_eff, L)
+        local_of = {p: p for p in range(L)}
+        for j, p in enumerate(hb):
+            local_of[p] = L + j
+        ps = passes[pi]
+        ps["m"] = m_eff
+        ps["L"] = L
+        ps["gate_begin"] = gi
+        ps["n_gates"] = len(chosen)
+        for j, p in enumerate(hb):
+            ps["hb"][j] = p
+        maxk = 0
+        for idx in chosen:
+            g = gates[idx]
+            e = garr[gi]
+            e["kind"] = g.kind
+            e["k"] = g.k
+            if g.kind == DIAG:
+                for j, b in enumerate(g.bits):
+                    e["bits"][j] = b
+            else:
+                loc = [local_of[b] for b in g.bits]
+                for j, b in enumerate(loc):
+                    e["bits"][j] = b
+                for j, b in enumerate(sorted(loc)):
+                    e["sbits"][j] = b
+                if g.kind == PAIR:
+                    e["off_a"] = sum(((g.pat_a >> j) & 1) << loc[j] for j in range(g.k))
+                    e["off_b"] = sum(((g.pat_b >> j) & 1) << loc[j] for j in range(g.k))
+                    e["zmask"] = g.zmask
+                else:
+                    maxk = max(maxk, g.k)
+            d = np.asarray(g.data, dtype=C128)
+            if batch_mats > 1:
+                d = d.reshape(batch_mats, -1)
+                per = d.shape[1]
+                e["mat_off"] = mat_off
+                e["mat_bstride"] = per
+                mats.append(d.reshape(-1))
+                mat_off += per * batch_mats
+            else:
+                d = d.reshape(-1)
+                e["mat_off"] = mat_off
+                e["mat_bstride"] = 0
+                mats.append(d)
+                mat_off += d.size
+            order.append(idx)
+            gi += 1
+        ps["max_dense_k"] = maxk
+    flat = np.concatenate(mats) if mats else np.zeros(0, dtype=C128)
+    return Program(n=n, passes=passes, gates=garr, mats=flat, n_gates_in=len(gates), tile=tile, order=order)
