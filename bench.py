@@ -156,6 +156,7 @@ def own_arm(args) -> None:
     from tyxonq_b200 import StatevectorEngine, _lib
     from tyxonq_b200 import program as P
     from tyxonq_b200.circuits import Circuit
+    from tyxonq_b200.fuse import fuse
     from tyxonq_b200.gates import lower_op
     from tyxonq_b200.planner import compile_program, default_tile
 
@@ -182,7 +183,7 @@ def own_arm(args) -> None:
         n_local = sb.n_local
     else:
         t0 = time.perf_counter()
-        lg = [g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None]
+        lg = fuse([g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None])
         prog = compile_program(lg, n, default_tile(n, B, 1))
         plan_ms = 1e3 * (time.perf_counter() - t0)
         dp = P.DeviceProgram(prog, dev, tdt)
@@ -201,7 +202,7 @@ def own_arm(args) -> None:
                 pass_ev.append((e0, e1))
             return P.expect_z_bits(state)
 
-        info = {"passes": prog.n_passes, "gates_per_pass": n_gates / prog.n_passes, "plan_ms": plan_ms,
+        info = {"passes": prog.n_passes, "gates_per_pass": n_gates / prog.n_passes, "fused_gate_sweeps": len(lg), "plan_ms": plan_ms,
                 "tile_m": prog.tile.m, "tile_L": prog.tile.L, "threads": prog.tile.threads, "swaps": 0}
         n_local = n
 
@@ -306,6 +307,7 @@ def extras(dev) -> dict:
     import torch
     from tyxonq_b200 import _lib, ucc
     from tyxonq_b200 import program as P
+    from tyxonq_b200.fuse import fuse
     from tyxonq_b200.gates import lower_op
     from tyxonq_b200.planner import compile_program, default_tile
     from tyxonq_b200.vqe import TFIMVqe
@@ -314,7 +316,7 @@ def extras(dev) -> dict:
     # complex64 sweep at n = 30
     n, layers = 30, 20
     ops, n_gates = workload(n, layers)
-    lg = [g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None]
+    lg = fuse([g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None])
     prog = compile_program(lg, n, default_tile(n, 8, 1))
     dp = P.DeviceProgram(prog, dev, torch.complex64)
     st = P.new_state(n, dtype=torch.complex64, device=dev)

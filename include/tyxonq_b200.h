@@ -37,20 +37,24 @@ extern "C" {
 #define TQB_GATE_DENSE 0 /* dense 2^k x 2^k matrix, k <= 4, row-major, row = output index      */
 #define TQB_GATE_DIAG 1  /* diagonal: table of 2^k entries indexed by k GLOBAL index bits       */
 #define TQB_GATE_PAIR 2  /* 2x2 matrix on the pair (pattern A, pattern B) of k target bits,     */
-                         /* all other patterns untouched (cx, swap, controlled-U, UCC Givens)  */
+                         /* all other patterns untouched (cry, iswap, controlled-U, UCC Givens)*/
+#define TQB_GATE_SWAP 3  /* exchange the amplitudes of pattern A and pattern B (x, cx, swap):   */
+                         /* a PAIR gate with the matrix [[0,1],[1,0]], done without arithmetic  */
 
 #define TQB_MAX_DENSE_K 4
 #define TQB_MAX_GATE_BITS 8
 #define TQB_MAX_TILE_HIGH 16
 
 /* One gate of a pass.  Matrix-index bit j (j = 0 least significant) lives on bits[j].
- * DENSE/PAIR: bits[] are TILE-LOCAL positions (see tqb_pass); DIAG: GLOBAL index bits.      */
+ * DENSE/PAIR/SWAP: bits[] are TILE-LOCAL positions (see tqb_pass), k <= 4.
+ * DIAG (k <= 6): bits[j] < 64 is a tile-local position; bits[j] = 64 + p is index bit p that
+ * is NOT in the tile (p may be a shard bit >= n of a sharded state).                          */
 typedef struct tqb_gate {
   int32_t kind;
   int32_t k;
   int8_t bits[TQB_MAX_GATE_BITS];
-  int8_t sbits[TQB_MAX_GATE_BITS]; /* DENSE/PAIR: bits[] sorted ascending                    */
-  uint32_t off_a, off_b;           /* PAIR: tile-local offsets of patterns A and B            */
+  int8_t sbits[TQB_MAX_GATE_BITS]; /* DENSE/PAIR/SWAP: bits[] sorted ascending               */
+  uint32_t off_a, off_b;           /* PAIR/SWAP: tile-local offsets of patterns A and B       */
   uint32_t mat_off;                /* offset (complex elements) into the matrix buffer        */
   uint32_t mat_bstride;            /* per-batch-member stride (complex elements), 0 = shared  */
   uint64_t zmask;                  /* PAIR: parity of popc(global_index & zmask) picks the     */

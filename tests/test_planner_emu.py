@@ -55,7 +55,8 @@ def test_dense_k3_k4_and_classifier(golden):
         for m, L in ((7, 3), (5, 2), (4, 0)):
             prog = P.compile_program([g], 7, P.TileConfig(m=m, L=L))
             assert np.abs(run_program_emulated(prog, psi) - golden[f"k7_out{k}"]).max() < 1e-13
-    assert G.classify_unitary(O.gate_cx_4x4(), [0, 1], 3).kind == G.PAIR
+    assert G.classify_unitary(O.gate_cx_4x4(), [0, 1], 3).kind == G.SWAP
+    assert G.classify_unitary(O.gate_cry_4x4(0.4), [0, 1], 3).kind == G.PAIR
     assert G.classify_unitary(O.gate_cz_4x4(), [0, 1], 3).kind == G.DIAG
     assert G.classify_unitary(O.gate_iswap_4x4(), [0, 1], 3).kind == G.PAIR
     assert G.classify_unitary(O.gate_rxx(0.3), [0, 1], 3).kind == G.DENSE
@@ -104,6 +105,22 @@ def test_ucc_pair_gates_with_parity():
             prog = P.compile_program([g], n, P.TileConfig(m=m, L=L))
             out = run_program_emulated(prog, psi)
             assert np.abs(out - U.evolve_excitation(psi, f_idx, theta, n)).max() < 1e-13, f_idx
+
+
+@pytest.mark.parametrize("n,seed", [(5, 0), (8, 1), (10, 2)])
+def test_gate_fusion_preserves_the_circuit(n, seed):
+    from tyxonq_b200.fuse import fuse
+    rng = np.random.default_rng(seed)
+    for ops in (random_ops(rng, n, 200), O.hea_ops(n, 3, rng.uniform(-3, 3, 6 * n)), O.qaoa_ring_ops(n, 3, rng.uniform(-3, 3, 6)),
+                O.trotter_ops(*O.tfim_terms(n), 1.0, 2), O.tfim_vqe_ops(n, 2, rng.normal(size=(4, n)))):
+        ref, _ = O.evolve_ops(n, ops, mode="run")
+        lg = _lower(ops, n)
+        fg = fuse(lg)
+        assert len(fg) <= len(lg)
+        prog = P.compile_program(fg, n, P.TileConfig(m=min(n, 6), L=2))
+        psi0 = np.zeros(1 << n, dtype=np.complex128)
+        psi0[0] = 1
+        assert np.abs(run_program_emulated(prog, psi0) - ref).max() < 1e-12
 
 
 def test_planner_fuses_layers():

@@ -22,7 +22,7 @@ import torch
 
 from . import _lib
 from . import program as P
-from .gates import DENSE, DIAG, GEN, PAIR, LGate, lower_op, _to_np
+from .gates import DENSE, DIAG, GEN, PAIR, SWAP, LGate, lower_op, _to_np
 from .planner import compile_program, default_tile
 
 
@@ -40,6 +40,8 @@ def dagger(g: LGate) -> LGate:
         d = g.data.conj().T.copy()
     elif g.kind == DIAG:
         d = g.data.conj().copy()
+    elif g.kind == SWAP:
+        d = g.data.copy()
     else:
         d = np.concatenate([b.reshape(2, 2).conj().T.reshape(4) for b in g.data.reshape(-1, 4)])
     return LGate(g.kind, g.bits, d, pat_a=g.pat_a, pat_b=g.pat_b, zmask=g.zmask, name=g.name + "^")

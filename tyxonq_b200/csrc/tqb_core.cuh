@@ -118,10 +118,21 @@ TQB_HD void tile_store(const cplx<T> *tile, cplx<T> *state, const TileGeom &g, c
 }
 
 // ---- phase 2: one gate on the staged tile ---------------------------------------------------
+// All descriptor fields are copied into registers first: the descriptor lives in shared memory
+// next to the tile, so the compiler would otherwise reload it after every tile store.
+template <int K>
+TQB_HD uint32_t insert_zeros_k(uint32_t g, const uint32_t (&sb)[K]) {
+#pragma unroll
+  for (int j = 0; j < K; ++j) g = ((g >> sb[j]) << (sb[j] + 1u)) | (g & ((1u << sb[j]) - 1u));
+  return g;
+}
+
 template <typename T, int K>
 TQB_HD void gate_dense(cplx<T> *tile, int m, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
   constexpr int D = 1 << K;
-  uint32_t off[D];
+  uint32_t sb[K], off[D];
+#pragma unroll
+  for (int j = 0; j < K; ++j) sb[j] = (uint32_t)g.sbits[j];
 #pragma unroll
   for (int s = 0; s < D; ++s) {
     uint32_t o = 0;
@@ -135,7 +146,7 @@ TQB_HD void gate_dense(cplx<T> *tile, int m, const tqb_gate &g, const cplx<T> *M
 #pragma unroll
     for (int i = 0; i < D * D; ++i) Mr[i] = M[i];
     for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
-      const uint32_t base = insert_zeros32(gi, g.sbits, K);
+      const uint32_t base = insert_zeros_k<K>(gi, sb);
       cplx<T> v[D];
 #pragma unroll
       for (int s = 0; s < D; ++s) v[s] = tile[base + off[s]];
@@ -149,7 +160,7 @@ TQB_HD void gate_dense(cplx<T> *tile, int m, const tqb_gate &g, const cplx<T> *M
     }
   } else {
     for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
-      const uint32_t base = insert_zeros32(gi, g.sbits, K);
+      const uint32_t base = insert_zeros_k<K>(gi, sb);
       cplx<T> v[D];
 #pragma unroll
       for (int s = 0; s < D; ++s) v[s] = tile[base + off[s]];
@@ -164,43 +175,96 @@ TQB_HD void gate_dense(cplx<T> *tile, int m, const tqb_gate &g, const cplx<T> *M
   }
 }
 
-template <typename T>
-TQB_HD void gate_pair(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, uint64_t gbase,
-                      const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
-  const uint32_t ngroups = 1u << (geo.m - g.k);
+// PAIR: 2x2 block on (pattern A, pattern B); SWAP: exchange A and B (x, cx, swap: no arithmetic).
+template <typename T, int K, bool SWAP>
+TQB_HD void gate_pair_k(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, uint64_t gbase,
+                        const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  uint32_t sb[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) sb[j] = (uint32_t)g.sbits[j];
+  const uint32_t off_a = g.off_a, off_b = g.off_b;
+  const uint64_t zmask = g.zmask;
+  const uint32_t ngroups = 1u << (geo.m - K);
+  if (SWAP) {
+    for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
+      const uint32_t base = insert_zeros_k<K>(gi, sb);
+      const cplx<T> a = tile[base + off_a], b = tile[base + off_b];
+      tile[base + off_a] = b;
+      tile[base + off_b] = a;
+    }
+    return;
+  }
   cplx<T> M0[4], M1[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) M0[i] = M[i];
-  if (g.zmask) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) M1[i] = M[4 + i];
-  }
+  for (int i = 0; i < 4; ++i) M1[i] = zmask ? M[4 + i] : M[i];
   for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
-    const uint32_t base = insert_zeros32(gi, g.sbits, g.k);
-    const uint32_t ia = base + g.off_a, ib = base + g.off_b;
+    const uint32_t base = insert_zeros_k<K>(gi, sb);
+    const uint32_t ia = base + off_a, ib = base + off_b;
     const cplx<T> a = tile[ia], b = tile[ib];
     bool odd = false;
-    if (g.zmask) odd = popc64(local_to_index(geo, roff, gbase, base) & g.zmask) & 1;
+    if (zmask) odd = popc64(local_to_index(geo, roff, gbase, base) & zmask) & 1;
     cplx<T> ra{0, 0}, rb{0, 0};
-    if (odd) {
-      cmac(ra, M1[0], a); cmac(ra, M1[1], b); cmac(rb, M1[2], a); cmac(rb, M1[3], b);
-    } else {
-      cmac(ra, M0[0], a); cmac(ra, M0[1], b); cmac(rb, M0[2], a); cmac(rb, M0[3], b);
-    }
+    cmac(ra, odd ? M1[0] : M0[0], a);
+    cmac(ra, odd ? M1[1] : M0[1], b);
+    cmac(rb, odd ? M1[2] : M0[2], a);
+    cmac(rb, odd ? M1[3] : M0[3], b);
     tile[ia] = ra;
     tile[ib] = rb;
   }
 }
 
-template <typename T>
-TQB_HD void gate_diag(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, uint64_t gbase,
-                      const tqb_gate &g, const cplx<T> *tab, int tid, int nthreads) {
-  const uint32_t nel = 1u << geo.m;
+template <typename T, bool SWAP>
+TQB_HD void gate_pair(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, uint64_t gbase,
+                      const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  switch (g.k) {
+    case 1: gate_pair_k<T, 1, SWAP>(tile, geo, roff, gbase, g, M, tid, nthreads); break;
+    case 2: gate_pair_k<T, 2, SWAP>(tile, geo, roff, gbase, g, M, tid, nthreads); break;
+    case 3: gate_pair_k<T, 3, SWAP>(tile, geo, roff, gbase, g, M, tid, nthreads); break;
+    case 4: gate_pair_k<T, 4, SWAP>(tile, geo, roff, gbase, g, M, tid, nthreads); break;
+    default: break;
+  }
+}
+
+// DIAG: bits[j] < 64 -> the table-index bit j is tile-local bit bits[j]; bits[j] >= 64 -> it is
+// index bit (bits[j] - 64) outside the tile, constant for the whole tile (read from gbase).
+template <typename T, int K>
+TQB_HD void gate_diag_k(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *tab,
+                        int tid, int nthreads) {
+  uint32_t pos[K];
+  uint32_t cpart = 0, lmask = 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const uint32_t b = (uint32_t)(uint8_t)g.bits[j];
+    if (b & 64u) {
+      cpart |= (uint32_t)((gbase >> (b & 63u)) & 1ull) << j;
+      pos[j] = 0;
+    } else {
+      pos[j] = b;
+      lmask |= 1u << j;
+    }
+  }
+  const uint32_t nel = 1u << m;
   for (uint32_t e = tid; e < nel; e += nthreads) {
-    const uint64_t idx = local_to_index(geo, roff, gbase, e);
-    uint32_t t = 0;
-    for (int j = 0; j < g.k; ++j) t |= (uint32_t)((idx >> g.bits[j]) & 1ull) << j;
+    uint32_t t = cpart;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if ((lmask >> j) & 1u) t |= ((e >> pos[j]) & 1u) << j;
     tile[e] = cmul(tile[e], tab[t]);
+  }
+}
+
+template <typename T>
+TQB_HD void gate_diag(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *tab, int tid, int nthreads) {
+  switch (g.k) {
+    case 1: gate_diag_k<T, 1>(tile, m, gbase, g, tab, tid, nthreads); break;
+    case 2: gate_diag_k<T, 2>(tile, m, gbase, g, tab, tid, nthreads); break;
+    case 3: gate_diag_k<T, 3>(tile, m, gbase, g, tab, tid, nthreads); break;
+    case 4: gate_diag_k<T, 4>(tile, m, gbase, g, tab, tid, nthreads); break;
+    case 5: gate_diag_k<T, 5>(tile, m, gbase, g, tab, tid, nthreads); break;
+    case 6: gate_diag_k<T, 6>(tile, m, gbase, g, tab, tid, nthreads); break;
+    default: break;
   }
 }
 
@@ -220,8 +284,9 @@ TQB_HD void tile_apply_gate(cplx<T> *tile, const TileGeom &geo, const uint64_t *
         default: break;
       }
       break;
-    case TQB_GATE_DIAG: gate_diag<T>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
-    case TQB_GATE_PAIR: gate_pair<T>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
+    case TQB_GATE_DIAG: gate_diag<T>(tile, geo.m, gbase, g, mat, tid, nthreads); break;
+    case TQB_GATE_PAIR: gate_pair<T, false>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
+    case TQB_GATE_SWAP: gate_pair<T, true>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
     default: break;
   }
 }

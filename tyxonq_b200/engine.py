@@ -60,8 +60,9 @@ class StatevectorEngine:
         if pending:
             ptr, n, batch, dt, _ = P._prep(state)
             from .planner import compile_program, default_tile
+            from .fuse import fuse
             tile = self.tile or default_tile(n, state.element_size(), batch)
-            prog = compile_program(pending, n, tile)
+            prog = compile_program(fuse(pending), n, tile)
             dp = P.DeviceProgram(prog, state.device, state.dtype)
             dp.run(state)
             self.last_h2d_bytes += dp.h2d_bytes

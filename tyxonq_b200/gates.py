@@ -9,8 +9,9 @@ circuit; the 2^n-sized work happens only in the CUDA kernels.
 A gate is lowered to one of three device kinds (include/tyxonq_b200.h):
   DENSE  full 2^k x 2^k matrix (h, rx, ry, rxx, ryy, user unitaries)
   DIAG   2^k-entry table       (rz, s, sdg, phase, cz, rzz) -- needs no qubit to be tile-local
-  PAIR   2x2 block on two basis patterns, identity elsewhere (x, cx, cry, swap, iswap, UCC
-         excitation rotations) -- touches only 2/2^k of the amplitudes
+  PAIR   2x2 block on two basis patterns, identity elsewhere (cry, iswap, UCC excitation
+         rotations) -- touches only 2/2^k of the amplitudes
+  SWAP   PAIR with the matrix X: a pure exchange of two patterns (x, cx, swap), no arithmetic
 """
 from __future__ import annotations
 
@@ -105,7 +106,7 @@ GEN = {
 # ---------------------------------------------------------------------------------------
 # lowered gates
 # ---------------------------------------------------------------------------------------
-DENSE, DIAG, PAIR = 0, 1, 2
+DENSE, DIAG, PAIR, SWAP = 0, 1, 2, 3
 
 
 @dataclass
@@ -162,6 +163,11 @@ def pair_gate(m2: np.ndarray, qubits: Sequence[int], n: int, pat_a: int, pat_b: 
     return LGate(PAIR, _bits_of(qubits, n), d, pat_a=int(pat_a), pat_b=int(pat_b), zmask=int(zmask), **kw)
 
 
+def swap_gate(qubits: Sequence[int], n: int, pat_a: int, pat_b: int, **kw: Any) -> LGate:
+    """Exchange of two basis patterns (x, cx, swap): a PAIR gate with matrix X, done without arithmetic."""
+    return LGate(SWAP, _bits_of(qubits, n), X_MAT.reshape(4).copy(), pat_a=int(pat_a), pat_b=int(pat_b), **kw)
+
+
 def classify_unitary(mat: np.ndarray, qubits: Sequence[int], n: int) -> LGate:
     """Lower a user-supplied matrix (``unitary`` op / apply_kqubit_unitary) structurally."""
     k = len(qubits)
@@ -174,7 +180,10 @@ def classify_unitary(mat: np.ndarray, qubits: Sequence[int], n: int) -> LGate:
         rows = [i for i in range(d) if np.any(off[i]) or np.any(off[:, i]) or M[i, i] != 1.0]
         if len(rows) == 2:
             a, b = rows
-            return pair_gate(M[np.ix_([a, b], [a, b])], qubits, n, a, b)
+            blk = M[np.ix_([a, b], [a, b])]
+            if np.array_equal(blk, X_MAT):
+                return swap_gate(qubits, n, a, b)
+            return pair_gate(blk, qubits, n, a, b)
     return dense_gate(M, qubits, n)
 
 
@@ -186,7 +195,7 @@ def lower_op(op: Sequence[Any], n: int, *, mode: str, unitary_cache: Optional[Di
     if nm == "h":
         return dense_gate(H_MAT, [op[1]], n, name=nm)
     if nm == "x":
-        return dense_gate(X_MAT, [op[1]], n, name=nm)
+        return swap_gate([op[1]], n, 0, 1, name=nm)
     if nm == "rx":
         return dense_gate(rx_mat(op[2]), [op[1]], n, name=nm, param=param)
     if nm == "ry":
@@ -202,11 +211,11 @@ def lower_op(op: Sequence[Any], n: int, *, mode: str, unitary_cache: Optional[Di
         if q0 == q1:  # apply_2q_statevector returns the input unchanged (statevector.py:46-47)
             return None
         if nm == "cx":
-            return pair_gate(X_MAT, [q0, q1], n, 0b10, 0b11, name=nm)
+            return swap_gate([q0, q1], n, 0b10, 0b11, name=nm)
         if nm == "cz":
             return diag_gate(np.array([1, 1, 1, -1], dtype=C128), [q0, q1], n, name=nm)
         if nm == "swap":
-            return pair_gate(X_MAT, [q0, q1], n, 0b01, 0b10, name=nm)
+            return swap_gate([q0, q1], n, 0b01, 0b10, name=nm)
         if nm == "iswap":
             return pair_gate(np.array([[0, 1j], [1j, 0]], dtype=C128), [q0, q1], n, 0b01, 0b10, name=nm)
         if nm == "rzz":

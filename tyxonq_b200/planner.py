@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from .gates import DENSE, DIAG, PAIR, LGate
+from .gates import DENSE, DIAG, PAIR, SWAP, LGate
 
 C128 = np.complex128
 
@@ -172,15 +172,17 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
             e["kind"] = g.kind
             e["k"] = g.k
             if g.kind == DIAG:
-                for j, b in enumerate(g.bits):
-                    e["bits"][j] = b
+                assert g.k <= 6, "diagonal tables are limited to 6 bits"
+                for j, b in enumerate(g.bits):  # tile-local position, or 64 + index bit when outside the tile
+                    e["bits"][j] = local_of[b] if b in local_of else 64 + b
             else:
+                assert g.k <= 4, "dense / pair gates are limited to 4 bits"
                 loc = [local_of[b] for b in g.bits]
                 for j, b in enumerate(loc):
                     e["bits"][j] = b
                 for j, b in enumerate(sorted(loc)):
                     e["sbits"][j] = b
-                if g.kind == PAIR:
+                if g.kind in (PAIR, SWAP):
                     e["off_a"] = sum(((g.pat_a >> j) & 1) << loc[j] for j in range(g.k))
                     e["off_b"] = sum(((g.pat_b >> j) & 1) << loc[j] for j in range(g.k))
                     e["zmask"] = g.zmask
