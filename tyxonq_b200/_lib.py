@@ -52,6 +52,7 @@ SIGNATURES = {
     "tqb_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i)]),
     "tqb_init_basis": (_i, [_vp, _i, _i64, _i, _u64, _u64, _vp]),
     "tqb_run_passes": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "tqb_set_tma": (_i, [_i]),
     "tqb_norm2": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_expect_z_bits": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_expect_zmasks": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp]),

@@ -82,6 +82,121 @@ tile_pass_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long lon
   }
 }
 
+// ---- TMA variant -------------------------------------------------------------------------------
+// Same pass, but tiles are staged by the TMA engine (cp.async.bulk, one bulk copy per contiguous
+// run) into a double buffer: while all warps apply the gates to tile i, the runs of tile i+1 are
+// already in flight and the runs of tile i-1 are being written back by bulk stores.  The SM issues
+// no load/store instructions for the state at all; completion is tracked by one mbarrier per buffer.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(MAXK <= 2 ? 512 : 256, 2)
+tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
+                     const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
+  cplx<T> *buf[2] = {reinterpret_cast<cplx<T> *>(smem_raw), reinterpret_cast<cplx<T> *>(smem_raw + tile_bytes)};
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * tile_bytes);  // 2 mbarriers (16 bytes)
+  uint64_t *roff = bars + 2;
+  tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
+
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (uint32_t j = tid; j < (1u << geo.h); j += nthreads) roff[j] = run_offset(geo, j);
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(gates);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
+    const int nw = n_gates * (int)(sizeof(tqb_gate) / 4);
+    for (int i = tid; i < nw; i += nthreads) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int tb = geo.n - geo.m;
+  const unsigned long long total = (unsigned long long)batch << tb;
+  const unsigned long long first = blockIdx.x, stride = gridDim.x;
+  const unsigned long long count = first < total ? (total - first + stride - 1) / stride : 0;
+  const uint32_t nruns = 1u << geo.h;
+  const uint32_t run_elems = 1u << geo.L;
+  const uint32_t run_bytes = (uint32_t)(sizeof(cplx<T>) << geo.L);
+
+  // issued by warp 0: the runs of this CTA's it-th tile -> buffer b
+  auto issue_load = [&](unsigned long long it, int b) {
+    const unsigned long long tt = first + it * stride;
+    const unsigned long long bm = tt >> tb;
+    const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
+    const cplx<T> *sb = state + (bm << geo.n) + base;
+    if (lane == 0) mbar_expect_tx(&bars[b], (uint32_t)tile_bytes);
+    __syncwarp();
+    for (uint32_t j = lane; j < nruns; j += 32) bulk_load(buf[b] + (size_t)j * run_elems, sb + roff[j], run_bytes, &bars[b]);
+  };
+
+  if (warp == 0 && count > 0) issue_load(0, 0);
+  for (unsigned long long it = 0; it < count; ++it) {
+    const int b = (int)(it & 1);
+    if (warp == 0 && it + 1 < count) {
+      bulk_wait_read0();  // this lane's bulk stores out of buffer b^1 (tile it-1) have read their source
+      __syncwarp();
+      issue_load(it + 1, b ^ 1);
+    }
+    mbar_wait(&bars[b], (uint32_t)((it >> 1) & 1));
+    const unsigned long long tt = first + it * stride;
+    const unsigned long long bm = tt >> tb;
+    const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
+    cplx<T> *tile = buf[b];
+    for (int gi = 0; gi < n_gates; ++gi) {
+      const tqb_gate &g = sg[gi];
+      const cplx<T> *mat = mats + g.mat_off + (size_t)bm * g.mat_bstride;
+      tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, g, mat, tid, nthreads);
+      __syncthreads();
+    }
+    fence_proxy_async();  // generic-proxy writes of the tile -> visible to the bulk-store engine
+    __syncthreads();
+    if (warp == 0) {
+      cplx<T> *sb = state + (bm << geo.n) + base;
+      for (uint32_t j = lane; j < nruns; j += 32) bulk_store(sb + roff[j], tile + (size_t)j * run_elems, run_bytes);
+      bulk_commit();
+    }
+  }
+  if (warp == 0) bulk_wait_all0();
+}
+
 template <typename T>
 __global__ void init_basis_kernel(cplx<T> *state, int n, long long batch, unsigned long long local_index,
                                   int present) {
@@ -103,19 +218,18 @@ static int launch_pass(void *state, const TileGeom &geo, int64_t batch, const tq
   const size_t smem = (sizeof(cplx<T>) << geo.m) + (sizeof(uint64_t) << geo.h) + (size_t)n_gates * sizeof(tqb_gate);
   TQB_REQUIRE(smem <= (size_t)ws.max_smem_optin, "tqb_run_passes: tile + gate list exceed shared memory");
   auto kern = tile_pass_kernel<T, V, MAXK>;
-  static thread_local size_t conf = 0;  // one per template instantiation
-  if (smem > 48 * 1024 && smem > conf) {
+  static thread_local bool configured = false;  // one per template instantiation and host thread
+  if (!configured) {
     TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
-    conf = ws.max_smem_optin;
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
   }
   const unsigned long long total = (unsigned long long)batch << (geo.n - geo.m);
-  int per_sm = ctas_per_sm;
-  if (per_sm <= 0) {
-    per_sm = (int)((size_t)(200 * 1024) / (smem + 1024));
-    const int by_threads = 2048 / threads;
-    if (per_sm > by_threads) per_sm = by_threads;
-    if (per_sm < 1) per_sm = 1;
-  }
+  // persistent grid: exactly the CTAs that are resident at once (a second wave would run half empty)
+  int resident = 0;
+  TQB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, threads, smem));
+  if (resident < 1) return fail("tqb_run_passes: tile does not fit on an SM");
+  int per_sm = ctas_per_sm > 0 && ctas_per_sm < resident ? ctas_per_sm : resident;
   unsigned long long grid = (unsigned long long)ws.sm_count * per_sm;
   if (grid > total) grid = total;
   kern<<<(unsigned)grid, threads, smem, st>>>(reinterpret_cast<cplx<T> *>(state), geo, (long long)batch, gates,
@@ -124,11 +238,47 @@ static int launch_pass(void *state, const TileGeom &geo, int64_t batch, const tq
   return 0;
 }
 
+static std::atomic<int> g_use_tma{1};
+
+template <typename T, int MAXK>
+static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
+                           const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st, bool *used) {
+  *used = false;
+  const int max_threads = MAXK <= 2 ? 512 : 256;
+  if (threads > max_threads) threads = max_threads;
+  const size_t smem = 2 * (sizeof(cplx<T>) << geo.m) + 16 + (sizeof(uint64_t) << geo.h) + (size_t)n_gates * sizeof(tqb_gate);
+  if (smem > (size_t)ws.max_smem_optin) return 0;  // caller falls back to the single-buffer kernel
+  auto kern = tile_pass_tma_kernel<T, MAXK>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  const unsigned long long total = (unsigned long long)batch << (geo.n - geo.m);
+  int resident = 0;
+  TQB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, threads, smem));
+  if (resident < 1) return 0;
+  int per_sm = ctas_per_sm > 0 && ctas_per_sm < resident ? ctas_per_sm : resident;
+  unsigned long long grid = (unsigned long long)ws.sm_count * per_sm;
+  if (grid > total) grid = total;
+  kern<<<(unsigned)grid, threads, smem, st>>>(reinterpret_cast<cplx<T> *>(state), geo, (long long)batch, gates, n_gates,
+                                               reinterpret_cast<const cplx<T> *>(mats));
+  TQB_CHECK_LAUNCH("tile_pass_tma_kernel");
+  *used = true;
+  return 0;
+}
+
 }  // namespace tqb
 
 using namespace tqb;
 
 extern "C" {
+
+int tqb_set_tma(int enable) {
+  const int old = g_use_tma.exchange(enable ? 1 : 0);
+  return old;
+}
 
 int tqb_abi_version(void) { return TQB_ABI_VERSION; }
 const char *tqb_last_error(void) { return t_err.c_str(); }
@@ -220,6 +370,19 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
     const bool heavy = ps.max_dense_k > 2;
     cudaStream_t st = as_stream(stream);
     int rc;
+    // TMA staging needs runs of >= 128 bytes and room for the double buffer; else vector LDG/STG
+    const size_t run_bytes = (dtype == TQB_C128 ? (size_t)16 : (size_t)8) << ps.L;
+    if (g_use_tma.load() && run_bytes >= 128 && n > ps.m) {
+      bool used = false;
+      if (dtype == TQB_C128)
+        rc = heavy ? launch_pass_tma<double, 4>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
+                   : launch_pass_tma<double, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used);
+      else
+        rc = heavy ? launch_pass_tma<float, 4>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
+                   : launch_pass_tma<float, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used);
+      if (rc) return rc;
+      if (used) continue;
+    }
 #define TQB_LAUNCH(T, V, MK) launch_pass<T, V, MK>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st)
     if (dtype == TQB_C128)
       rc = heavy ? TQB_LAUNCH(double, 1, 4) : TQB_LAUNCH(double, 1, 2);
