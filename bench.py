@@ -184,7 +184,7 @@ def own_arm(args) -> None:
     else:
         t0 = time.perf_counter()
         lg = fuse([g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None])
-        prog = compile_program(lg, n, default_tile(n, B, 1))
+        prog = compile_program(lg, n, default_tile(n, B, 1), itemsize=B)
         plan_ms = 1e3 * (time.perf_counter() - t0)
         dp = P.DeviceProgram(prog, dev, tdt)
         state = torch.empty(1 << n, dtype=tdt, device=dev)
@@ -317,7 +317,7 @@ def extras(dev) -> dict:
     n, layers = 30, 20
     ops, n_gates = workload(n, layers)
     lg = fuse([g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None])
-    prog = compile_program(lg, n, default_tile(n, 8, 1))
+    prog = compile_program(lg, n, default_tile(n, 8, 1), itemsize=8)
     dp = P.DeviceProgram(prog, dev, torch.complex64)
     st = P.new_state(n, dtype=torch.complex64, device=dev)
     dp.run(st); torch.cuda.synchronize()

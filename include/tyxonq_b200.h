@@ -41,6 +41,17 @@ extern "C" {
 #define TQB_GATE_SWAP 3  /* exchange the amplitudes of pattern A and pattern B (x, cx, swap):   */
                          /* a PAIR gate with the matrix [[0,1],[1,0]], done without arithmetic  */
 
+/* Register micro-passes (planned by the host, executed inside a pass): a TQB_GATE_MICRO header
+ * (k = R register bits, bits[] = their tile-local positions ascending, off_a = number of register
+ * gates that follow) and then R-gates whose bits[] index the register bits 0..R-1.
+ * R = 3 for complex128 (8 amplitudes per thread), 4 for complex64 (16 amplitudes per thread).   */
+#define TQB_GATE_MICRO 16
+#define TQB_GATE_RDENSE 32 /* k = 1: bits[0]; k = 2: matrix-index bit 0 on bits[0] < bits[1] (bit 1)   */
+#define TQB_GATE_RDIAG 33  /* bits[j]: 32+rho register bit | <32 tile-local bit | 64+p outside tile;    */
+                           /* sbits[rho] = weight (1<<j) of register bit rho in the table index         */
+#define TQB_GATE_RSWAP 35  /* off_a = mask of the gate's register bits, off_b = pattern A on them,      */
+                           /* zmask = A xor B (register-index space)                                     */
+
 #define TQB_MAX_DENSE_K 4
 #define TQB_MAX_GATE_BITS 8
 #define TQB_MAX_TILE_HIGH 16
@@ -64,16 +75,18 @@ typedef struct tqb_gate {
 /* One pass = one read-modify-write sweep over the whole state.  Every CTA stages tiles of 2^m
  * amplitudes in shared memory: the L lowest index bits (contiguous runs of 2^L amplitudes)
  * plus the m-L high bits hb[] (ascending, each >= L).  Tile-local bit j is index bit j for
- * j < L and index bit hb[j-L] otherwise.  All gates[gate_begin .. gate_begin+n_gates) are
- * applied to the tile before it is written back.                                             */
+ * j < L and index bit hb[j-L] otherwise.  The descriptor stream gates[gate_begin .. gate_begin+
+ * n_gates) is applied to the tile before it is written back.                                             */
 typedef struct tqb_pass {
   int32_t m;
   int32_t L;
   int32_t gate_begin;
   int32_t n_gates;
   int32_t max_dense_k; /* largest k of a DENSE gate in the pass (selects the kernel variant)  */
+  int32_t mat_begin;   /* the pass's matrices are mats[mat_begin .. mat_begin+mat_count): they  */
+  int32_t mat_count;   /* are staged in shared memory once per CTA; 0 = read from global memory */
   int8_t hb[TQB_MAX_TILE_HIGH];
-} tqb_pass; /* 36 bytes */
+} tqb_pass; /* 44 bytes */
 
 /* ---- library ------------------------------------------------------------------------- */
 int tqb_abi_version(void);

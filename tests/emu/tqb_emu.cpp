@@ -26,15 +26,15 @@ static void run_pass(cplx<T> *state, const TileGeom &geo, long long batch, const
     const uint64_t base = tile_base(geo, t);
     cplx<T> *sb = state + (b << geo.n);
     for (int tid = 0; tid < nthreads; ++tid) tile_load<T, V>(tile.data(), sb, geo, roff.data(), base, tid, nthreads);
-    for (int gi = 0; gi < n_gates; ++gi) {
-      const tqb_gate &g = gates[gi];
-      const cplx<T> *mat = mats + g.mat_off + (size_t)b * g.mat_bstride;
+    for (int gi = 0; gi < n_gates;) {
+      int step = 1;
       for (int tid = 0; tid < nthreads; ++tid) {
         if (max_dense_k > 2)
-          tile_apply_gate<T, 4>(tile.data(), geo, roff.data(), geo.global_base | base, g, mat, tid, nthreads);
+          step = tile_exec_unit<T, 4>(tile.data(), geo, roff.data(), geo.global_base | base, gates + gi, mats, (size_t)b, tid, nthreads);
         else
-          tile_apply_gate<T, 2>(tile.data(), geo, roff.data(), geo.global_base | base, g, mat, tid, nthreads);
+          step = tile_exec_unit<T, 2>(tile.data(), geo, roff.data(), geo.global_base | base, gates + gi, mats, (size_t)b, tid, nthreads);
       }
+      gi += step;
     }
     for (int tid = 0; tid < nthreads; ++tid) tile_store<T, V>(tile.data(), sb, geo, roff.data(), base, tid, nthreads);
   }
@@ -47,6 +47,7 @@ extern "C" int tqb_emu_run_passes(void *state, int n, long long batch, int dtype
     const tqb_pass &ps = passes[p];
     TileGeom geo;
     geo.n = n; geo.m = ps.m; geo.L = ps.L; geo.h = ps.m - ps.L; geo.global_base = global_base;
+    geo.mat_begin = 0; geo.mat_count = 0;
     if (geo.m > n || geo.L > geo.m || geo.h > TQB_MAX_TILE_HIGH) return -1;
     int prev = ps.L - 1;
     for (int i = 0; i < TQB_MAX_TILE_HIGH; ++i) {

@@ -39,10 +39,11 @@ def test_struct_layouts_match_header():
 
     class Pass(ctypes.Structure):
         _fields_ = [("m", ctypes.c_int32), ("L", ctypes.c_int32), ("gate_begin", ctypes.c_int32), ("n_gates", ctypes.c_int32),
-                    ("max_dense_k", ctypes.c_int32), ("hb", ctypes.c_int8 * 16)]
+                    ("max_dense_k", ctypes.c_int32), ("mat_begin", ctypes.c_int32), ("mat_count", ctypes.c_int32),
+                    ("hb", ctypes.c_int8 * 16)]
 
     assert ctypes.sizeof(Gate) == _lib.GATE_DTYPE.itemsize == 48
-    assert ctypes.sizeof(Pass) == _lib.PASS_DTYPE.itemsize == 36
+    assert ctypes.sizeof(Pass) == _lib.PASS_DTYPE.itemsize == 44
     for name, _ in Gate._fields_:
         assert getattr(Gate, name).offset == _lib.GATE_DTYPE.fields[name][1], name
     for name, _ in Pass._fields_:

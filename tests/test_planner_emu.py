@@ -28,7 +28,7 @@ def test_random_circuits(n, m, L, dtype):
     rng = np.random.default_rng(n * 100 + m)
     ops = random_ops(rng, n, 120)
     ref, _ = O.evolve_ops(n, ops, mode="run")
-    prog = P.compile_program(_lower(ops, n), n, P.TileConfig(m=m, L=L))
+    prog = P.compile_program(_lower(ops, n), n, P.TileConfig(m=m, L=L), itemsize=np.dtype(dtype).itemsize)
     psi0 = np.zeros(1 << n, dtype=dtype)
     psi0[0] = 1
     out = run_program_emulated(prog, psi0)

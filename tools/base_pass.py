@@ -23,7 +23,7 @@ def main():
     _lib.ensure_device(0)
     st = P.new_state(n, dtype=tdt, device=dev)
     op = (gate, q) if gate in ("h", "x", "s") else ((gate, q, 0.3) if gate in ("rx", "rz") else (gate, q, (q + 1) % n))
-    prog = compile_program([lower_op(op, n, mode="run")], n, TileConfig(m=m, L=L, threads=thr))
+    prog = compile_program([lower_op(op, n, mode="run")], n, TileConfig(m=m, L=L, threads=thr), itemsize=B)
     dp = P.DeviceProgram(prog, dev, tdt)
     dp.run(st)
     torch.cuda.synchronize()

@@ -50,7 +50,7 @@ def main():
                                (11 if B == 16 else 12, 5 if B == 16 else 6, 256, 3)]:
             for q in (n - 1, n // 2, 0):
                 g = lower_op(("h", q), n, mode="run")
-                prog = compile_program([g], n, TileConfig(m=m, L=L, threads=thr, ctas_per_sm=cps))
+                prog = compile_program([g], n, TileConfig(m=m, L=L, threads=thr, ctas_per_sm=cps), itemsize=B)
                 ms = time_prog(prog, state, 3)
                 print(f"BASE B={B} m={m} L={L} thr={thr} cps={cps} qubit={q} ms={ms:.3f} GBps={bytes_pass / ms / 1e6:.0f}", flush=True)
         params = np.random.default_rng(1234).uniform(-np.pi, np.pi, 2 * layers * n)
@@ -61,7 +61,7 @@ def main():
                 m += 1; L += 1
             if (B << m) > 128 * 1024:
                 continue
-            prog = compile_program(lg, n, TileConfig(m=m, L=L, threads=thr, ctas_per_sm=cps))
+            prog = compile_program(lg, n, TileConfig(m=m, L=L, threads=thr, ctas_per_sm=cps), itemsize=B)
             ms = time_prog(prog, state, 1)
             print(f"HEA B={B} m={m} L={L} thr={thr} cps={cps} passes={prog.n_passes} ms={ms:.1f} ms/pass={ms / prog.n_passes:.2f} "
                   f"gates/s={len(ops) / ms * 1e3:.0f} GBps={prog.n_passes * bytes_pass / ms / 1e6:.0f}", flush=True)

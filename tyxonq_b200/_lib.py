@@ -18,6 +18,7 @@ LIB_PATH = PKG / "libtyxonq_b200.so"
 
 TQB_C64, TQB_C128 = 0, 1
 GATE_DENSE, GATE_DIAG, GATE_PAIR, GATE_SWAP = 0, 1, 2, 3
+GATE_MICRO, GATE_RDENSE, GATE_RDIAG, GATE_RSWAP = 16, 32, 33, 35
 MAX_GATE_BITS = 8
 MAX_TILE_HIGH = 16
 SCAN_BLOCK = 4096
@@ -31,10 +32,11 @@ GATE_DTYPE = np.dtype([
 ], align=True)
 PASS_DTYPE = np.dtype([
     ("m", "<i4"), ("L", "<i4"), ("gate_begin", "<i4"), ("n_gates", "<i4"), ("max_dense_k", "<i4"),
+    ("mat_begin", "<i4"), ("mat_count", "<i4"),
     ("hb", "i1", (MAX_TILE_HIGH,)),
 ], align=True)
 assert GATE_DTYPE.itemsize == 48, GATE_DTYPE.itemsize
-assert PASS_DTYPE.itemsize == 36, PASS_DTYPE.itemsize
+assert PASS_DTYPE.itemsize == 44, PASS_DTYPE.itemsize
 
 _vp = C.c_void_p
 _i = C.c_int

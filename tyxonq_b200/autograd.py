@@ -109,7 +109,7 @@ class _CircuitState(torch.autograd.Function):
             state = P.new_state(n, dtype=engine.dtype, device=engine.device)
         tile = engine.tile or default_tile(n, state.element_size(), 1)
         if gates:
-            P.DeviceProgram(compile_program(gates, n, tile), state.device, state.dtype).run(state)
+            P.DeviceProgram(compile_program(gates, n, tile, itemsize=state.element_size()), state.device, state.dtype).run(state)
         ctx.engine = engine
         ctx.gates = gates
         ctx.n = n
@@ -133,7 +133,7 @@ class _CircuitState(torch.autograd.Function):
 
         def flush() -> None:
             if pending:
-                P.DeviceProgram(compile_program(pending, n, tile), dev, dtype).run(kb)
+                P.DeviceProgram(compile_program(pending, n, tile, itemsize=kb.element_size()), dev, dtype).run(kb)
                 pending.clear()
 
         for g in reversed(gates):

@@ -44,16 +44,18 @@ Workspace *workspace() {
 // MAXK = 2: light variant (<= 512 threads, <= 64 registers); MAXK = 4: heavy variant
 // (<= 256 threads, <= 128 registers) for passes that carry dense 3- and 4-qubit blocks.
 template <typename T, int V, int MAXK>
-__global__ void __launch_bounds__(MAXK <= 2 ? 512 : 256, 2)
+__global__ void __launch_bounds__(256, MAXK <= 2 ? 3 : 2)
 tile_pass_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                  const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
   uint64_t *roff = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(cplx<T>) << geo.m));
-  tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
+  cplx<T> *smats = reinterpret_cast<cplx<T> *>(roff + (1u << geo.h));
+  tqb_gate *sg = reinterpret_cast<tqb_gate *>(smats + geo.mat_count);
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   for (uint32_t j = tid; j < (1u << geo.h); j += nthreads) roff[j] = run_offset(geo, j);
+  for (int i = tid; i < geo.mat_count; i += nthreads) smats[i] = mats[geo.mat_begin + i];
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(gates);
     uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
@@ -61,6 +63,7 @@ tile_pass_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long lon
     for (int i = tid; i < nw; i += nthreads) dst[i] = src[i];
   }
   __syncthreads();
+  const cplx<T> *mat_base = geo.mat_count > 0 ? smats - geo.mat_begin : mats;
 
   const int tb = geo.n - geo.m;  // tile-index bits per batch member
   const unsigned long long total = (unsigned long long)batch << tb;
@@ -71,10 +74,8 @@ tile_pass_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long lon
     cplx<T> *sb = state + (b << geo.n);
     tile_load<T, V>(tile, sb, geo, roff, base, tid, nthreads);
     __syncthreads();
-    for (int gi = 0; gi < n_gates; ++gi) {
-      const tqb_gate &g = sg[gi];
-      const cplx<T> *mat = mats + g.mat_off + (size_t)b * g.mat_bstride;
-      tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, g, mat, tid, nthreads);
+    for (int gi = 0; gi < n_gates;) {
+      gi += tile_exec_unit<T, MAXK>(tile, geo, roff, geo.global_base | base, sg + gi, mat_base, (size_t)b, tid, nthreads);
       __syncthreads();
     }
     tile_store<T, V>(tile, sb, geo, roff, base, tid, nthreads);
@@ -122,7 +123,7 @@ __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename T, int MAXK>
-__global__ void __launch_bounds__(MAXK <= 2 ? 512 : 256, 2)
+__global__ void __launch_bounds__(256, MAXK <= 2 ? 3 : 2)
 tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                      const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -130,11 +131,14 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
   cplx<T> *buf[2] = {reinterpret_cast<cplx<T> *>(smem_raw), reinterpret_cast<cplx<T> *>(smem_raw + tile_bytes)};
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * tile_bytes);  // 2 mbarriers (16 bytes)
   uint64_t *roff = bars + 2;
-  tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
+  cplx<T> *smats = reinterpret_cast<cplx<T> *>(roff + (1u << geo.h));
+  tqb_gate *sg = reinterpret_cast<tqb_gate *>(smats + geo.mat_count);
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   for (uint32_t j = tid; j < (1u << geo.h); j += nthreads) roff[j] = run_offset(geo, j);
+  for (int i = tid; i < geo.mat_count; i += nthreads) smats[i] = mats[geo.mat_begin + i];
+  const cplx<T> *mat_base = geo.mat_count > 0 ? smats - geo.mat_begin : mats;
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(gates);
     uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
@@ -180,10 +184,8 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
     const unsigned long long bm = tt >> tb;
     const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
     cplx<T> *tile = buf[b];
-    for (int gi = 0; gi < n_gates; ++gi) {
-      const tqb_gate &g = sg[gi];
-      const cplx<T> *mat = mats + g.mat_off + (size_t)bm * g.mat_bstride;
-      tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, g, mat, tid, nthreads);
+    for (int gi = 0; gi < n_gates;) {
+      gi += tile_exec_unit<T, MAXK>(tile, geo, roff, geo.global_base | base, sg + gi, mat_base, (size_t)bm, tid, nthreads);
       __syncthreads();
     }
     fence_proxy_async();  // generic-proxy writes of the tile -> visible to the bulk-store engine
@@ -213,9 +215,10 @@ __global__ void init_basis_kernel(cplx<T> *state, int n, long long batch, unsign
 template <typename T, int V, int MAXK>
 static int launch_pass(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
                        const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st) {
-  const int max_threads = MAXK <= 2 ? 512 : 256;
+  const int max_threads = 256;
   if (threads > max_threads) threads = max_threads;
-  const size_t smem = (sizeof(cplx<T>) << geo.m) + (sizeof(uint64_t) << geo.h) + (size_t)n_gates * sizeof(tqb_gate);
+  const size_t smem = (sizeof(cplx<T>) << geo.m) + (sizeof(uint64_t) << geo.h) + (size_t)geo.mat_count * sizeof(cplx<T>) +
+                      (size_t)n_gates * sizeof(tqb_gate);
   TQB_REQUIRE(smem <= (size_t)ws.max_smem_optin, "tqb_run_passes: tile + gate list exceed shared memory");
   auto kern = tile_pass_kernel<T, V, MAXK>;
   static thread_local bool configured = false;  // one per template instantiation and host thread
@@ -244,9 +247,10 @@ template <typename T, int MAXK>
 static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
                            const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st, bool *used) {
   *used = false;
-  const int max_threads = MAXK <= 2 ? 512 : 256;
+  const int max_threads = 256;
   if (threads > max_threads) threads = max_threads;
-  const size_t smem = 2 * (sizeof(cplx<T>) << geo.m) + 16 + (sizeof(uint64_t) << geo.h) + (size_t)n_gates * sizeof(tqb_gate);
+  const size_t smem = 2 * (sizeof(cplx<T>) << geo.m) + 16 + (sizeof(uint64_t) << geo.h) +
+                      (size_t)geo.mat_count * sizeof(cplx<T>) + (size_t)n_gates * sizeof(tqb_gate);
   if (smem > (size_t)ws.max_smem_optin) return 0;  // caller falls back to the single-buffer kernel
   auto kern = tile_pass_tma_kernel<T, MAXK>;
   static thread_local bool configured = false;
@@ -358,6 +362,8 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
     TQB_REQUIRE(ps.n_gates >= 1 && ps.gate_begin >= 0, "tqb_run_passes: empty pass");
     TileGeom geo;
     geo.n = n; geo.m = ps.m; geo.L = ps.L; geo.h = h; geo.global_base = global_base;
+    geo.mat_begin = ps.mat_begin; geo.mat_count = ps.mat_count;
+    TQB_REQUIRE(ps.mat_begin >= 0 && ps.mat_count >= 0 && ps.mat_count <= 4096, "tqb_run_passes: bad staged matrix range");
     int prev = ps.L - 1;
     for (int i = 0; i < TQB_MAX_TILE_HIGH; ++i) {
       geo.hb[i] = i < h ? ps.hb[i] : 0;

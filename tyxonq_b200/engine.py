@@ -62,7 +62,7 @@ class StatevectorEngine:
             from .planner import compile_program, default_tile
             from .fuse import fuse
             tile = self.tile or default_tile(n, state.element_size(), batch)
-            prog = compile_program(fuse(pending), n, tile)
+            prog = compile_program(fuse(pending), n, tile, itemsize=state.element_size())
             dp = P.DeviceProgram(prog, state.device, state.dtype)
             dp.run(state)
             self.last_h2d_bytes += dp.h2d_bytes
@@ -125,7 +125,7 @@ class StatevectorEngine:
         batch = state.unsqueeze(0).repeat(m, 1).contiguous()
         g = dense_gate(np.stack([np.asarray(k, dtype=np.complex128).reshape(2, 2) for k in kraus]), [q], n)
         from .planner import compile_program, default_tile
-        prog = compile_program([g], n, self.tile or default_tile(n, state.element_size(), m), batch_mats=m)
+        prog = compile_program([g], n, self.tile or default_tile(n, state.element_size(), m), batch_mats=m, itemsize=state.element_size())
         P.DeviceProgram(prog, state.device, state.dtype).run(batch)
         p = P.norm2(batch).cpu().numpy()
         self.last_d2h_bytes += p.nbytes

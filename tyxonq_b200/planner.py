@@ -66,6 +66,7 @@ class Program:
     n_gates_in: int             # gates before planning (for gates/s accounting)
     tile: TileConfig
     order: List[int]            # order[i] = index (into the input list) of the i-th scheduled gate
+    itemsize: int = 16          # 16: compiled for complex128 (R = 3), 8: complex64 (R = 4)
 
     @property
     def n_passes(self) -> int:
@@ -138,20 +139,106 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
     return out
 
 
-def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_mats: int = 1) -> Program:
+_PERM_SWAP_BITS = [0, 2, 1, 3]  # 2-bit index with its bits exchanged
+
+
+def _reg_capable(g: LGate, R: int) -> bool:
+    if g.kind == DENSE:
+        return g.k <= 2
+    if g.kind == DIAG:
+        return g.k <= 6
+    if g.kind == SWAP:
+        return g.k <= R
+    if g.kind == PAIR:
+        return g.k == 2 and g.zmask == 0
+    return False
+
+
+def micro_schedule(chosen: Sequence[int], gates: Sequence[LGate], local_of: dict, R: int, m: int):
+    """Split one pass's gate list into units: ("micro", reg_bits(local, ascending), [gate idx]) runs whose
+    non-diagonal gates act inside R register bits, and ("smem", gate idx) single shared-memory sweeps."""
+    units = []
+    remaining = list(chosen)
+    if m < R:
+        return [("smem", i) for i in remaining]
+    while remaining:
+        first = gates[remaining[0]]
+        if not _reg_capable(first, R):
+            units.append(("smem", remaining.pop(0)))
+            continue
+        rset: List[int] = []
+        picked: List[int] = []
+        rest: List[int] = []
+        blocked = 0
+        blocked_nd = 0
+        for i in remaining:
+            g = gates[i]
+            mk = g.mask
+            if g.kind == DIAG and _reg_capable(g, R):
+                if mk & blocked_nd:
+                    blocked |= mk
+                    rest.append(i)
+                else:
+                    picked.append(i)
+                continue
+            if (mk & blocked) or not _reg_capable(g, R):
+                blocked |= mk
+                blocked_nd |= mk
+                rest.append(i)
+                continue
+            need = [local_of[b] for b in g.bits if local_of[b] not in rset]
+            if len(rset) + len(need) <= R:
+                rset += need
+                picked.append(i)
+            else:
+                blocked |= mk
+                blocked_nd |= mk
+                rest.append(i)
+        p = 0
+        while len(rset) < R:  # pad with unused tile-local bits
+            if p not in rset:
+                rset.append(p)
+            p += 1
+        units.append(("micro", sorted(rset), picked))
+        remaining = rest
+    return units
+
+
+def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_mats: int = 1, micro: bool = True,
+                    itemsize: int = 16) -> Program:
     """Pack scheduled gates into the ABI arrays.  ``batch_mats`` > 1: every gate's ``data`` has a
-    leading batch axis (one matrix per batch member)."""
+    leading batch axis (one matrix per batch member).  ``micro``: group gates into register
+    micro-passes (R = 3 register bits for complex128, 4 for complex64 -- ``itemsize`` 16 / 8)."""
     m_eff = min(tile.m, n)
     tile = TileConfig(m=m_eff, L=min(tile.L, m_eff), threads=tile.threads, ctas_per_sm=tile.ctas_per_sm,
                       max_gates=tile.max_gates)
+    R = 3 if itemsize == 16 else 4
     sched = schedule(gates, n, tile)
-    ng = sum(len(c) for _, c in sched)
     passes = np.zeros(len(sched), dtype=_lib.PASS_DTYPE)
-    garr = np.zeros(ng, dtype=_lib.GATE_DTYPE)
+    descs: List[np.void] = []
     mats: List[np.ndarray] = []
     mat_off = 0
-    gi = 0
     order: List[int] = []
+
+    def new_desc() -> np.ndarray:
+        return np.zeros(1, dtype=_lib.GATE_DTYPE)
+
+    def add_matrix(e, data: np.ndarray) -> None:
+        nonlocal mat_off
+        d = np.asarray(data, dtype=C128)
+        if batch_mats > 1:
+            d = d.reshape(batch_mats, -1)
+            e["mat_off"] = mat_off
+            e["mat_bstride"] = d.shape[1]
+            mats.append(d.reshape(-1))
+            mat_off += d.size
+        else:
+            d = d.reshape(-1)
+            e["mat_off"] = mat_off
+            e["mat_bstride"] = 0
+            mats.append(d)
+            mat_off += d.size
+
     for pi, (hb, chosen) in enumerate(sched):
         L = tile.L
         assert len(hb) == m_eff - L, (hb, m_eff, L)
@@ -161,49 +248,100 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
         ps = passes[pi]
         ps["m"] = m_eff
         ps["L"] = L
-        ps["gate_begin"] = gi
-        ps["n_gates"] = len(chosen)
+        ps["gate_begin"] = len(descs)
+        ps["mat_begin"] = mat_off
         for j, p in enumerate(hb):
             ps["hb"][j] = p
         maxk = 0
-        for idx in chosen:
-            g = gates[idx]
-            e = garr[gi]
-            e["kind"] = g.kind
-            e["k"] = g.k
-            if g.kind == DIAG:
-                assert g.k <= 6, "diagonal tables are limited to 6 bits"
-                for j, b in enumerate(g.bits):  # tile-local position, or 64 + index bit when outside the tile
-                    e["bits"][j] = local_of[b] if b in local_of else 64 + b
-            else:
-                assert g.k <= 4, "dense / pair gates are limited to 4 bits"
-                loc = [local_of[b] for b in g.bits]
-                for j, b in enumerate(loc):
-                    e["bits"][j] = b
-                for j, b in enumerate(sorted(loc)):
-                    e["sbits"][j] = b
-                if g.kind in (PAIR, SWAP):
-                    e["off_a"] = sum(((g.pat_a >> j) & 1) << loc[j] for j in range(g.k))
-                    e["off_b"] = sum(((g.pat_b >> j) & 1) << loc[j] for j in range(g.k))
-                    e["zmask"] = g.zmask
+        units = micro_schedule(chosen, gates, local_of, R, m_eff) if micro else [("smem", i) for i in chosen]
+        for unit in units:
+            if unit[0] == "smem":
+                g = gates[unit[1]]
+                e = new_desc()
+                e["kind"] = g.kind
+                e["k"] = g.k
+                if g.kind == DIAG:
+                    assert g.k <= 6, "diagonal tables are limited to 6 bits"
+                    for j, b in enumerate(g.bits):  # tile-local position, or 64 + index bit when outside the tile
+                        e["bits"][0, j] = local_of[b] if b in local_of else 64 + b
                 else:
-                    maxk = max(maxk, g.k)
-            d = np.asarray(g.data, dtype=C128)
-            if batch_mats > 1:
-                d = d.reshape(batch_mats, -1)
-                per = d.shape[1]
-                e["mat_off"] = mat_off
-                e["mat_bstride"] = per
-                mats.append(d.reshape(-1))
-                mat_off += per * batch_mats
-            else:
-                d = d.reshape(-1)
-                e["mat_off"] = mat_off
-                e["mat_bstride"] = 0
-                mats.append(d)
-                mat_off += d.size
-            order.append(idx)
-            gi += 1
+                    assert g.k <= 4, "dense / pair gates are limited to 4 bits"
+                    loc = [local_of[b] for b in g.bits]
+                    for j, b in enumerate(loc):
+                        e["bits"][0, j] = b
+                    for j, b in enumerate(sorted(loc)):
+                        e["sbits"][0, j] = b
+                    if g.kind in (PAIR, SWAP):
+                        e["off_a"] = sum(((g.pat_a >> j) & 1) << loc[j] for j in range(g.k))
+                        e["off_b"] = sum(((g.pat_b >> j) & 1) << loc[j] for j in range(g.k))
+                        e["zmask"] = g.zmask
+                    else:
+                        maxk = max(maxk, g.k)
+                add_matrix(e, g.data)
+                descs.append(e)
+                order.append(unit[1])
+                continue
+            _, rbits, picked = unit
+            hdr = new_desc()
+            hdr["kind"] = _lib.GATE_MICRO
+            hdr["k"] = R
+            for j, b in enumerate(rbits):
+                hdr["bits"][0, j] = b
+            hdr["off_a"] = len(picked)
+            descs.append(hdr)
+            rho_of = {b: j for j, b in enumerate(rbits)}
+            for idx in picked:
+                g = gates[idx]
+                e = new_desc()
+                e["k"] = g.k
+                if g.kind == DIAG:
+                    e["kind"] = _lib.GATE_RDIAG
+                    for j, b in enumerate(g.bits):
+                        if b in local_of and local_of[b] in rho_of:
+                            rho = rho_of[local_of[b]]
+                            e["bits"][0, j] = 32 + rho
+                            e["sbits"][0, rho] = 1 << j
+                        elif b in local_of:
+                            e["bits"][0, j] = local_of[b]
+                        else:
+                            e["bits"][0, j] = 64 + b
+                    add_matrix(e, g.data)
+                elif g.kind == SWAP:
+                    e["kind"] = _lib.GATE_RSWAP
+                    rho = [rho_of[local_of[b]] for b in g.bits]
+                    e["off_a"] = sum(1 << r for r in rho)
+                    aval = sum(((g.pat_a >> j) & 1) << rho[j] for j in range(g.k))
+                    bval = sum(((g.pat_b >> j) & 1) << rho[j] for j in range(g.k))
+                    e["off_b"] = aval
+                    e["zmask"] = aval ^ bval
+                    add_matrix(e, g.data)
+                else:
+                    e["kind"] = _lib.GATE_RDENSE
+                    data = g.data
+                    if g.kind == PAIR:  # 2x2 block on (pat_a, pat_b) of a 2-bit index, identity elsewhere
+                        assert batch_mats == 1
+                        M4 = np.eye(4, dtype=C128)
+                        blk = np.asarray(g.data[:4]).reshape(2, 2)
+                        ab = [g.pat_a, g.pat_b]
+                        for r_ in range(2):
+                            for c_ in range(2):
+                                M4[ab[r_], ab[c_]] = blk[r_, c_]
+                        data = M4
+                    rho = [rho_of[local_of[b]] for b in g.bits]
+                    if g.k == 2 and rho[0] > rho[1]:  # canonical order: matrix-index bit 0 on the lower register bit
+                        rho = [rho[1], rho[0]]
+                        d4 = np.asarray(data, dtype=C128).reshape(-1, 4, 4)
+                        data = d4[:, _PERM_SWAP_BITS][:, :, _PERM_SWAP_BITS]
+                    for j, r in enumerate(rho):
+                        e["bits"][0, j] = r
+                    e["k"] = len(rho)
+                    add_matrix(e, data)
+                descs.append(e)
+                order.append(idx)
+        ps["n_gates"] = len(descs) - int(ps["gate_begin"])
         ps["max_dense_k"] = maxk
+        cnt = mat_off - int(ps["mat_begin"])
+        ps["mat_count"] = cnt if (batch_mats == 1 and cnt <= 4096) else 0
+    garr = np.concatenate(descs) if descs else np.zeros(0, dtype=_lib.GATE_DTYPE)
     flat = np.concatenate(mats) if mats else np.zeros(0, dtype=C128)
-    return Program(n=n, passes=passes, gates=garr, mats=flat, n_gates_in=len(gates), tile=tile, order=order)
+    return Program(n=n, passes=passes, gates=garr, mats=flat, n_gates_in=len(gates), tile=tile, order=order, itemsize=itemsize)

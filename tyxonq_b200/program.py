@@ -58,6 +58,8 @@ class DeviceProgram:
         self.prog = prog
         self.device = torch.device(device)
         self.dtype = dtype
+        if prog.itemsize != (16 if dtype == torch.complex128 else 8):
+            raise _lib.TqbError("program was compiled for the other complex dtype (register tile size differs)")
         self.h2d_bytes = 0
         self._passes = np.ascontiguousarray(prog.passes)
         with torch.cuda.device(self.device):
@@ -101,7 +103,7 @@ def apply_gates(state: torch.Tensor, gates: Sequence[LGate], *, tile: Optional[T
         return state
     ptr, n, batch, dt, _ = _prep(state)
     tile = tile or default_tile(n, state.element_size(), batch)
-    prog = compile_program(list(gates), n, tile)
+    prog = compile_program(list(gates), n, tile, itemsize=state.element_size())
     DeviceProgram(prog, state.device, state.dtype).run(state, global_base=global_base)
     return state
 
