@@ -40,17 +40,10 @@ extern "C" {
                          /* all other patterns untouched (cry, iswap, controlled-U, UCC Givens)*/
 #define TQB_GATE_SWAP 3  /* exchange the amplitudes of pattern A and pattern B (x, cx, swap):   */
                          /* a PAIR gate with the matrix [[0,1],[1,0]], done without arithmetic  */
-
-/* Register micro-passes (planned by the host, executed inside a pass): a TQB_GATE_MICRO header
- * (k = R register bits, bits[] = their tile-local positions ascending, off_a = number of register
- * gates that follow) and then R-gates whose bits[] index the register bits 0..R-1.
- * R = 3 for complex128 (8 amplitudes per thread), 4 for complex64 (16 amplitudes per thread).   */
-#define TQB_GATE_MICRO 16
-#define TQB_GATE_RDENSE 32 /* k = 1: bits[0]; k = 2: matrix-index bit 0 on bits[0] < bits[1] (bit 1)   */
-#define TQB_GATE_RDIAG 33  /* bits[j]: 32+rho register bit | <32 tile-local bit | 64+p outside tile;    */
-                           /* sbits[rho] = weight (1<<j) of register bit rho in the table index         */
-#define TQB_GATE_RSWAP 35  /* off_a = mask of the gate's register bits, off_b = pattern A on them,      */
-                           /* zmask = A xor B (register-index space)                                     */
+#define TQB_GATE_MUX 4   /* 1-qubit gate on tile-local bit bits[0] whose 2x2 is selected by one  */
+                         /* control bit bits[1] (< 64 tile-local, 64+p index bit p outside the  */
+                         /* tile): U0 at mat_off, U1 at mat_off+4.  cx fused with a 1-qubit gate */
+                         /* on its target costs one sweep and needs only the TARGET tile-local. */
 
 #define TQB_MAX_DENSE_K 4
 #define TQB_MAX_GATE_BITS 8

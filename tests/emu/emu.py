@@ -15,7 +15,6 @@ def run_program_emulated(prog, state: np.ndarray, *, batch: int = 1, global_base
     lib.tqb_emu_run_passes.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_ulonglong, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_void_p, C.c_int]
     st = np.ascontiguousarray(state).copy()
-    assert prog.itemsize == st.dtype.itemsize, "program compiled for the other dtype"
     dtype = 1 if st.dtype == np.complex128 else 0
     mats = np.ascontiguousarray(prog.mats.astype(st.dtype))
     passes = np.ascontiguousarray(prog.passes)

@@ -26,15 +26,13 @@ static void run_pass(cplx<T> *state, const TileGeom &geo, long long batch, const
     const uint64_t base = tile_base(geo, t);
     cplx<T> *sb = state + (b << geo.n);
     for (int tid = 0; tid < nthreads; ++tid) tile_load<T, V>(tile.data(), sb, geo, roff.data(), base, tid, nthreads);
-    for (int gi = 0; gi < n_gates;) {
-      int step = 1;
+    for (int gi = 0; gi < n_gates; ++gi) {
       for (int tid = 0; tid < nthreads; ++tid) {
         if (max_dense_k > 2)
-          step = tile_exec_unit<T, 4>(tile.data(), geo, roff.data(), geo.global_base | base, gates + gi, mats, (size_t)b, tid, nthreads);
+          tile_apply_gate<T, 4>(tile.data(), geo, roff.data(), geo.global_base | base, gates[gi], mats, (size_t)b, tid, nthreads);
         else
-          step = tile_exec_unit<T, 2>(tile.data(), geo, roff.data(), geo.global_base | base, gates + gi, mats, (size_t)b, tid, nthreads);
+          tile_apply_gate<T, 2>(tile.data(), geo, roff.data(), geo.global_base | base, gates[gi], mats, (size_t)b, tid, nthreads);
       }
-      gi += step;
     }
     for (int tid = 0; tid < nthreads; ++tid) tile_store<T, V>(tile.data(), sb, geo, roff.data(), base, tid, nthreads);
   }

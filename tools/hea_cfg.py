@@ -33,7 +33,7 @@ def main():
         f = [int(x) for x in cfg.split(":")]
         m, L, thr = f[:3]
         cps = f[3] if len(f) > 3 else 0
-        prog = compile_program(lg, n, TileConfig(m=m, L=L, threads=thr, ctas_per_sm=cps), itemsize=B, micro=MICRO)
+        prog = compile_program(lg, n, TileConfig(m=m, L=L, threads=thr, ctas_per_sm=cps), itemsize=B)
         dp = P.DeviceProgram(prog, dev, tdt)
         dp.run(st); torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

@@ -269,175 +269,55 @@ TQB_HD void gate_diag(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, c
   }
 }
 
-// ---- register micro-passes --------------------------------------------------------------------
-// A micro-pass keeps 2^R amplitudes per thread in registers (the R "register bits" are tile-local
-// bits chosen by the host planner) and applies a whole run of gates to them before they go back
-// to shared memory: one LDS/STS round trip and one barrier per micro-pass instead of per gate.
-// All register indexing is compile-time; the runtime gate positions select among unrolled cases.
-template <typename T, int R, int P>
-TQB_HD void reg_dense1_p(cplx<T> (&v)[1 << R], const cplx<T> *M) {
+// MUX: dense 1-qubit gate on tile-local bit bits[0] whose 2x2 matrix is selected by ONE control
+// bit (matrix U0 at mat[0..4) when the control is 0, U1 at mat[4..8) when it is 1).  This is
+// what "cx followed / preceded by a 1-qubit gate on its target" fuses to on the host: the sweep
+// costs the same as a plain 1-qubit gate.  bits[1] < 64: the control is tile-local bit bits[1];
+// bits[1] >= 64: it is index bit bits[1] - 64 outside the tile (constant for the whole tile).
+template <typename T>
+TQB_HD void mux_sweep(cplx<T> *tile, uint32_t ngroups, uint32_t p0, uint32_t p1, bool two, uint32_t fixed,
+                      uint32_t tstride, const cplx<T> *M, int tid, int nthreads) {
   const cplx<T> m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
-#pragma unroll
-  for (int s = 0; s < (1 << R); ++s) {
-    if (s & (1 << P)) continue;
-    const cplx<T> a = v[s], b = v[s | (1 << P)];
+#pragma unroll 4
+  for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
+    uint32_t base = ((gi >> p0) << (p0 + 1u)) | (gi & ((1u << p0) - 1u));
+    if (two) base = ((base >> p1) << (p1 + 1u)) | (base & ((1u << p1) - 1u));
+    base |= fixed;
+    const cplx<T> a = tile[base], b = tile[base + tstride];
     cplx<T> x{0, 0}, y{0, 0};
     cmac(x, m00, a); cmac(x, m01, b);
     cmac(y, m10, a); cmac(y, m11, b);
-    v[s] = x;
-    v[s | (1 << P)] = y;
-  }
-}
-template <typename T, int R>
-TQB_HD void reg_dense1(cplx<T> (&v)[1 << R], int p, const cplx<T> *M) {
-  switch (p) {
-    case 0: reg_dense1_p<T, R, 0>(v, M); break;
-    case 1: if (R > 1) reg_dense1_p<T, R, (R > 1 ? 1 : 0)>(v, M); break;
-    case 2: if (R > 2) reg_dense1_p<T, R, (R > 2 ? 2 : 0)>(v, M); break;
-    case 3: if (R > 3) reg_dense1_p<T, R, (R > 3 ? 3 : 0)>(v, M); break;
-    default: break;
-  }
-}
-// matrix-index bit 0 lives on register bit P, bit 1 on register bit Q (P < Q: canonical order)
-template <typename T, int R, int P, int Q>
-TQB_HD void reg_dense2_pq(cplx<T> (&v)[1 << R], const cplx<T> *M) {
-#pragma unroll
-  for (int s = 0; s < (1 << R); ++s) {
-    if (s & ((1 << P) | (1 << Q))) continue;
-    const cplx<T> a0 = v[s], a1 = v[s | (1 << P)], a2 = v[s | (1 << Q)], a3 = v[s | (1 << P) | (1 << Q)];
-    cplx<T> o[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      cplx<T> acc{0, 0};
-      cmac(acc, M[4 * r + 0], a0); cmac(acc, M[4 * r + 1], a1);
-      cmac(acc, M[4 * r + 2], a2); cmac(acc, M[4 * r + 3], a3);
-      o[r] = acc;
-    }
-    v[s] = o[0]; v[s | (1 << P)] = o[1]; v[s | (1 << Q)] = o[2]; v[s | (1 << P) | (1 << Q)] = o[3];
-  }
-}
-template <typename T, int R>
-TQB_HD void reg_dense2(cplx<T> (&v)[1 << R], int p, int q, const cplx<T> *M) {
-  switch (p * 4 + q) {
-    case 1: if (R > 1) reg_dense2_pq<T, R, 0, (R > 1 ? 1 : 1)>(v, M); break;
-    case 2: if (R > 2) reg_dense2_pq<T, R, 0, (R > 2 ? 2 : 1)>(v, M); break;
-    case 3: if (R > 3) reg_dense2_pq<T, R, 0, (R > 3 ? 3 : 1)>(v, M); break;
-    case 6: if (R > 2) reg_dense2_pq<T, R, (R > 2 ? 1 : 0), (R > 2 ? 2 : 1)>(v, M); break;
-    case 7: if (R > 3) reg_dense2_pq<T, R, (R > 3 ? 1 : 0), (R > 3 ? 3 : 1)>(v, M); break;
-    case 11: if (R > 3) reg_dense2_pq<T, R, (R > 3 ? 2 : 0), (R > 3 ? 3 : 1)>(v, M); break;
-    default: break;
-  }
-}
-// exchange v[s] <-> v[s ^ F] wherever s (or its partner) matches pattern `aval` on the bits `gmask`
-template <typename T, int R, int F>
-TQB_HD void reg_swap_f(cplx<T> (&v)[1 << R], uint32_t gmask, uint32_t aval) {
-#pragma unroll
-  for (int s = 0; s < (1 << R); ++s) {
-    if ((s ^ F) < s) continue;
-    const bool c = (((uint32_t)s & gmask) == aval) || (((uint32_t)(s ^ F) & gmask) == aval);
-    const cplx<T> a = v[s], b = v[s ^ F];
-    v[s] = c ? b : a;
-    v[s ^ F] = c ? a : b;
-  }
-}
-template <typename T, int R>
-TQB_HD void reg_swap(cplx<T> (&v)[1 << R], uint32_t gmask, uint32_t aval, uint32_t flip) {
-  switch (flip) {
-#define TQB_SW(F) case F: if ((1 << R) > F) reg_swap_f<T, R, ((1 << R) > F ? F : 1)>(v, gmask, aval); break;
-    TQB_SW(1) TQB_SW(2) TQB_SW(3) TQB_SW(4) TQB_SW(5) TQB_SW(6) TQB_SW(7) TQB_SW(8)
-    TQB_SW(9) TQB_SW(10) TQB_SW(11) TQB_SW(12) TQB_SW(13) TQB_SW(14) TQB_SW(15)
-#undef TQB_SW
-    default: break;
-  }
-}
-// RDIAG: bits[j] = 32 + rho -> table-index bit j is register bit rho (its weight 1<<j is listed in
-// sbits[rho]); < 32 -> tile-local bit outside the register set; >= 64 -> index bit outside the tile.
-template <typename T, int R>
-TQB_HD void reg_diag(cplx<T> (&v)[1 << R], const tqb_gate &g, uint32_t lbase, uint64_t gbase, const cplx<T> *tab) {
-  uint32_t tg = 0;
-  const int k = g.k;
-  for (int j = 0; j < k; ++j) {
-    const uint32_t b = (uint32_t)(uint8_t)g.bits[j];
-    if (b & 64u) tg |= (uint32_t)((gbase >> (b & 63u)) & 1ull) << j;
-    else if (!(b & 32u)) tg |= ((lbase >> b) & 1u) << j;
-  }
-  uint32_t c[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) c[r] = (uint32_t)(uint8_t)g.sbits[r];
-#pragma unroll
-  for (int s = 0; s < (1 << R); ++s) {
-    uint32_t t = tg;
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (s & (1 << r)) t |= c[r];
-    v[s] = cmul(v[s], tab[t]);
+    tile[base] = x;
+    tile[base + tstride] = y;
   }
 }
 
-// One micro-pass: hdr = the TQB_GATE_MICRO descriptor, gl = the hdr.off_a register gates after it.
-template <typename T, int R>
-TQB_HD void micro_pass(cplx<T> *tile, const TileGeom &geo, uint64_t gbase, const tqb_gate &hdr, const tqb_gate *gl,
-                       const cplx<T> *mats, size_t bm, int tid, int nthreads) {
-  uint32_t rb[R];
-#pragma unroll
-  for (int j = 0; j < R; ++j) rb[j] = (uint32_t)hdr.bits[j];
-  const int count = (int)hdr.off_a;
-  const uint32_t ngroups = 1u << (geo.m - R);
-  for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
-    const uint32_t base = insert_zeros_k<R>(gi, rb);
-    cplx<T> v[1 << R];
-#pragma unroll
-    for (int s = 0; s < (1 << R); ++s) {
-      uint32_t o = base;
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (s & (1 << j)) o |= 1u << rb[j];
-      v[s] = tile[o];
-    }
-    for (int q = 0; q < count; ++q) {
-      const tqb_gate &d = gl[q];
-      const cplx<T> *M = mats + d.mat_off + bm * d.mat_bstride;
-      switch (d.kind) {
-        case TQB_GATE_RDENSE:
-          if (d.k == 1) reg_dense1<T, R>(v, d.bits[0], M);
-          else reg_dense2<T, R>(v, d.bits[0], d.bits[1], M);
-          break;
-        case TQB_GATE_RSWAP: reg_swap<T, R>(v, d.off_a, d.off_b, (uint32_t)d.zmask); break;
-        case TQB_GATE_RDIAG: reg_diag<T, R>(v, d, base, gbase, M); break;
-        default: break;
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < (1 << R); ++s) {
-      uint32_t o = base;
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (s & (1 << j)) o |= 1u << rb[j];
-      tile[o] = v[s];
-    }
+template <typename T>
+TQB_HD void gate_mux(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  const uint32_t tb = (uint32_t)g.bits[0];
+  const uint32_t cb = (uint32_t)(uint8_t)g.bits[1];
+  if (cb & 64u) {  // control outside the tile: one matrix for the whole tile
+    const uint32_t cv = (uint32_t)((gbase >> (cb & 63u)) & 1ull);
+    mux_sweep<T>(tile, 1u << (m - 1), tb, 0, false, 0, 1u << tb, M + 4 * cv, tid, nthreads);
+  } else {
+    const uint32_t p0 = tb < cb ? tb : cb, p1 = tb < cb ? cb : tb;
+    mux_sweep<T>(tile, 1u << (m - 2), p0, p1, true, 0, 1u << tb, M, tid, nthreads);
+    mux_sweep<T>(tile, 1u << (m - 2), p0, p1, true, 1u << cb, 1u << tb, M + 4, tid, nthreads);
   }
 }
 
 // gbase = global_base | tile base: the state index of tile element 0, high shard bits included.
 // MAXK bounds the dense gate size this instantiation can execute (2 = light, few registers;
-// 4 = heavy): the host picks the variant per pass.
-// Executes one unit of the pass's descriptor stream for one thread and returns how many
-// descriptors it covered: a shared-memory sweep of one gate (1) or a register micro-pass
-// (1 + hdr.off_a).  The caller puts a block barrier between units.
+// 4 = heavy): the host picks the variant per pass.  mats = base of the matrix buffer (staged in
+// shared memory when the pass says so), bm = batch member of the tile.
 template <typename T, int MAXK>
-TQB_HD int tile_exec_unit(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, uint64_t gbase,
-                          const tqb_gate *gl, const cplx<T> *mats, size_t bm, int tid, int nthreads) {
-  const tqb_gate &g = gl[0];
-  if (g.kind == TQB_GATE_MICRO) {
-    constexpr int R = sizeof(T) == 8 ? 3 : 4;
-    if (g.k == R) micro_pass<T, R>(tile, geo, gbase, g, gl + 1, mats, bm, tid, nthreads);
-    return 1 + (int)g.off_a;
-  }
+TQB_HD void tile_apply_gate(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, uint64_t gbase,
+                            const tqb_gate &g, const cplx<T> *mats, size_t bm, int tid, int nthreads) {
   const cplx<T> *mat = mats + g.mat_off + bm * g.mat_bstride;
   switch (g.kind) {
     case TQB_GATE_DENSE:
       switch (g.k) {
-        case 1: gate_dense<T, 1>(tile, geo.m, g, mat, tid, nthreads); break;
+        case 1: mux_sweep<T>(tile, 1u << (geo.m - 1), (uint32_t)g.bits[0], 0, false, 0, 1u << g.bits[0], mat, tid, nthreads); break;
         case 2: gate_dense<T, 2>(tile, geo.m, g, mat, tid, nthreads); break;
         case 3: if (MAXK >= 3) gate_dense<T, 3>(tile, geo.m, g, mat, tid, nthreads); break;
         case 4: if (MAXK >= 4) gate_dense<T, 4>(tile, geo.m, g, mat, tid, nthreads); break;
@@ -447,9 +327,9 @@ TQB_HD int tile_exec_unit(cplx<T> *tile, const TileGeom &geo, const uint64_t *ro
     case TQB_GATE_DIAG: gate_diag<T>(tile, geo.m, gbase, g, mat, tid, nthreads); break;
     case TQB_GATE_PAIR: gate_pair<T, false>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
     case TQB_GATE_SWAP: gate_pair<T, true>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
+    case TQB_GATE_MUX: gate_mux<T>(tile, geo.m, gbase, g, mat, tid, nthreads); break;
     default: break;
   }
-  return 1;
 }
 
 }  // namespace tqb

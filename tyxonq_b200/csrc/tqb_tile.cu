@@ -41,6 +41,11 @@ Workspace *workspace() {
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
+template <typename T>
+__host__ __device__ constexpr size_t tile_region_bytes(int m) {
+  return (sizeof(cplx<T>) << m) < 16 ? 16 : (sizeof(cplx<T>) << m);
+}
+
 // MAXK = 2: light variant (<= 512 threads, <= 64 registers); MAXK = 4: heavy variant
 // (<= 256 threads, <= 128 registers) for passes that carry dense 3- and 4-qubit blocks.
 template <typename T, int V, int MAXK>
@@ -49,9 +54,10 @@ tile_pass_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long lon
                  const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
-  uint64_t *roff = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(cplx<T>) << geo.m));
-  cplx<T> *smats = reinterpret_cast<cplx<T> *>(roff + (1u << geo.h));
-  tqb_gate *sg = reinterpret_cast<tqb_gate *>(smats + geo.mat_count);
+  // layout: tile | staged matrices | run-offset table | descriptors (each region keeps 16/8-byte alignment)
+  cplx<T> *smats = reinterpret_cast<cplx<T> *>(smem_raw + tile_region_bytes<T>(geo.m));
+  uint64_t *roff = reinterpret_cast<uint64_t *>(smats + geo.mat_count);
+  tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   for (uint32_t j = tid; j < (1u << geo.h); j += nthreads) roff[j] = run_offset(geo, j);
@@ -74,8 +80,8 @@ tile_pass_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long lon
     cplx<T> *sb = state + (b << geo.n);
     tile_load<T, V>(tile, sb, geo, roff, base, tid, nthreads);
     __syncthreads();
-    for (int gi = 0; gi < n_gates;) {
-      gi += tile_exec_unit<T, MAXK>(tile, geo, roff, geo.global_base | base, sg + gi, mat_base, (size_t)b, tid, nthreads);
+    for (int gi = 0; gi < n_gates; ++gi) {
+      tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], mat_base, (size_t)b, tid, nthreads);
       __syncthreads();
     }
     tile_store<T, V>(tile, sb, geo, roff, base, tid, nthreads);
@@ -127,12 +133,13 @@ __global__ void __launch_bounds__(256, MAXK <= 2 ? 3 : 2)
 tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                      const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: tile 0 | tile 1 | 2 mbarriers | staged matrices | run-offset table | descriptors
   const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
   cplx<T> *buf[2] = {reinterpret_cast<cplx<T> *>(smem_raw), reinterpret_cast<cplx<T> *>(smem_raw + tile_bytes)};
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * tile_bytes);  // 2 mbarriers (16 bytes)
-  uint64_t *roff = bars + 2;
-  cplx<T> *smats = reinterpret_cast<cplx<T> *>(roff + (1u << geo.h));
-  tqb_gate *sg = reinterpret_cast<tqb_gate *>(smats + geo.mat_count);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * tile_bytes);
+  cplx<T> *smats = reinterpret_cast<cplx<T> *>(bars + 2);
+  uint64_t *roff = reinterpret_cast<uint64_t *>(smats + geo.mat_count);
+  tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -184,8 +191,8 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
     const unsigned long long bm = tt >> tb;
     const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
     cplx<T> *tile = buf[b];
-    for (int gi = 0; gi < n_gates;) {
-      gi += tile_exec_unit<T, MAXK>(tile, geo, roff, geo.global_base | base, sg + gi, mat_base, (size_t)bm, tid, nthreads);
+    for (int gi = 0; gi < n_gates; ++gi) {
+      tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], mat_base, (size_t)bm, tid, nthreads);
       __syncthreads();
     }
     fence_proxy_async();  // generic-proxy writes of the tile -> visible to the bulk-store engine
@@ -217,7 +224,7 @@ static int launch_pass(void *state, const TileGeom &geo, int64_t batch, const tq
                        const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st) {
   const int max_threads = 256;
   if (threads > max_threads) threads = max_threads;
-  const size_t smem = (sizeof(cplx<T>) << geo.m) + (sizeof(uint64_t) << geo.h) + (size_t)geo.mat_count * sizeof(cplx<T>) +
+  const size_t smem = tile_region_bytes<T>(geo.m) + (sizeof(uint64_t) << geo.h) + (size_t)geo.mat_count * sizeof(cplx<T>) +
                       (size_t)n_gates * sizeof(tqb_gate);
   TQB_REQUIRE(smem <= (size_t)ws.max_smem_optin, "tqb_run_passes: tile + gate list exceed shared memory");
   auto kern = tile_pass_kernel<T, V, MAXK>;

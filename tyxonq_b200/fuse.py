@@ -7,6 +7,8 @@ are first merged where that is free:
   * consecutive 1-qubit gates on the same qubit        -> one 2x2 (rz then rx of the HEA layer)
   * consecutive diagonal gates (rz, s, cz, rzz, ...)   -> one table over the union of their bits (<= 6)
   * a 1-qubit gate next to a dense 2-qubit gate        -> folded into the 4x4 (same arithmetic cost)
+  * cx next to a 1-qubit gate on its target            -> one MUX gate: the 2x2 is U (control 0) or
+    X.U / U.X (control 1); costs one 1-qubit sweep and only the target has to be tile-local
 
 Gates only move past gates they share no index bit with, so the circuit's unitary is unchanged
 (products are formed in complex128 on the host).  Fused gates lose their gradient bookkeeping:
@@ -18,7 +20,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from .gates import DENSE, DIAG, LGate
+from .gates import DENSE, DIAG, MUX, SWAP, X_MAT, LGate, mux_gate
 
 C128 = np.complex128
 _I2 = np.eye(2, dtype=C128)
@@ -26,6 +28,15 @@ _I2 = np.eye(2, dtype=C128)
 
 def _batched(g: LGate) -> bool:
     return g.kind == DENSE and g.data.ndim == 2 and g.data.shape[0] != g.data.shape[1]
+
+
+def _is_1q(g: Optional[LGate]) -> bool:
+    return g is not None and g.kind in (DENSE, DIAG) and len(g.bits) == 1 and not _batched(g)
+
+
+def _is_cx(g: LGate) -> bool:
+    """SWAP gate that flips matrix bit 0 (target = bits[0]) when matrix bit 1 (control = bits[1]) is set."""
+    return g.kind == SWAP and len(g.bits) == 2 and g.pat_a == 0b10 and g.pat_b == 0b11
 
 
 def _m1(g: LGate) -> np.ndarray:
@@ -71,17 +82,36 @@ def fuse(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
             out.append(g)
             touch(g, len(out) - 1)
             continue
-        one_q = g.k == 1 and g.kind in (DENSE, DIAG)
-        if one_q:
-            j = last.get(g.bits[0])
+        if _is_1q(g):
+            t = g.bits[0]
+            j = last.get(t)
             p = out[j] if j is not None else None
             if p is not None and not _batched(p):
-                if p.k == 1 and p.kind in (DENSE, DIAG):
+                if _is_1q(p):
                     out[j] = _mul_1q(g, p)
                     continue
-                if p.kind == DENSE and p.k == 2:
-                    out[j] = LGate(DENSE, p.bits, _embed_1q(_m1(g), p.bits.index(g.bits[0])) @ p.data, name="fused")
+                if p.kind == DENSE and len(p.bits) == 2:
+                    out[j] = LGate(DENSE, p.bits, _embed_1q(_m1(g), p.bits.index(t)) @ p.data, name="fused")
                     continue
+                if p.kind == MUX and p.bits[0] == t:      # 1q gate after a MUX on the same target
+                    v = _m1(g)
+                    out[j] = mux_gate(v @ p.data[:4].reshape(2, 2), v @ p.data[4:].reshape(2, 2), t, p.bits[1], name="fused")
+                    continue
+                if _is_cx(p) and p.bits[0] == t:          # 1q gate after cx on its target: V (c=0), V.X (c=1)
+                    v = _m1(g)
+                    out[j] = mux_gate(v, v @ X_MAT, t, p.bits[1], name="fused")
+                    continue
+        if _is_cx(g):
+            t, c = g.bits[0], g.bits[1]
+            j = last.get(t)
+            p = out[j] if j is not None else None
+            if _is_1q(p):                                  # cx after a 1q gate on its target: U (c=0), X.U (c=1)
+                u = _m1(p)
+                out[j] = None
+                g = mux_gate(u, X_MAT @ u, t, c, name="fused")
+            elif p is not None and p.kind == MUX and p.bits == (t, c) and last.get(c) == j:
+                out[j] = mux_gate(p.data[:4].reshape(2, 2), X_MAT @ p.data[4:].reshape(2, 2), t, c, name="fused")
+                continue
         if g.kind == DIAG:
             js = [last[b] for b in g.bits if b in last]
             if js:
@@ -91,12 +121,12 @@ def fuse(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
                     out[j] = _merge_diag(p, g)
                     touch(g, j)
                     continue
-        if g.kind == DENSE and g.k == 2:
+        if g.kind == DENSE and len(g.bits) == 2:
             M = g.data
             for b in g.bits:
                 j = last.get(b)
                 p = out[j] if j is not None else None
-                if p is not None and p.k == 1 and p.kind in (DENSE, DIAG) and not _batched(p):
+                if _is_1q(p):
                     M = M @ _embed_1q(_m1(p), g.bits.index(b))
                     out[j] = None
             if M is not g.data:

@@ -106,7 +106,7 @@ GEN = {
 # ---------------------------------------------------------------------------------------
 # lowered gates
 # ---------------------------------------------------------------------------------------
-DENSE, DIAG, PAIR, SWAP = 0, 1, 2, 3
+DENSE, DIAG, PAIR, SWAP, MUX = 0, 1, 2, 3, 4
 
 
 @dataclass
@@ -115,7 +115,10 @@ class LGate:
 
     bits[j] is the index bit carrying matrix-index bit j (j = 0 least significant), i.e. for
     reference qubits (q0, .., qk-1) on n qubits: bits[j] = n-1-q_{k-1-j}.
-    data: DENSE (2^k,2^k) | DIAG (2^k,) | PAIR (4,) or (8,) [even-parity 2x2, odd-parity 2x2].
+    data: DENSE (2^k,2^k) | DIAG (2^k,) | PAIR (4,) or (8,) [even-parity 2x2, odd-parity 2x2]
+          | MUX (8,) [2x2 for control = 0, 2x2 for control = 1], bits = (target, control).
+    mask = all index bits the gate touches (ordering); local_mask = the bits that must be inside
+    the shared-memory tile (none for DIAG, only the target for MUX).
     """
     kind: int
     bits: Tuple[int, ...]
@@ -127,12 +130,19 @@ class LGate:
     param: Optional[int] = None
     name: str = ""
     mask: int = field(default=0, init=False)
+    local_mask: int = field(default=0, init=False)
 
     def __post_init__(self) -> None:
         m = 0
         for b in self.bits:
             m |= 1 << int(b)
         self.mask = m
+        if self.kind == DIAG:
+            self.local_mask = 0
+        elif self.kind == MUX:
+            self.local_mask = 1 << int(self.bits[0])
+        else:
+            self.local_mask = m
 
     @property
     def k(self) -> int:
@@ -166,6 +176,12 @@ def pair_gate(m2: np.ndarray, qubits: Sequence[int], n: int, pat_a: int, pat_b: 
 def swap_gate(qubits: Sequence[int], n: int, pat_a: int, pat_b: int, **kw: Any) -> LGate:
     """Exchange of two basis patterns (x, cx, swap): a PAIR gate with matrix X, done without arithmetic."""
     return LGate(SWAP, _bits_of(qubits, n), X_MAT.reshape(4).copy(), pat_a=int(pat_a), pat_b=int(pat_b), **kw)
+
+
+def mux_gate(u0: np.ndarray, u1: np.ndarray, target_bit: int, control_bit: int, **kw: Any) -> LGate:
+    """1-qubit gate on index bit ``target_bit``: u0 where index bit ``control_bit`` is 0, u1 where it is 1."""
+    d = np.concatenate([np.asarray(u0, dtype=C128).reshape(4), np.asarray(u1, dtype=C128).reshape(4)])
+    return LGate(MUX, (int(target_bit), int(control_bit)), d, **kw)
 
 
 def classify_unitary(mat: np.ndarray, qubits: Sequence[int], n: int) -> LGate:

@@ -58,8 +58,6 @@ class DeviceProgram:
         self.prog = prog
         self.device = torch.device(device)
         self.dtype = dtype
-        if prog.itemsize != (16 if dtype == torch.complex128 else 8):
-            raise _lib.TqbError("program was compiled for the other complex dtype (register tile size differs)")
         self.h2d_bytes = 0
         self._passes = np.ascontiguousarray(prog.passes)
         with torch.cuda.device(self.device):

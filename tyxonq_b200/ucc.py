@@ -227,15 +227,15 @@ class UCCStatevector:
         # structure (zmask, sign, patterns) is parameter independent: lower once with theta = 0
         self._proto = [excitation_gate(f, 0.0, self.n, mode=mode, param=pid) for f, pid in zip(self.ex_ops, self.param_ids)]
         self._signs = np.array([g.sign for g in self._proto], dtype=np.float64)  # type: ignore[attr-defined]
-        self._fwd = compile_program(self._proto, self.n, self.tile, micro=False, itemsize=itemsize)
+        self._fwd = compile_program(self._proto, self.n, self.tile, itemsize=itemsize)
         one = TileConfig(m=self.tile.m, L=self.tile.L, threads=self.tile.threads, ctas_per_sm=self.tile.ctas_per_sm, max_gates=1)
-        self._rev = compile_program(list(reversed(self._proto)), self.n, one, micro=False, itemsize=itemsize)
+        self._rev = compile_program(list(reversed(self._proto)), self.n, one, itemsize=itemsize)
         assert self._rev.order == list(range(len(self._proto)))
         self._fwd_dev = P.DeviceProgram(self._fwd, self.device, dtype)
         self._rev_dev = P.DeviceProgram(self._rev, self.device, dtype)
         # whole-state PAIR descriptors for the gradient reductions (m = n: local bit == index bit)
         full = compile_program(list(reversed(self._proto)), self.n, TileConfig(m=self.n, L=min(self.tile.L, self.n), max_gates=1),
-                               micro=False, itemsize=itemsize)
+                               itemsize=itemsize)
         self._grad_descs = np.ascontiguousarray(full.gates)
         self._kb = torch.empty((2, 1 << self.n), dtype=dtype, device=self.device)
         self._gout = torch.zeros(max(self.n_params, 1), dtype=torch.float64, device=self.device)
