@@ -44,6 +44,13 @@ extern "C" {
                          /* control bit bits[1] (< 64 tile-local, 64+p index bit p outside the  */
                          /* tile): U0 at mat_off, U1 at mat_off+4.  cx fused with a 1-qubit gate */
                          /* on its target costs one sweep and needs only the TARGET tile-local. */
+#define TQB_GATE_CHAIN 5 /* k = R (2 or 3) 1-qubit layers on tile-local bits bits[0..R) applied  */
+                         /* to 2^R register-resident amplitudes per thread (one shared-memory   */
+                         /* round trip for R gates).  Layer 0's 2x2 is selected by the control   */
+                         /* bit bits[R] (< 64 tile-local, 64+p outside the tile, 127 = none),    */
+                         /* layer i > 0 by the value of bit bits[i-1] after layer i-1.  Matrices: */
+                         /* layer i at mat_off + 8i (selector 0) and + 8i + 4 (selector 1).      */
+                         /* sbits[] = ascending positions of the targets (+ a tile-local control) */
 
 #define TQB_MAX_DENSE_K 4
 #define TQB_MAX_GATE_BITS 8

@@ -18,7 +18,7 @@ LIB_PATH = PKG / "libtyxonq_b200.so"
 
 TQB_C64, TQB_C128 = 0, 1
 GATE_DENSE, GATE_DIAG, GATE_PAIR, GATE_SWAP = 0, 1, 2, 3
-GATE_MUX = 4
+GATE_MUX, GATE_CHAIN = 4, 5
 MAX_GATE_BITS = 8
 MAX_TILE_HIGH = 16
 SCAN_BLOCK = 4096

@@ -306,6 +306,84 @@ TQB_HD void gate_mux(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, co
   }
 }
 
+// CHAIN: R (2 or 3) 1-qubit layers applied to 2^R register-resident amplitudes per thread: one
+// shared-memory round trip for R gates (the sweeps are shared-memory-bandwidth bound, so this is
+// what buys the factor R).  Layer i acts on tile-local bit bits[i]; its 2x2 is selected by
+//   i = 0: the outer control bit bits[R] (< 64 tile-local, 64+p outside the tile, 127 = none)
+//   i > 0: the value of bit bits[i-1] AFTER layer i-1 (the cx chain of a hardware-efficient layer;
+//          for independent gates the host stores the same matrix twice).
+// Matrix layout: layer i -> M[8i .. 8i+4) (selector 0), M[8i+4 .. 8i+8) (selector 1).
+// All register indexing is compile-time: register bit i <-> layer i.
+template <typename T, int R, int I, int SEL>
+TQB_HD void chain_layer(cplx<T> (&v)[1 << R], const cplx<T> *M) {
+  const cplx<T> m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+#pragma unroll
+  for (int s = 0; s < (1 << R); ++s) {
+    if (s & (1 << I)) continue;
+    if (I > 0 && SEL >= 0 && ((s >> (I > 0 ? I - 1 : 0)) & 1) != SEL) continue;
+    const cplx<T> a = v[s], b = v[s | (1 << I)];
+    cplx<T> x{0, 0}, y{0, 0};
+    cmac(x, m00, a); cmac(x, m01, b);
+    cmac(y, m10, a); cmac(y, m11, b);
+    v[s] = x;
+    v[s | (1 << I)] = y;
+  }
+}
+
+template <typename T, int R>
+TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  uint32_t tb[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) tb[i] = (uint32_t)g.bits[i];
+  const uint32_t cb = (uint32_t)(uint8_t)g.bits[R];
+  const bool ctrl_local = cb < 64u;
+  uint32_t cv_fixed = 0;
+  if (!ctrl_local && cb != 127u) cv_fixed = (uint32_t)((gbase >> (cb & 63u)) & 1ull);
+  constexpr int NZ = R + 1;
+  uint32_t sb[NZ];  // ascending positions where zero bits are inserted (targets [+ local control])
+#pragma unroll
+  for (int j = 0; j < NZ; ++j) sb[j] = (uint32_t)g.sbits[j];
+  const int nz = ctrl_local ? R + 1 : R;
+  const uint32_t free_bits = (uint32_t)(m - nz);
+  const uint32_t ngroups = 1u << (m - R);  // control value = top bit of the group counter when local
+  for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
+    uint32_t cv = cv_fixed, lo = gi;
+    if (ctrl_local) {
+      cv = gi >> free_bits;
+      lo = gi & ((1u << free_bits) - 1u);
+    }
+    uint32_t base = lo;
+#pragma unroll
+    for (int j = 0; j < NZ; ++j)
+      if (j < nz) base = ((base >> sb[j]) << (sb[j] + 1u)) | (base & ((1u << sb[j]) - 1u));
+    if (ctrl_local) base |= cv << cb;
+    cplx<T> v[1 << R];
+#pragma unroll
+    for (int s = 0; s < (1 << R); ++s) {
+      uint32_t o = base;
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        if (s & (1 << i)) o |= 1u << tb[i];
+      v[s] = tile[o];
+    }
+    chain_layer<T, R, 0, -1>(v, M + 4 * cv);
+    chain_layer<T, R, 1, 0>(v, M + 8);
+    chain_layer<T, R, 1, 1>(v, M + 12);
+    if (R > 2) {
+      chain_layer<T, R, (R > 2 ? 2 : 1), 0>(v, M + 16);
+      chain_layer<T, R, (R > 2 ? 2 : 1), 1>(v, M + 20);
+    }
+#pragma unroll
+    for (int s = 0; s < (1 << R); ++s) {
+      uint32_t o = base;
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        if (s & (1 << i)) o |= 1u << tb[i];
+      tile[o] = v[s];
+    }
+  }
+}
+
 // gbase = global_base | tile base: the state index of tile element 0, high shard bits included.
 // MAXK bounds the dense gate size this instantiation can execute (2 = light, few registers;
 // 4 = heavy): the host picks the variant per pass.  mats = base of the matrix buffer (staged in
@@ -328,6 +406,10 @@ TQB_HD void tile_apply_gate(cplx<T> *tile, const TileGeom &geo, const uint64_t *
     case TQB_GATE_PAIR: gate_pair<T, false>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
     case TQB_GATE_SWAP: gate_pair<T, true>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
     case TQB_GATE_MUX: gate_mux<T>(tile, geo.m, gbase, g, mat, tid, nthreads); break;
+    case TQB_GATE_CHAIN:
+      if (g.k == 2) gate_chain<T, 2>(tile, geo.m, gbase, g, mat, tid, nthreads);
+      else if (g.k == 3) gate_chain<T, 3>(tile, geo.m, gbase, g, mat, tid, nthreads);
+      break;
     default: break;
   }
 }

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from .gates import DENSE, DIAG, MUX, SWAP, X_MAT, LGate, mux_gate
+from .gates import DENSE, DIAG, MUX, SWAP, X_MAT, LGate, chain_gate, mux_gate
 
 C128 = np.complex128
 _I2 = np.eye(2, dtype=C128)
@@ -69,7 +69,58 @@ def _merge_diag(a: LGate, b: LGate) -> LGate:
     return LGate(DIAG, tuple(bits), sub(a) * sub(b), name="fused")
 
 
-def fuse(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
+def _as_layer(g: LGate):
+    """(target_bit, control_bit | None, M_sel0, M_sel1) for gates a CHAIN layer can carry."""
+    if _is_1q(g):
+        m = _m1(g)
+        return g.bits[0], None, m, m
+    if g.kind == MUX:
+        return g.bits[0], g.bits[1], g.data[:4].reshape(2, 2), g.data[4:].reshape(2, 2)
+    return None
+
+
+def chain_fuse(gates: Sequence[LGate], R: int = 3) -> List[LGate]:
+    """Group ADJACENT 1-qubit / MUX gates into CHAIN gates of up to R layers: one shared-memory round
+    trip for R gates.  Layer i > 0 must be uncontrolled or controlled by layer i-1's target (the shape
+    of a cx ladder); layer 0 may carry any control."""
+    out: List[LGate] = []
+    cur: List[tuple] = []   # (layer, original gate)
+
+    def flush() -> None:
+        if len(cur) == 1:
+            out.append(cur[0][1])
+        elif cur:
+            c0 = cur[0][0][1]
+            out.append(chain_gate([(l[0], l[2], l[3]) for l, _ in cur], control_bit=c0, name="chain"))
+        cur.clear()
+
+    for g in gates:
+        lay = _as_layer(g)
+        if lay is None:
+            flush()
+            out.append(g)
+            continue
+        t, c = lay[0], lay[1]
+        if cur:
+            tgts = [l[0] for l, _ in cur]
+            c0 = cur[0][0][1]
+            if len(cur) < R and t not in tgts and t != c0 and (c is None or c == tgts[-1]):
+                cur.append((lay, g))
+                continue
+            flush()
+        cur.append((lay, g))
+    flush()
+    return out
+
+
+def fuse(gates: Sequence[LGate], max_diag_k: int = 6, chain: int = 3) -> List[LGate]:
+    """Algebraic merges (see module docstring), then CHAIN grouping of up to ``chain`` layers
+    (0/1 disables it)."""
+    merged = _merge(gates, max_diag_k)
+    return chain_fuse(merged, chain) if chain >= 2 else merged
+
+
+def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
     out: List[Optional[LGate]] = []
     last: Dict[int, int] = {}
 

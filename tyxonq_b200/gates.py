@@ -106,7 +106,7 @@ GEN = {
 # ---------------------------------------------------------------------------------------
 # lowered gates
 # ---------------------------------------------------------------------------------------
-DENSE, DIAG, PAIR, SWAP, MUX = 0, 1, 2, 3, 4
+DENSE, DIAG, PAIR, SWAP, MUX, CHAIN = 0, 1, 2, 3, 4, 5
 
 
 @dataclass
@@ -141,6 +141,11 @@ class LGate:
             self.local_mask = 0
         elif self.kind == MUX:
             self.local_mask = 1 << int(self.bits[0])
+        elif self.kind == CHAIN:   # bits = targets in layer order (+ outer control when pat_a == 1)
+            nt = len(self.bits) - (1 if self.pat_a else 0)
+            self.local_mask = 0
+            for b in self.bits[:nt]:
+                self.local_mask |= 1 << int(b)
         else:
             self.local_mask = m
 
@@ -182,6 +187,18 @@ def mux_gate(u0: np.ndarray, u1: np.ndarray, target_bit: int, control_bit: int, 
     """1-qubit gate on index bit ``target_bit``: u0 where index bit ``control_bit`` is 0, u1 where it is 1."""
     d = np.concatenate([np.asarray(u0, dtype=C128).reshape(4), np.asarray(u1, dtype=C128).reshape(4)])
     return LGate(MUX, (int(target_bit), int(control_bit)), d, **kw)
+
+
+def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit: Optional[int] = None, **kw: Any) -> LGate:
+    """R = 2 or 3 one-qubit layers [(target_bit, M_sel0, M_sel1), ...]: layer 0 is selected by
+    ``control_bit`` (None: M_sel0 is used), layer i > 0 by the value of layer i-1's target bit."""
+    assert 2 <= len(layers) <= 3
+    bits = [int(t) for t, _, _ in layers]
+    data = np.concatenate([np.concatenate([np.asarray(a, dtype=C128).reshape(4), np.asarray(b, dtype=C128).reshape(4)])
+                           for _, a, b in layers])
+    if control_bit is not None:
+        bits.append(int(control_bit))
+    return LGate(CHAIN, tuple(bits), data, pat_a=1 if control_bit is not None else 0, **kw)
 
 
 def classify_unitary(mat: np.ndarray, qubits: Sequence[int], n: int) -> LGate:

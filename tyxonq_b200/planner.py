@@ -21,7 +21,7 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from .gates import DENSE, DIAG, MUX, PAIR, SWAP, LGate
+from .gates import CHAIN, DENSE, DIAG, MUX, PAIR, SWAP, LGate
 
 C128 = np.complex128
 
@@ -183,6 +183,17 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
                 e["k"] = 1
                 e["bits"][0] = local_of[g.bits[0]]
                 e["bits"][1] = enc(g.bits[1])
+            elif g.kind == CHAIN:
+                r = len(g.bits) - (1 if g.pat_a else 0)
+                e["k"] = r
+                loc = [local_of[b] for b in g.bits[:r]]
+                for j, b in enumerate(loc):
+                    e["bits"][j] = b
+                ctrl = enc(g.bits[r]) if g.pat_a else 127
+                e["bits"][r] = ctrl
+                zs = sorted(loc + ([ctrl] if ctrl < 64 else []))
+                for j, b in enumerate(zs):
+                    e["sbits"][j] = b
             else:
                 assert g.k <= 4, "dense / pair gates are limited to 4 bits"
                 loc = [local_of[b] for b in g.bits]
