@@ -116,10 +116,11 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
                    const tqb_pass *passes, int n_passes, const tqb_gate *gates_dev,
                    const void *mats_dev, int threads, int ctas_per_sm, void *stream);
 
-/* Tile staging mode of tqb_run_passes: 1 (default) = TMA bulk copies (cp.async.bulk) into a
- * double buffer with mbarrier completion, used whenever the contiguous runs are >= 128 bytes and
- * two tiles fit in shared memory; 0 = vectorised LDG/STG single buffer.  Returns the old value. */
-int tqb_set_tma(int enable);
+/* Tile staging mode of tqb_run_passes.  0 = vectorised LDG/STG, single buffer.  Otherwise TMA bulk
+ * copies (cp.async.bulk) with mbarrier completion into a ring of tile buffers, used whenever the
+ * contiguous runs are >= 128 bytes: 2 = two buffers, 3 = three, 1 (default) = three when two CTAs
+ * per SM still fit, else two.  Returns the old mode.                                             */
+int tqb_set_tma(int mode);
 
 /* ---- reductions ---------------------------------------------------------------------- */
 /* out_dev[b] = sum_i |psi_b,i|^2 (float64).                                                  */

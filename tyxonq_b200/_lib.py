@@ -114,6 +114,8 @@ def ensure_device(device_index: int) -> None:
     if not torch.cuda.is_available():
         raise TqbError("tyxonq_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     check(load().tqb_init(int(device_index)))
+    if os.environ.get("TQB_TMA"):  # tuning knob: 0 = LDG/STG, 2 / 3 = TMA ring depth, 1 = auto
+        load().tqb_set_tma(int(os.environ["TQB_TMA"]))
     _inited_devices.add(device_index)
 
 

@@ -124,20 +124,26 @@ __device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem,
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <typename T, int MAXK>
-__global__ void __launch_bounds__(256, MAXK <= 2 ? 3 : 2)
+// NB = number of tile buffers: with 2, the refill of a buffer waits until the bulk store of the tile
+// that just left it has drained (the store and the next compute phase serialise); with 3 the store
+// of tile i-1 drains while tile i is computed and tile i+1 is loaded.
+template <typename T, int MAXK, int NB>
+__global__ void __launch_bounds__(256, MAXK <= 2 ? (NB == 2 ? 3 : 2) : 2)
 tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                      const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: tile 0 | tile 1 | 2 mbarriers | staged matrices | run-offset table | descriptors
+  // layout: NB tiles | 4 mbarrier slots | staged matrices | run-offset table | descriptors
   const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
-  cplx<T> *buf[2] = {reinterpret_cast<cplx<T> *>(smem_raw), reinterpret_cast<cplx<T> *>(smem_raw + tile_bytes)};
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * tile_bytes);
-  cplx<T> *smats = reinterpret_cast<cplx<T> *>(bars + 2);
+  cplx<T> *buf[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) buf[i] = reinterpret_cast<cplx<T> *>(smem_raw + i * tile_bytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NB * tile_bytes);
+  cplx<T> *smats = reinterpret_cast<cplx<T> *>(bars + 4);
   uint64_t *roff = reinterpret_cast<uint64_t *>(smats + geo.mat_count);
   tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
 
@@ -153,8 +159,7 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
     for (int i = tid; i < nw; i += nthreads) dst[i] = src[i];
   }
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int i = 0; i < NB; ++i) mbar_init(&bars[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -180,13 +185,14 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
 
   if (warp == 0 && count > 0) issue_load(0, 0);
   for (unsigned long long it = 0; it < count; ++it) {
-    const int b = (int)(it & 1);
+    const int b = (int)(it % NB);
     if (warp == 0 && it + 1 < count) {
-      bulk_wait_read0();  // this lane's bulk stores out of buffer b^1 (tile it-1) have read their source
+      // the buffer to refill last held tile it+1-NB: this lane's bulk stores of that tile have read their source
+      bulk_wait_read<NB - 2>();
       __syncwarp();
-      issue_load(it + 1, b ^ 1);
+      issue_load(it + 1, (int)((it + 1) % NB));
     }
-    mbar_wait(&bars[b], (uint32_t)((it >> 1) & 1));
+    mbar_wait(&bars[b], (uint32_t)((it / NB) & 1));
     const unsigned long long tt = first + it * stride;
     const unsigned long long bm = tt >> tb;
     const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
@@ -250,16 +256,17 @@ static int launch_pass(void *state, const TileGeom &geo, int64_t batch, const tq
 
 static std::atomic<int> g_use_tma{1};
 
-template <typename T, int MAXK>
+template <typename T, int MAXK, int NB>
 static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
                            const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st, bool *used) {
   *used = false;
   const int max_threads = 256;
   if (threads > max_threads) threads = max_threads;
-  const size_t smem = 2 * (sizeof(cplx<T>) << geo.m) + 16 + (sizeof(uint64_t) << geo.h) +
+  const size_t smem = NB * (sizeof(cplx<T>) << geo.m) + 32 + (sizeof(uint64_t) << geo.h) +
                       (size_t)geo.mat_count * sizeof(cplx<T>) + (size_t)n_gates * sizeof(tqb_gate);
-  if (smem > (size_t)ws.max_smem_optin) return 0;  // caller falls back to the single-buffer kernel
-  auto kern = tile_pass_tma_kernel<T, MAXK>;
+  // caller falls back (fewer buffers, then the single-buffer kernel); 3 buffers only with >= 2 CTAs per SM
+  if (smem > (size_t)ws.max_smem_optin || (NB == 3 && 2 * (smem + 1024) > (size_t)228 * 1024)) return 0;
+  auto kern = tile_pass_tma_kernel<T, MAXK, NB>;
   static thread_local bool configured = false;
   if (!configured) {
     TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
@@ -286,8 +293,8 @@ using namespace tqb;
 
 extern "C" {
 
-int tqb_set_tma(int enable) {
-  const int old = g_use_tma.exchange(enable ? 1 : 0);
+int tqb_set_tma(int mode) {
+  const int old = g_use_tma.exchange(mode < 0 ? 0 : (mode > 3 ? 1 : mode));
   return old;
 }
 
@@ -387,13 +394,19 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
     const size_t run_bytes = (dtype == TQB_C128 ? (size_t)16 : (size_t)8) << ps.L;
     if (g_use_tma.load() && run_bytes >= 128 && n > ps.m) {
       bool used = false;
-      if (dtype == TQB_C128)
-        rc = heavy ? launch_pass_tma<double, 4>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
-                   : launch_pass_tma<double, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used);
-      else
-        rc = heavy ? launch_pass_tma<float, 4>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
-                   : launch_pass_tma<float, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used);
-      if (rc) return rc;
+      rc = 0;
+#define TQB_TMA(T, MK, NB) launch_pass_tma<T, MK, NB>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
+      if (g_use_tma.load() != 2) {  // 1 = auto (3 buffers when two CTAs still fit), 3 = force three
+        if (dtype == TQB_C128) rc = heavy ? TQB_TMA(double, 4, 3) : TQB_TMA(double, 2, 3);
+        else rc = heavy ? TQB_TMA(float, 4, 3) : TQB_TMA(float, 2, 3);
+        if (rc) return rc;
+      }
+      if (!used) {
+        if (dtype == TQB_C128) rc = heavy ? TQB_TMA(double, 4, 2) : TQB_TMA(double, 2, 2);
+        else rc = heavy ? TQB_TMA(float, 4, 2) : TQB_TMA(float, 2, 2);
+        if (rc) return rc;
+      }
+#undef TQB_TMA
       if (used) continue;
     }
 #define TQB_LAUNCH(T, V, MK) launch_pass<T, V, MK>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st)
