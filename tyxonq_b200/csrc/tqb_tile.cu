@@ -129,26 +129,34 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// NB = number of tile buffers: with 2, the refill of a buffer waits until the bulk store of the tile
-// that just left it has drained (the store and the next compute phase serialise); with 3 the store
-// of tile i-1 drains while tile i is computed and tile i+1 is loaded.
+// Warp-specialised: blockDim = C consumer threads + one producer warp.  The producer warp issues
+// every bulk load and bulk store (a UBLKCP per contiguous run, tens of cycles each) so that the
+// consumers never wait for TMA issue; the two sides meet only through mbarriers:
+//   full[b]  (1 arrival + tx bytes)  producer -> consumers: tile landed in buffer b
+//   done[b]  (C arrivals)            consumers -> producer: gates applied, tile may be stored
+// Consumers synchronise among themselves with named barrier 1.  NB = ring depth (2 or 3).
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
+
 template <typename T, int MAXK, int NB>
-__global__ void __launch_bounds__(256, MAXK <= 2 ? (NB == 2 ? 3 : 2) : 2)
+__global__ void __launch_bounds__(288, 2)
 tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                      const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: NB tiles | 4 mbarrier slots | staged matrices | run-offset table | descriptors
+  // layout: NB tiles | 8 mbarrier slots (full[NB], done[NB]) | staged matrices | run-offset table | descriptors
   const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
-  cplx<T> *buf[NB];
-#pragma unroll
-  for (int i = 0; i < NB; ++i) buf[i] = reinterpret_cast<cplx<T> *>(smem_raw + i * tile_bytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + NB * tile_bytes);
-  cplx<T> *smats = reinterpret_cast<cplx<T> *>(bars + 4);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NB * tile_bytes);
+  uint64_t *done = full + 4;
+  cplx<T> *smats = reinterpret_cast<cplx<T> *>(full + 8);
   uint64_t *roff = reinterpret_cast<uint64_t *>(smats + geo.mat_count);
   tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int ncons = nthreads - 32;  // consumer threads; the last warp is the producer
+  const int lane = tid & 31;
+  const bool producer = tid >= ncons;
   for (uint32_t j = tid; j < (1u << geo.h); j += nthreads) roff[j] = run_offset(geo, j);
   for (int i = tid; i < geo.mat_count; i += nthreads) smats[i] = mats[geo.mat_begin + i];
   const cplx<T> *mat_base = geo.mat_count > 0 ? smats - geo.mat_begin : mats;
@@ -159,7 +167,10 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
     for (int i = tid; i < nw; i += nthreads) dst[i] = src[i];
   }
   if (tid == 0) {
-    for (int i = 0; i < NB; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&done[i], (uint32_t)ncons);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -172,44 +183,52 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
   const uint32_t run_elems = 1u << geo.L;
   const uint32_t run_bytes = (uint32_t)(sizeof(cplx<T>) << geo.L);
 
-  // issued by warp 0: the runs of this CTA's it-th tile -> buffer b
-  auto issue_load = [&](unsigned long long it, int b) {
-    const unsigned long long tt = first + it * stride;
-    const unsigned long long bm = tt >> tb;
-    const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
-    const cplx<T> *sb = state + (bm << geo.n) + base;
-    if (lane == 0) mbar_expect_tx(&bars[b], (uint32_t)tile_bytes);
-    __syncwarp();
-    for (uint32_t j = lane; j < nruns; j += 32) bulk_load(buf[b] + (size_t)j * run_elems, sb + roff[j], run_bytes, &bars[b]);
-  };
-
-  if (warp == 0 && count > 0) issue_load(0, 0);
-  for (unsigned long long it = 0; it < count; ++it) {
-    const int b = (int)(it % NB);
-    if (warp == 0 && it + 1 < count) {
-      // the buffer to refill last held tile it+1-NB: this lane's bulk stores of that tile have read their source
-      bulk_wait_read<NB - 2>();
+  if (producer) {
+    auto tile_ptr = [&](unsigned long long it) -> cplx<T> * {
+      const unsigned long long tt = first + it * stride;
+      return state + ((tt >> tb) << geo.n) + tile_base(geo, tt & ((1ull << tb) - 1ull));
+    };
+    auto issue_load = [&](unsigned long long it) {
+      const int b = (int)(it % NB);
+      cplx<T> *dst = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
+      const cplx<T> *src = tile_ptr(it);
+      if (lane == 0) mbar_expect_tx(&full[b], (uint32_t)tile_bytes);
       __syncwarp();
-      issue_load(it + 1, (int)((it + 1) % NB));
-    }
-    mbar_wait(&bars[b], (uint32_t)((it / NB) & 1));
-    const unsigned long long tt = first + it * stride;
-    const unsigned long long bm = tt >> tb;
-    const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
-    cplx<T> *tile = buf[b];
-    for (int gi = 0; gi < n_gates; ++gi) {
-      tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], mat_base, (size_t)bm, tid, nthreads);
-      __syncthreads();
-    }
-    fence_proxy_async();  // generic-proxy writes of the tile -> visible to the bulk-store engine
-    __syncthreads();
-    if (warp == 0) {
-      cplx<T> *sb = state + (bm << geo.n) + base;
-      for (uint32_t j = lane; j < nruns; j += 32) bulk_store(sb + roff[j], tile + (size_t)j * run_elems, run_bytes);
+      for (uint32_t j = lane; j < nruns; j += 32) bulk_load(dst + (size_t)j * run_elems, src + roff[j], run_bytes, &full[b]);
+    };
+    for (unsigned long long it = 0; it < (unsigned long long)(NB - 1) && it < count; ++it) issue_load(it);
+    for (unsigned long long it = 0; it < count; ++it) {
+      const int b = (int)(it % NB);
+      if (it + NB - 1 < count) {
+        // the buffer to refill last held tile it-1: this lane's bulk stores of it have read their source
+        bulk_wait_read<0>();
+        __syncwarp();
+        issue_load(it + NB - 1);
+      }
+      mbar_wait(&done[b], (uint32_t)((it / NB) & 1));  // consumers finished tile it (their fence.proxy.async precedes the arrive)
+      cplx<T> *dstg = tile_ptr(it);
+      const cplx<T> *srcs = reinterpret_cast<const cplx<T> *>(smem_raw + b * tile_bytes);
+      for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], srcs + (size_t)j * run_elems, run_bytes);
       bulk_commit();
     }
+    bulk_wait_all0();
+    return;
   }
-  if (warp == 0) bulk_wait_all0();
+
+  for (unsigned long long it = 0; it < count; ++it) {
+    const int b = (int)(it % NB);
+    mbar_wait(&full[b], (uint32_t)((it / NB) & 1));
+    const unsigned long long tt = first + it * stride;
+    const unsigned long long bm = tt >> tb;
+    const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
+    cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
+    for (int gi = 0; gi < n_gates; ++gi) {
+      tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], mat_base, (size_t)bm, tid, ncons);
+      if (gi + 1 < n_gates) consumer_sync(ncons);
+    }
+    fence_proxy_async();  // this thread's generic-proxy writes of the tile -> visible to the bulk-store engine
+    mbar_arrive(&done[b]);
+  }
 }
 
 template <typename T>
@@ -262,7 +281,7 @@ static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, cons
   *used = false;
   const int max_threads = 256;
   if (threads > max_threads) threads = max_threads;
-  const size_t smem = NB * (sizeof(cplx<T>) << geo.m) + 32 + (sizeof(uint64_t) << geo.h) +
+  const size_t smem = NB * (sizeof(cplx<T>) << geo.m) + 64 + (sizeof(uint64_t) << geo.h) +
                       (size_t)geo.mat_count * sizeof(cplx<T>) + (size_t)n_gates * sizeof(tqb_gate);
   // caller falls back (fewer buffers, then the single-buffer kernel); 3 buffers only with >= 2 CTAs per SM
   if (smem > (size_t)ws.max_smem_optin || (NB == 3 && 2 * (smem + 1024) > (size_t)228 * 1024)) return 0;
@@ -275,13 +294,14 @@ static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, cons
   }
   const unsigned long long total = (unsigned long long)batch << (geo.n - geo.m);
   int resident = 0;
-  TQB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, threads, smem));
+  const int block = threads + 32;  // consumers + the producer warp
+  TQB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, block, smem));
   if (resident < 1) return 0;
   int per_sm = ctas_per_sm > 0 && ctas_per_sm < resident ? ctas_per_sm : resident;
   unsigned long long grid = (unsigned long long)ws.sm_count * per_sm;
   if (grid > total) grid = total;
-  kern<<<(unsigned)grid, threads, smem, st>>>(reinterpret_cast<cplx<T> *>(state), geo, (long long)batch, gates, n_gates,
-                                               reinterpret_cast<const cplx<T> *>(mats));
+  kern<<<(unsigned)grid, block, smem, st>>>(reinterpret_cast<cplx<T> *>(state), geo, (long long)batch, gates, n_gates,
+                                             reinterpret_cast<const cplx<T> *>(mats));
   TQB_CHECK_LAUNCH("tile_pass_tma_kernel");
   *used = true;
   return 0;
