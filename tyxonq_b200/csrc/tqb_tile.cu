@@ -159,7 +159,6 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
   const bool producer = tid >= ncons;
   for (uint32_t j = tid; j < (1u << geo.h); j += nthreads) roff[j] = run_offset(geo, j);
   for (int i = tid; i < geo.mat_count; i += nthreads) smats[i] = mats[geo.mat_begin + i];
-  const cplx<T> *mat_base = geo.mat_count > 0 ? smats - geo.mat_begin : mats;
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(gates);
     uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
@@ -222,9 +221,17 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
     const unsigned long long bm = tt >> tb;
     const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
     cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
-    for (int gi = 0; gi < n_gates; ++gi) {
-      tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], mat_base, (size_t)bm, tid, ncons);
-      if (gi + 1 < n_gates) consumer_sync(ncons);
+    if (geo.mat_count > 0) {  // matrices staged in shared memory: keep the pointer's address space known (LDS, not LD)
+      const cplx<T> *sm = smats - geo.mat_begin;
+      for (int gi = 0; gi < n_gates; ++gi) {
+        tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], sm, (size_t)0, tid, ncons);
+        if (gi + 1 < n_gates) consumer_sync(ncons);
+      }
+    } else {
+      for (int gi = 0; gi < n_gates; ++gi) {
+        tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], mats, (size_t)bm, tid, ncons);
+        if (gi + 1 < n_gates) consumer_sync(ncons);
+      }
     }
     fence_proxy_async();  // this thread's generic-proxy writes of the tile -> visible to the bulk-store engine
     mbar_arrive(&done[b]);
