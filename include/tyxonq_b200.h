@@ -118,8 +118,9 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
 
 /* Tile staging mode of tqb_run_passes.  0 = vectorised LDG/STG, single buffer.  Otherwise TMA bulk
  * copies (cp.async.bulk) with mbarrier completion into a ring of tile buffers, used whenever the
- * contiguous runs are >= 128 bytes: 2 = two buffers, 3 = three, 1 (default) = three when two CTAs
- * per SM still fit, else two.  Returns the old mode.                                             */
+ * contiguous runs are >= 128 bytes: 1 (default) and 2 = two buffers (three CTAs per SM at 32 KiB
+ * tiles), 3 = three buffers when two CTAs per SM still fit (measured slower: profiles/).  A
+ * producer warp issues all bulk copies.  Returns the old mode.                                   */
 int tqb_set_tma(int mode);
 
 /* ---- reductions ---------------------------------------------------------------------- */

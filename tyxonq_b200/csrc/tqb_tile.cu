@@ -423,7 +423,7 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
       bool used = false;
       rc = 0;
 #define TQB_TMA(T, MK, NB) launch_pass_tma<T, MK, NB>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
-      if (g_use_tma.load() != 2) {  // 1 = auto (3 buffers when two CTAs still fit), 3 = force three
+      if (g_use_tma.load() == 3) {  // 3 = three buffers when two CTAs still fit; 1 (auto) and 2 = two buffers
         if (dtype == TQB_C128) rc = heavy ? TQB_TMA(double, 4, 3) : TQB_TMA(double, 2, 3);
         else rc = heavy ? TQB_TMA(float, 4, 3) : TQB_TMA(float, 2, 3);
         if (rc) return rc;

@@ -41,19 +41,19 @@ class TileConfig:
 
 def default_tile(n: int, itemsize: int, batch: int = 1) -> TileConfig:
     """itemsize = 8 (complex64) or 16 (complex128).  Streaming regime: 32 KiB tiles, double
-    buffered by TMA (3 CTAs per SM), 1 KiB contiguous runs (bulk copies below 1 KiB lose
-    bandwidth: 4.2 TB/s at 512 B vs 5.5 TB/s at 1 KiB, profiles/r01_tile_sweep.md).  Small
-    states use one big tile so that whole layers stay in shared memory."""
+    buffered by TMA (3 CTAs per SM: 128 consumer threads + a producer warp each), 512-byte
+    contiguous runs, 6 high tile bits (profiles/r01_tile_sweep.md: one-gate pass 6.18 TB/s).
+    Small states use one big tile so that whole layers stay in shared memory."""
     big = 13 if itemsize == 16 else 14           # 128 KiB tile
     stream_m = 11 if itemsize == 16 else 12      # 32 KiB tile
-    stream_L = 6 if itemsize == 16 else 7        # 1 KiB runs
+    stream_L = 5 if itemsize == 16 else 6        # 512 B runs
     m = int(os.environ.get("TQB_TILE_M", 0)) or (min(n, big) if (n <= big + 3 and batch <= 64) else stream_m)
     m = min(m, n)
     L = int(os.environ.get("TQB_TILE_L", 0)) or stream_L
     L = min(L, m)
     if m - L > 12:
         L = m - 12
-    threads = int(os.environ.get("TQB_THREADS", 0)) or 256
+    threads = int(os.environ.get("TQB_THREADS", 0)) or (128 if m <= (11 if itemsize == 16 else 12) else 256)
     cps = int(os.environ.get("TQB_CTAS_PER_SM", 0))
     return TileConfig(m=m, L=L, threads=threads, ctas_per_sm=cps)
 
