@@ -1,0 +1,338 @@
+"""States too large for one GPU: shard by the high-order index bits, one process per GPU.
+
+The reference has no distributed path at all (zero collectives).  Design:
+
+  * rank r of G = 2^g owns the amplitudes whose g highest PHYSICAL index bits equal r
+    (n_local = n - g local bits).  A logical->physical bit map is tracked on the host, so "which
+    qubits are global" changes as the circuit runs; TyxonQ's big-endian convention (qubit 0 = most
+    significant bit, libs/quantum_library/kernels/statevector.py:28-42) fixes the INITIAL map only.
+  * Gates run as ordinary local fused passes with ``global_base = rank << n_local``: diagonal tables
+    and MUX/CHAIN controls read the rank bits from global_base, so diagonal gates and controls on
+    global qubits need no communication.
+  * A gate whose target is a global bit forces a *global <-> local exchange*: the g global bits
+    are swapped with the g top local bits by ONE all-to-all of contiguous chunks over NVLink
+    (each rank keeps 1/G of its shard, sends (G-1)/G); victims (the local bits that become global)
+    are chosen by farthest next use and moved to the top local positions by in-tile SWAP gates
+    that ride in the preceding local passes.
+  * Reductions (<Z_q>, norms, energies) are local reductions + one all-reduce of a few doubles.
+
+The only data-path collective is that all-to-all.  ``exchange`` uses NCCL's all_to_all_single on
+GPUs and grouped send/recv elsewhere (gloo has no all-to-all), which is what the CPU tests run.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Any, Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .gates import CHAIN, DENSE, DIAG, MUX, PAIR, SWAP, X_MAT, LGate
+
+
+# ------------------------------------------------------------------------------------------
+# host planning
+# ------------------------------------------------------------------------------------------
+def _bits(mask: int) -> List[int]:
+    out = []
+    b = 0
+    while mask:
+        if mask & 1:
+            out.append(b)
+        mask >>= 1
+        b += 1
+    return out
+
+
+def remap_gate(g: LGate, phys: Sequence[int]) -> LGate:
+    """Same gate on physical bit positions (phys[logical bit] = physical bit)."""
+    ng = LGate(g.kind, tuple(phys[b] for b in g.bits), g.data, pat_a=g.pat_a, pat_b=g.pat_b,
+               zmask=_remap_mask(g.zmask, phys), param=g.param, name=g.name)
+    return ng
+
+
+def _remap_mask(mask: int, phys: Sequence[int]) -> int:
+    out = 0
+    for b in _bits(mask):
+        out |= 1 << phys[b]
+    return out
+
+
+@dataclass
+class Segment:
+    gates: List[LGate]            # on PHYSICAL bits; bits >= n_local are rank bits (controls / diagonals only)
+    exchange_after: bool = False  # all-to-all of the g global bits with the g top local bits after the gates
+
+
+@dataclass
+class ShardPlan:
+    n: int
+    g: int
+    segments: List[Segment]
+    final_phys: List[int]         # final_phys[logical bit] = physical bit after the last segment
+    n_exchanges: int = 0
+
+
+def plan_sharded(gates: Sequence[LGate], n: int, g: int) -> ShardPlan:
+    """Split a gate list (logical index bits) into local segments separated by global<->local exchanges."""
+    n_local = n - g
+    phys = list(range(n))                     # logical -> physical
+    remaining = list(range(len(gates)))
+    segments: List[Segment] = []
+    n_ex = 0
+    if g == 0:
+        return ShardPlan(n, 0, [Segment(list(gates))], phys)
+    guard = 0
+    while remaining:
+        guard += 1
+        if guard > 4 * len(gates) + 8:
+            raise RuntimeError("sharded planner failed to make progress")
+        chosen: List[int] = []
+        rest: List[int] = []
+        blocked = 0
+        blocked_nd = 0
+        for i in remaining:
+            gt = gates[i]
+            mk = gt.mask
+            if gt.kind == DIAG:
+                if mk & blocked_nd:
+                    blocked |= mk
+                    rest.append(i)
+                else:
+                    chosen.append(i)
+                continue
+            ok = not (mk & blocked) and all(phys[b] < n_local for b in _bits(gt.local_mask))
+            if ok:
+                chosen.append(i)
+            else:
+                blocked |= mk
+                blocked_nd |= mk
+                rest.append(i)
+        seg = Segment([remap_gate(gates[i], phys) for i in chosen])
+        remaining = rest
+        if remaining:
+            # choose the g local logical bits that become global: farthest next use as a tile-local bit,
+            # never a bit the first blocked gate needs
+            inv = {p: l for l, p in enumerate(phys)}
+            first_need = gates[remaining[0]].local_mask
+            next_use = {}
+            for pos, i in enumerate(remaining):
+                for b in _bits(gates[i].local_mask):
+                    next_use.setdefault(b, pos)
+            local_logical = [l for l in range(n) if phys[l] < n_local]
+            cands = [l for l in local_logical if not (first_need >> l) & 1]
+            cands.sort(key=lambda l: -next_use.get(l, 1 << 30))
+            victims = cands[:g]
+            if len(victims) < g:
+                raise RuntimeError("not enough local qubits to exchange")
+            # move the victims to the top g local positions with in-tile SWAP gates (physical bit swaps)
+            top = list(range(n_local - g, n_local))
+            vict_set = set(victims)
+            free_top = [p for p in top if inv[p] not in vict_set]
+            for v in victims:
+                pv = phys[v]
+                if pv >= n_local - g:
+                    continue
+                pt = free_top.pop()
+                other = inv[pt]
+                seg.gates.append(LGate(SWAP, (pv, pt), X_MAT.reshape(4).copy(), pat_a=0b01, pat_b=0b10, name="bitswap"))
+                phys[v], phys[other] = pt, pv
+                inv[pt], inv[pv] = v, other
+            seg.exchange_after = True
+            n_ex += 1
+            # the all-to-all swaps physical bit (n_local - g + i) with physical bit (n_local + i)
+            for i in range(g):
+                a, b = n_local - g + i, n_local + i
+                la, lb = inv[a], inv[b]
+                phys[la], phys[lb] = b, a
+                inv[a], inv[b] = lb, la
+        segments.append(seg)
+    return ShardPlan(n, g, segments, phys, n_ex)
+
+
+# ------------------------------------------------------------------------------------------
+# the exchange
+# ------------------------------------------------------------------------------------------
+def exchange(out: torch.Tensor, inp: torch.Tensor, group: Any = None) -> None:
+    """out[j] <- chunk `rank` of rank j's inp, for inp/out viewed as [G, chunk] (the global<->local swap)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    inp2 = inp.view(world, -1)
+    out2 = out.view(world, -1)
+    if dist.get_backend(group) == "nccl":
+        # complex tensors go over the wire as reals
+        dist.all_to_all_single(torch.view_as_real(out2).reshape(world, -1), torch.view_as_real(inp2).reshape(world, -1), group=group)
+        return
+    ops = []
+    for j in range(world):
+        if j == rank:
+            out2[j].copy_(inp2[j])
+            continue
+        ops.append(dist.P2POp(dist.isend, torch.view_as_real(inp2[j]).contiguous(), j, group))
+        ops.append(dist.P2POp(dist.irecv, torch.view_as_real(out2[j]), j, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+# ------------------------------------------------------------------------------------------
+# execution
+# ------------------------------------------------------------------------------------------
+class ShardedState:
+    """One rank's shard plus the scratch buffer of the exchange (ping-pong: no copy back)."""
+
+    def __init__(self, n: int, dtype: torch.dtype, device: torch.device, group: Any = None,
+                 backend: Optional[Any] = None) -> None:
+        """``backend``: object with init_local / run_local / reduce_local (default: the CUDA kernels of this
+        package).  The CPU test tier injects an oracle-backed one to exercise the planner and the exchange
+        over gloo; the package itself has no CPU compute path."""
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        self.g = int(self.world).bit_length() - 1
+        if (1 << self.g) != self.world:
+            raise ValueError("world size must be a power of two")
+        self.n = n
+        self.n_local = n - self.g
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self.state = torch.empty(1 << self.n_local, dtype=dtype, device=self.device)
+        self.scratch = torch.empty_like(self.state) if self.g else None
+        self.global_base = self.rank << self.n_local
+        self.phys = list(range(n))
+        self.programs: List[Any] = []
+        self.backend = backend or _CudaLocal(self)
+        self.exchange_s = 0.0
+
+    def init_zero(self) -> None:
+        self.backend.init_local(self.state, self.n_local, self.global_base)
+        self.phys = list(range(self.n))
+
+    def run(self, plan: ShardPlan) -> None:
+        for si, seg in enumerate(plan.segments):
+            if seg.gates:
+                self.backend.run_local(self.state, seg.gates, self.n_local, self.global_base, si)
+            if seg.exchange_after:
+                t0 = time.perf_counter()
+                exchange(self.scratch, self.state, self.group)
+                self.state, self.scratch = self.scratch, self.state
+                self.exchange_s += time.perf_counter() - t0
+        self.phys = list(plan.final_phys)
+
+    # -- reductions -----------------------------------------------------------------------
+    def expect_z_all(self) -> torch.Tensor:
+        """<Z> for every LOGICAL index bit (float64 [n]); one local read + one all-reduce."""
+        zl, nrm = self.backend.reduce_local(self.state, self.n_local)
+        zphys = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        zphys[: self.n_local] = zl
+        for i in range(self.g):
+            zphys[self.n_local + i] = nrm if not (self.rank >> i) & 1 else -nrm
+        if self.world > 1:
+            dist.all_reduce(zphys, group=self.group)
+        return zphys[torch.tensor(self.phys, device=self.device)]
+
+
+class _CudaLocal:
+    """Local work of one rank on its GPU: the fused passes and reductions of libtyxonq_b200.so."""
+
+    def __init__(self, owner: "ShardedState") -> None:
+        self.owner = owner
+
+    def init_local(self, state: torch.Tensor, n_local: int, global_base: int) -> None:
+        from . import _lib
+        from . import program as P
+        ptr, n_, b_, dt, stream = P._prep(state)
+        _lib.check(_lib.load().tqb_init_basis(ptr, n_, 1, dt, global_base, 0, stream))
+
+    def run_local(self, state: torch.Tensor, gates: List[LGate], n_local: int, global_base: int, cache_slot: int) -> None:
+        from . import program as P
+        from .planner import compile_program, default_tile
+        progs = self.owner.programs
+        while len(progs) <= cache_slot:
+            progs.append(None)
+        if progs[cache_slot] is None:
+            prog = compile_program(gates, n_local, default_tile(n_local, state.element_size(), 1), itemsize=state.element_size())
+            progs[cache_slot] = P.DeviceProgram(prog, state.device, state.dtype)
+        progs[cache_slot].run(state, global_base=global_base)
+
+    def reduce_local(self, state: torch.Tensor, n_local: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        from . import program as P
+        return P.expect_z_bits(state)[0], P.norm2(state)[0]
+
+
+def lower_and_fuse(ops: Sequence[tuple], n: int, mode: str = "run") -> List[LGate]:
+    from .fuse import fuse
+    from .gates import lower_op
+    return fuse([g for g in (lower_op(o, n, mode=mode) for o in ops) if g is not None])
+
+
+class ShardedBench:
+    """bench.py's N > 1 arm: the HEA workload on a state sharded over all ranks of the default group."""
+
+    def __init__(self, n: int, ops: Sequence[tuple], dtype: torch.dtype, device: torch.device) -> None:
+        self.ops = list(ops)
+        self.n = n
+        t0 = time.perf_counter()
+        gates = lower_and_fuse(self.ops, n)
+        self.st = ShardedState(n, dtype, device)
+        self.plan = plan_sharded(gates, n, self.st.g)
+        self.plan_ms = 1e3 * (time.perf_counter() - t0)
+        self.n_local = self.st.n_local
+        self._ev: List[Tuple[Any, Any]] = []
+        self.st.init_zero()
+        self.st.run(self.plan)          # compiles + uploads the per-segment programs
+        torch.cuda.synchronize()
+        passes = sum(p.prog.n_passes for p in self.st.programs if p is not None)
+        B = 16 if dtype == torch.complex128 else 8
+        self.info = {"passes": passes, "gates_per_pass": len([o for o in self.ops if o[0] != "measure_z"]) / max(passes, 1),
+                     "plan_ms": self.plan_ms, "swaps": self.plan.n_exchanges, "n_local": self.n_local,
+                     "exchange_bytes_per_gpu": self.plan.n_exchanges * ((1 << self.n_local) * B * (self.st.world - 1)) // self.st.world}
+        self._local_ms = 0.0
+        self._local_n = 0
+
+    def step(self, timed: bool = False) -> torch.Tensor:
+        self.st.init_zero()
+        self.st.run(self.plan)
+        return self.st.expect_z_all()
+
+    def pass_ms_per_launch(self) -> float:
+        """Device time of the local passes alone (one extra untimed run with events around each segment)."""
+        self.st.init_zero()
+        tot = 0.0
+        for si, seg in enumerate(self.plan.segments):
+            if seg.gates:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self.st.backend.run_local(self.st.state, seg.gates, self.st.n_local, self.st.global_base, si)
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            if seg.exchange_after:
+                exchange(self.st.scratch, self.st.state, self.st.group)
+                self.st.state, self.st.scratch = self.st.scratch, self.st.state
+        return tot / max(self.info["passes"], 1)
+
+    def e2e(self, args: Any) -> dict:
+        """Host op list -> plan -> upload -> passes/exchanges -> <Z_q> on the host, all ranks."""
+        n_gates = len([o for o in self.ops if o[0] != "measure_z"])
+        ts = []
+        for _ in range(2):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            gates = lower_and_fuse(self.ops, self.n)
+            st = self.st
+            st.programs = []
+            plan = plan_sharded(gates, self.n, st.g)
+            st.init_zero()
+            st.run(plan)
+            z = st.expect_z_all().cpu()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ts.append(time.perf_counter() - t0)
+        h2d = sum(p.h2d_bytes for p in self.st.programs if p is not None)
+        return {"value": n_gates * 2.0 ** (self.n - 30) / float(np.mean(ts)), "unit": "gates/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(z.numel() * 8), "ms_per_step": 1e3 * float(np.mean(ts)),
+                "api": "lower+fuse+plan_sharded -> ShardedState.run -> expect_z_all().cpu() on every rank"}
