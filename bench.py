@@ -290,6 +290,14 @@ def own_arm(args) -> None:
                        "value_definition": "gates * 2^(n-30) / s", **info},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
             "hbm_gbps_per_gpu": achieved, "expz_checksum": float(z.sum().item())}
+    if world > 1:
+        bd = sb.breakdown
+        # combined roofline: local passes at the measured HBM peak + exchanges at the measured NVLink peer peak, no overlap
+        ideal_ms = info["passes"] * alg_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3 + \
+            bd["exchange_bytes_per_gpu_each_way"] / (bd["nvlink_peak_gbps"] * 1e9) * 1e3
+        bd["combined_roofline_ms"] = ideal_ms
+        bd["combined_roofline_frac"] = ideal_ms / ms_per_step
+        line["nvlink"] = bd
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(n, args.layers, args.dtype)
     if world == 1 and not args.no_extras:

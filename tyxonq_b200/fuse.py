@@ -69,6 +69,17 @@ def _merge_diag(a: LGate, b: LGate) -> LGate:
     return LGate(DIAG, tuple(bits), sub(a) * sub(b), name="fused")
 
 
+def _simplify_mux(g: LGate) -> LGate:
+    """A MUX whose two matrices are both diagonal is a 2-bit diagonal gate (cx.rz.cx = rzz):
+    table index bit 0 = target, bit 1 = control."""
+    if g.kind != MUX:
+        return g
+    u0, u1 = g.data[:4].reshape(2, 2), g.data[4:].reshape(2, 2)
+    if u0[0, 1] == 0 and u0[1, 0] == 0 and u1[0, 1] == 0 and u1[1, 0] == 0:
+        return LGate(DIAG, (g.bits[0], g.bits[1]), np.array([u0[0, 0], u0[1, 1], u1[0, 0], u1[1, 1]], dtype=C128), name="fused")
+    return g
+
+
 def _as_layer(g: LGate):
     """(target_bit, control_bit | None, M_sel0, M_sel1) for gates a CHAIN layer can carry."""
     if _is_1q(g):
@@ -113,10 +124,45 @@ def chain_fuse(gates: Sequence[LGate], R: int = 3) -> List[LGate]:
     return out
 
 
+def _conjugated_diagonals(gates: Sequence[LGate]) -> List[LGate]:
+    """Peephole: cx(c,t) . D(t) . cx(c,t) with D diagonal on t and nothing else on c or t in between is the
+    2-bit diagonal table[c*2+t] = D[t xor c] (the ZZ rotation of a Trotter step, trotter_circuit.py:52-60)."""
+    gates = list(gates)
+    n = len(gates)
+    nxt: List[Dict[int, int]] = [dict() for _ in range(n)]   # nxt[i][bit] = index of the next gate touching bit
+    last: Dict[int, int] = {}
+    for i in range(n - 1, -1, -1):
+        for b in gates[i].bits:
+            if b in last:
+                nxt[i][b] = last[b]
+            last[b] = i
+    dead = [False] * n
+    for i, g in enumerate(gates):
+        if dead[i] or not _is_cx(g):
+            continue
+        t, c = g.bits[0], g.bits[1]
+        j = nxt[i].get(t)
+        if j is None or dead[j]:
+            continue
+        d = gates[j]
+        if not (d.kind == DIAG and d.bits == (t,)):
+            continue
+        k = nxt[j].get(t)
+        if k is None or dead[k] or nxt[i].get(c) != k:
+            continue
+        g2 = gates[k]
+        if not (_is_cx(g2) and g2.bits == (t, c)):
+            continue
+        tab = np.array([d.data[0], d.data[1], d.data[1], d.data[0]], dtype=C128)
+        gates[i] = LGate(DIAG, (t, c), tab, name="fused")
+        dead[j] = dead[k] = True
+    return [g for i, g in enumerate(gates) if not dead[i]]
+
+
 def fuse(gates: Sequence[LGate], max_diag_k: int = 6, chain: int = 3) -> List[LGate]:
     """Algebraic merges (see module docstring), then CHAIN grouping of up to ``chain`` layers
     (0/1 disables it)."""
-    merged = _merge(gates, max_diag_k)
+    merged = _merge(_conjugated_diagonals(gates), max_diag_k)
     return chain_fuse(merged, chain) if chain >= 2 else merged
 
 
@@ -161,7 +207,7 @@ def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
                 out[j] = None
                 g = mux_gate(u, X_MAT @ u, t, c, name="fused")
             elif p is not None and p.kind == MUX and p.bits == (t, c) and last.get(c) == j:
-                out[j] = mux_gate(p.data[:4].reshape(2, 2), X_MAT @ p.data[4:].reshape(2, 2), t, c, name="fused")
+                out[j] = _simplify_mux(mux_gate(p.data[:4].reshape(2, 2), X_MAT @ p.data[4:].reshape(2, 2), t, c, name="fused"))
                 continue
         if g.kind == DIAG:
             js = [last[b] for b in g.bits if b in last]

@@ -298,9 +298,11 @@ class ShardedBench:
         return self.st.expect_z_all()
 
     def pass_ms_per_launch(self) -> float:
-        """Device time of the local passes alone (one extra untimed run with events around each segment)."""
+        """Device time of the local passes alone (one extra untimed run with events around each segment);
+        also fills ``self.breakdown`` with the exchange time (NCCL kernels are on the same stream)."""
         self.st.init_zero()
         tot = 0.0
+        xch = 0.0
         for si, seg in enumerate(self.plan.segments):
             if seg.gates:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -310,8 +312,22 @@ class ShardedBench:
                 torch.cuda.synchronize()
                 tot += e0.elapsed_time(e1)
             if seg.exchange_after:
+                dist.barrier()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
                 exchange(self.st.scratch, self.st.state, self.st.group)
+                e1.record()
+                torch.cuda.synchronize()
+                xch += e0.elapsed_time(e1)
                 self.st.state, self.st.scratch = self.st.scratch, self.st.state
+        t = torch.tensor([tot, xch], dtype=torch.float64, device=self.st.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot, xch = float(t[0]), float(t[1])
+        nbytes = self.info["exchange_bytes_per_gpu"]
+        self.breakdown = {"pass_ms": tot, "exchange_ms": xch, "exchanges": self.plan.n_exchanges,
+                          "exchange_bytes_per_gpu_each_way": nbytes,
+                          "nvlink_gbps_per_gpu_each_way": (nbytes / (xch * 1e-3) / 1e9) if xch > 0 else None,
+                          "nvlink_peak_gbps": 770.0, "nvlink_peak_source": "measured peer copy, B200_PROFILING.md"}
         return tot / max(self.info["passes"], 1)
 
     def e2e(self, args: Any) -> dict:
