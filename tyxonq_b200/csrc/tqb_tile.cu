@@ -238,6 +238,117 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
   }
 }
 
+// ---- ring variant: one CTA per SM, one producer warp, G consumer groups, NB-deep tile ring ----------
+// With one tile in flight per CTA (two buffers) the memory system sees at most 3 x 32 KiB per SM and only
+// while a CTA is not computing (ncu: DRAM 59 % busy, FP64 40 % busy, time = sum of both).  Here a single
+// CTA owns all of the SM's shared memory as a ring of NB tiles: tile `it` lives in buffer it % NB, is computed
+// by consumer group it % G (128 threads, named barrier 1 + group), loads run K = NB - S tiles ahead and up
+// to S bulk stores drain behind, so loads, stores and G computations overlap inside one CTA.
+template <typename T, int MAXK>
+__global__ void __launch_bounds__(544, 1)
+tile_pass_ring_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
+                      const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats,
+                      const int NB, const int G, const int S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: NB tiles | 16 mbarrier slots (full[8], done[8]) | staged matrices | run-offset table | descriptors
+  const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NB * tile_bytes);
+  uint64_t *done = full + 8;
+  cplx<T> *smats = reinterpret_cast<cplx<T> *>(full + 16);
+  uint64_t *roff = reinterpret_cast<uint64_t *>(smats + geo.mat_count);
+  tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
+
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int ncons = nthreads - 32;
+  const int gsize = ncons / G;  // threads per consumer group
+  const int lane = tid & 31;
+  const bool producer = tid >= ncons;
+  for (uint32_t j = tid; j < (1u << geo.h); j += nthreads) roff[j] = run_offset(geo, j);
+  for (int i = tid; i < geo.mat_count; i += nthreads) smats[i] = mats[geo.mat_begin + i];
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(gates);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
+    const int nw = n_gates * (int)(sizeof(tqb_gate) / 4);
+    for (int i = tid; i < nw; i += nthreads) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&done[i], (uint32_t)gsize);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int tb = geo.n - geo.m;
+  const unsigned long long total = (unsigned long long)batch << tb;
+  const unsigned long long first = blockIdx.x, stride = gridDim.x;
+  const unsigned long long count = first < total ? (total - first + stride - 1) / stride : 0;
+  const uint32_t nruns = 1u << geo.h;
+  const uint32_t run_elems = 1u << geo.L;
+  const uint32_t run_bytes = (uint32_t)(sizeof(cplx<T>) << geo.L);
+
+  if (producer) {
+    const unsigned long long K = (unsigned long long)(NB - S);  // prefetch distance
+    auto tile_ptr = [&](unsigned long long it) -> cplx<T> * {
+      const unsigned long long tt = first + it * stride;
+      return state + ((tt >> tb) << geo.n) + tile_base(geo, tt & ((1ull << tb) - 1ull));
+    };
+    auto issue_load = [&](unsigned long long it) {
+      const int b = (int)(it % NB);
+      cplx<T> *dst = reinterpret_cast<cplx<T> *>(smem_raw + (size_t)b * tile_bytes);
+      const cplx<T> *src = tile_ptr(it);
+      if (lane == 0) mbar_expect_tx(&full[b], (uint32_t)tile_bytes);
+      __syncwarp();
+      for (uint32_t j = lane; j < nruns; j += 32) bulk_load(dst + (size_t)j * run_elems, src + roff[j], run_bytes, &full[b]);
+    };
+    for (unsigned long long it = 0; it < K && it < count; ++it) issue_load(it);
+    for (unsigned long long it = 0; it < count; ++it) {
+      const int b = (int)(it % NB);
+      mbar_wait(&done[b], (uint32_t)((it / NB) & 1));  // group it % G finished tile it
+      cplx<T> *dstg = tile_ptr(it);
+      const cplx<T> *srcs = reinterpret_cast<const cplx<T> *>(smem_raw + (size_t)b * tile_bytes);
+      for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], srcs + (size_t)j * run_elems, run_bytes);
+      bulk_commit();
+      if (it + K < count) {
+        // tile it+K reuses the buffer of tile it+K-NB = it-S: all but the S newest bulk stores have read their source
+        if (S == 1) bulk_wait_read<1>();
+        else if (S == 2) bulk_wait_read<2>();
+        else bulk_wait_read<3>();
+        __syncwarp();
+        issue_load(it + K);
+      }
+    }
+    bulk_wait_all0();
+    return;
+  }
+
+  const int group = tid / gsize;
+  const int gtid = tid - group * gsize;
+  for (unsigned long long it = (unsigned long long)group; it < count; it += (unsigned long long)G) {
+    const int b = (int)(it % NB);
+    mbar_wait(&full[b], (uint32_t)((it / NB) & 1));
+    const unsigned long long tt = first + it * stride;
+    const unsigned long long bm = tt >> tb;
+    const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
+    cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + (size_t)b * tile_bytes);
+    if (geo.mat_count > 0) {
+      const cplx<T> *sm = smats - geo.mat_begin;
+      for (int gi = 0; gi < n_gates; ++gi) {
+        tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], sm, (size_t)0, gtid, gsize);
+        if (gi + 1 < n_gates) asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(gsize) : "memory");
+      }
+    } else {
+      for (int gi = 0; gi < n_gates; ++gi) {
+        tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], mats, (size_t)bm, gtid, gsize);
+        if (gi + 1 < n_gates) asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(gsize) : "memory");
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(&done[b]);
+  }
+}
+
 template <typename T>
 __global__ void init_basis_kernel(cplx<T> *state, int n, long long batch, unsigned long long local_index,
                                   int present) {
@@ -314,6 +425,39 @@ static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, cons
   return 0;
 }
 
+template <typename T, int MAXK>
+static int launch_pass_ring(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
+                            const void *mats, int threads, const Workspace &ws, cudaStream_t st, bool *used) {
+  *used = false;
+  const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
+  const size_t extras = 128 + (sizeof(uint64_t) << geo.h) + (size_t)geo.mat_count * sizeof(cplx<T>) + (size_t)n_gates * sizeof(tqb_gate);
+  if (extras + 3 * tile_bytes > (size_t)ws.max_smem_optin) return 0;
+  int NB = (int)(((size_t)ws.max_smem_optin - extras) / tile_bytes);
+  if (NB > 8) NB = 8;
+  const int G = NB >= 6 ? 3 : (NB >= 4 ? 2 : 1);
+  const int S = NB - G >= 3 ? 2 : 1;   // loads run NB - S tiles ahead
+  if (threads > 160) threads = 160;
+  if (threads < 32) threads = 32;
+  threads = (threads / 32) * 32;
+  const size_t smem = extras + (size_t)NB * tile_bytes;
+  auto kern = tile_pass_ring_kernel<T, MAXK>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  const unsigned long long total = (unsigned long long)batch << (geo.n - geo.m);
+  unsigned long long grid = (unsigned long long)ws.sm_count;
+  if (grid > total) grid = total;
+  const int block = G * threads + 32;
+  kern<<<(unsigned)grid, block, smem, st>>>(reinterpret_cast<cplx<T> *>(state), geo, (long long)batch, gates, n_gates,
+                                             reinterpret_cast<const cplx<T> *>(mats), NB, G, S);
+  TQB_CHECK_LAUNCH("tile_pass_ring_kernel");
+  *used = true;
+  return 0;
+}
+
 }  // namespace tqb
 
 using namespace tqb;
@@ -321,7 +465,7 @@ using namespace tqb;
 extern "C" {
 
 int tqb_set_tma(int mode) {
-  const int old = g_use_tma.exchange(mode < 0 ? 0 : (mode > 3 ? 1 : mode));
+  const int old = g_use_tma.exchange(mode < 0 ? 0 : (mode > 4 ? 1 : mode));
   return old;
 }
 
@@ -422,6 +566,16 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
     if (g_use_tma.load() && run_bytes >= 128 && n > ps.m) {
       bool used = false;
       rc = 0;
+      if (g_use_tma.load() == 4) {  // ring: one CTA per SM, G consumer groups, NB-deep tile ring
+        if (dtype == TQB_C128)
+          rc = heavy ? launch_pass_ring<double, 4>(state, geo, batch, g, ps.n_gates, mats_dev, threads, *ws, st, &used)
+                     : launch_pass_ring<double, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, *ws, st, &used);
+        else
+          rc = heavy ? launch_pass_ring<float, 4>(state, geo, batch, g, ps.n_gates, mats_dev, threads, *ws, st, &used)
+                     : launch_pass_ring<float, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, *ws, st, &used);
+        if (rc) return rc;
+        if (used) continue;
+      }
 #define TQB_TMA(T, MK, NB) launch_pass_tma<T, MK, NB>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
       if (g_use_tma.load() == 3) {  // 3 = three buffers when two CTAs still fit; 1 (auto) and 2 = two buffers
         if (dtype == TQB_C128) rc = heavy ? TQB_TMA(double, 4, 3) : TQB_TMA(double, 2, 3);
