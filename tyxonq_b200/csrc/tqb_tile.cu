@@ -245,10 +245,10 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
 // by consumer group it % G (128 threads, named barrier 1 + group), loads run K = NB - S tiles ahead and up
 // to S bulk stores drain behind, so loads, stores and G computations overlap inside one CTA.
 template <typename T, int MAXK>
-__global__ void __launch_bounds__(544, 1)
+__global__ void __launch_bounds__(608, 1)
 tile_pass_ring_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                       const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats,
-                      const int NB, const int G, const int S) {
+                      const int NB, const int G, const int S, const int PW) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: NB tiles | 16 mbarrier slots (full[8], done[8]) | staged matrices | run-offset table | descriptors
   const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
@@ -259,7 +259,7 @@ tile_pass_ring_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
   tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
 
   const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int ncons = nthreads - 32;
+  const int ncons = nthreads - 32 * PW;  // the last PW warps are producers; producer w moves runs j = w (mod PW)
   const int gsize = ncons / G;  // threads per consumer group
   const int lane = tid & 31;
   const bool producer = tid >= ncons;
@@ -290,6 +290,8 @@ tile_pass_ring_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
 
   if (producer) {
     const unsigned long long K = (unsigned long long)(NB - S);  // prefetch distance
+    const int pw = (tid - ncons) >> 5;
+    const uint32_t jstep = 32u * (uint32_t)PW, j0 = (uint32_t)(pw * 32 + lane);
     auto tile_ptr = [&](unsigned long long it) -> cplx<T> * {
       const unsigned long long tt = first + it * stride;
       return state + ((tt >> tb) << geo.n) + tile_base(geo, tt & ((1ull << tb) - 1ull));
@@ -298,9 +300,9 @@ tile_pass_ring_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
       const int b = (int)(it % NB);
       cplx<T> *dst = reinterpret_cast<cplx<T> *>(smem_raw + (size_t)b * tile_bytes);
       const cplx<T> *src = tile_ptr(it);
-      if (lane == 0) mbar_expect_tx(&full[b], (uint32_t)tile_bytes);
+      if (pw == 0 && lane == 0) mbar_expect_tx(&full[b], (uint32_t)tile_bytes);
       __syncwarp();
-      for (uint32_t j = lane; j < nruns; j += 32) bulk_load(dst + (size_t)j * run_elems, src + roff[j], run_bytes, &full[b]);
+      for (uint32_t j = j0; j < nruns; j += jstep) bulk_load(dst + (size_t)j * run_elems, src + roff[j], run_bytes, &full[b]);
     };
     for (unsigned long long it = 0; it < K && it < count; ++it) issue_load(it);
     for (unsigned long long it = 0; it < count; ++it) {
@@ -308,7 +310,7 @@ tile_pass_ring_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
       mbar_wait(&done[b], (uint32_t)((it / NB) & 1));  // group it % G finished tile it
       cplx<T> *dstg = tile_ptr(it);
       const cplx<T> *srcs = reinterpret_cast<const cplx<T> *>(smem_raw + (size_t)b * tile_bytes);
-      for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], srcs + (size_t)j * run_elems, run_bytes);
+      for (uint32_t j = j0; j < nruns; j += jstep) bulk_store(dstg + roff[j], srcs + (size_t)j * run_elems, run_bytes);
       bulk_commit();
       if (it + K < count) {
         // tile it+K reuses the buffer of tile it+K-NB = it-S: all but the S newest bulk stores have read their source
@@ -450,9 +452,10 @@ static int launch_pass_ring(void *state, const TileGeom &geo, int64_t batch, con
   const unsigned long long total = (unsigned long long)batch << (geo.n - geo.m);
   unsigned long long grid = (unsigned long long)ws.sm_count;
   if (grid > total) grid = total;
-  const int block = G * threads + 32;
+  const int PW = 4;
+  const int block = G * threads + 32 * PW;
   kern<<<(unsigned)grid, block, smem, st>>>(reinterpret_cast<cplx<T> *>(state), geo, (long long)batch, gates, n_gates,
-                                             reinterpret_cast<const cplx<T> *>(mats), NB, G, S);
+                                             reinterpret_cast<const cplx<T> *>(mats), NB, G, S, PW);
   TQB_CHECK_LAUNCH("tile_pass_ring_kernel");
   *used = true;
   return 0;
