@@ -118,3 +118,10 @@ def test_ucc_h2o_shape_energy_grad(cuda_device):
     e2, g2 = sv.energy_and_grad(params * 0.5)
     e2_ref, g2_ref = U.energy_and_grad_adjoint(params * 0.5, Hs, n, nes, ex_ops, pids)
     assert abs(e2 - e2_ref) < 1e-8 and np.abs(g2 - g2_ref).max() < 1e-8
+    # third call replays the captured CUDA graph with new matrices; the un-graphed path must agree too
+    e3, g3 = sv.energy_and_grad(params * -0.3)
+    e3_ref, g3_ref = U.energy_and_grad_adjoint(params * -0.3, Hs, n, nes, ex_ops, pids)
+    assert sv._graph is not None
+    assert abs(e3 - e3_ref) < 1e-8 and np.abs(g3 - g3_ref).max() < 1e-8
+    e4, g4 = sv.energy_and_grad(params * -0.3, graph=False)
+    assert abs(e4 - e3) < 1e-12 and np.abs(g4 - g3).max() < 1e-10

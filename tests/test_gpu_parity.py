@@ -251,6 +251,22 @@ def test_tfim_vqe_energy(cuda_device):
     fd = O.central_fd_gradient(lambda x: O.tfim_vqe_energy(10, 1, x.reshape(2, 10)), p.reshape(-1), 1e-6)
     assert abs(e - O.tfim_vqe_energy(10, 1, p)) < TOL128
     assert np.abs(g.reshape(-1) - fd).max() < 1e-7
+    # later calls replay one CUDA graph with rewritten matrices
+    for scale in (0.5, -1.3):
+        q = p * scale
+        e2, g2 = v.energy_and_grad(q)
+        assert abs(e2 - O.tfim_vqe_energy(10, 1, q)) < TOL128
+        fd2 = O.central_fd_gradient(lambda x: O.tfim_vqe_energy(10, 1, x.reshape(2, 10)), q.reshape(-1), 1e-6)
+        assert np.abs(g2.reshape(-1) - fd2).max() < 1e-7
+    assert v._graph is not None
+    # two layers, complex64 state
+    import torch
+    v2 = TFIMVqe(8, 2, device=cuda_device, dtype=torch.complex64)
+    p2 = rng.normal(size=(4, 8))
+    e3, g3 = v2.energy_and_grad(p2)
+    assert abs(e3 - O.tfim_vqe_energy(8, 2, p2)) < 1e-4
+    fd3 = O.central_fd_gradient(lambda x: O.tfim_vqe_energy(8, 2, x.reshape(4, 8)), p2.reshape(-1), 1e-6)
+    assert np.abs(g3.reshape(-1) - fd3).max() < 1e-3
 
 
 def test_large_state_invariants(cuda_device):

@@ -70,14 +70,24 @@ class DeviceProgram:
             self.h2d_bytes += prog.gates.nbytes
             self.upload_mats(prog.mats)
 
-    def upload_mats(self, mats: np.ndarray) -> None:
-        """(Re)load the matrix buffer, e.g. for new variational parameters."""
+    def fill_host(self, mats: np.ndarray) -> None:
+        """Write new matrices into the pinned staging buffer (host only; see ``upload``)."""
         src = torch.from_numpy(np.ascontiguousarray(mats, dtype=np.complex128))
         if src.numel():
             self.mats_host[: src.numel()].copy_(src)  # casts to complex64 when needed
-            with torch.cuda.device(self.device):
-                self.mats_dev.copy_(self.mats_host, non_blocking=True)
-            self.h2d_bytes += self.mats_host.numel() * self.mats_host.element_size()
+
+    def upload(self) -> None:
+        """Async H2D copy of the staging buffer on the current stream (capturable into a CUDA graph:
+        a replay re-reads the pinned buffer, so new parameters only need ``fill_host``)."""
+        with torch.cuda.device(self.device):
+            self.mats_dev.copy_(self.mats_host, non_blocking=True)
+        self.h2d_bytes += self.mats_host.numel() * self.mats_host.element_size()
+
+    def upload_mats(self, mats: np.ndarray) -> None:
+        """(Re)load the matrix buffer, e.g. for new variational parameters."""
+        if np.asarray(mats).size:
+            self.fill_host(mats)
+            self.upload()
 
     def run(self, state: torch.Tensor, *, global_base: int = 0) -> torch.Tensor:
         if state.dtype != self.dtype:

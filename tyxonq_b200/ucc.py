@@ -271,34 +271,65 @@ class UCCStatevector:
         psi = self.statevector(params)
         return float(self.ham.expectation(psi)[0].real.cpu())
 
-    def energy_and_grad(self, params: Sequence[float]) -> Tuple[float, np.ndarray]:
-        """energy_and_grad_statevector (statevector_ops.py:203-244) with an analytic adjoint gradient."""
-        params = np.asarray(params, dtype=np.float64)
+    def _enqueue(self) -> None:
+        """Everything of one energy + gradient evaluation on the current stream, device side only: H2D of the
+        two matrix buffers, HF state, forward passes, |bra> = H|ket>, <ket|bra>, and the reverse sweep.  No
+        host synchronisation and no allocation, so the whole thing is captured into one CUDA graph."""
         lib = _lib.load()
         kb = self._kb
+        ptr, n, _, dt, stream = P._prep(kb[0])
+        _lib.check(lib.tqb_init_basis(ptr, n, 1, dt, 0, self.hf_index, stream))
+        if self._proto:
+            self._fwd_dev.upload()
+            self._rev_dev.upload()
+            self._fwd_dev.run(kb[0])
+        self.ham.apply(kb[0], kb[1])
+        _lib.check(lib.tqb_inner(kb[0].data_ptr(), kb[1].data_ptr(), n, 1, dt, self._e.data_ptr(), stream))
+        self._gout.zero_()
+        ket_ptr, bra_ptr = kb[0].data_ptr(), kb[1].data_ptr()
+        N = len(self._proto)
+        t = self.tile
+        passes = self._rev_dev._passes
+        psz = passes.dtype.itemsize
+        gsz = self._grad_descs.dtype.itemsize
+        for i in range(N):
+            j = N - 1 - i
+            _lib.check(lib.tqb_grad_pair(bra_ptr, ket_ptr, n, dt, self._grad_descs.ctypes.data + i * gsz,
+                                         -2.0 * float(self._signs[j]), self._gout.data_ptr(), self.param_ids[j], stream))
+            if i + 1 < N:  # the last un-apply is not needed
+                _lib.check(lib.tqb_run_passes(kb.data_ptr(), n, 2, dt, 0, passes.ctypes.data + i * psz, 1,
+                                              self._rev_dev.gates_dev.data_ptr(), self._rev_dev.mats_dev.data_ptr(),
+                                              t.threads, t.ctas_per_sm, stream))
+        self._out[0:1].copy_(self._e[0:1])
+        self._out[1:1 + self.n_params].copy_(self._gout[: self.n_params])
+
+    def energy_and_grad(self, params: Sequence[float], *, graph: bool = True) -> Tuple[float, np.ndarray]:
+        """energy_and_grad_statevector (statevector_ops.py:203-244) with an analytic adjoint gradient.
+        ``graph``: replay the evaluation as one CUDA graph (captured on the second call) instead of ~300
+        separate launches; new parameters only rewrite the pinned matrix buffers."""
+        params = np.asarray(params, dtype=np.float64)
+        if not hasattr(self, "_e"):
+            self._e = torch.zeros(2, dtype=torch.float64, device=self.device)
+            self._out = torch.zeros(1 + max(self.n_params, 1), dtype=torch.float64, device=self.device)
+            self._out_host = torch.zeros(1 + max(self.n_params, 1), dtype=torch.float64).pin_memory()
+            self._graph = None
+            self._calls = 0
+        if self._proto:
+            self._fwd_dev.fill_host(self._fill(self._fwd, params, False))
+            self._rev_dev.fill_host(self._fill(self._rev, params, True))
         with torch.cuda.device(self.device):
-            ptr, n, _, dt, stream = P._prep(kb[0])
-            _lib.check(lib.tqb_init_basis(ptr, n, 1, dt, 0, self.hf_index, stream))
-            if self._proto:
-                self._fwd_dev.upload_mats(self._fill(self._fwd, params, False))
-                self._fwd_dev.run(kb[0])
-                self._rev_dev.upload_mats(self._fill(self._rev, params, True))
-            self.ham.apply(kb[0], kb[1])
-            e = P.inner(kb[0], kb[1])
-            self._gout.zero_()
-            ket_ptr, bra_ptr = kb[0].data_ptr(), kb[1].data_ptr()
-            N = len(self._proto)
-            t = self.tile
-            passes = self._rev_dev._passes
-            psz = passes.dtype.itemsize
-            gsz = self._grad_descs.dtype.itemsize
-            for i in range(N):
-                j = N - 1 - i
-                _lib.check(lib.tqb_grad_pair(bra_ptr, ket_ptr, n, dt, self._grad_descs.ctypes.data + i * gsz,
-                                             -2.0 * float(self._signs[j]), self._gout.data_ptr(), self.param_ids[j], stream))
-                if i + 1 < N:  # the last un-apply is not needed
-                    _lib.check(lib.tqb_run_passes(kb.data_ptr(), n, 2, dt, 0, passes.ctypes.data + i * psz, 1,
-                                                  self._rev_dev.gates_dev.data_ptr(), self._rev_dev.mats_dev.data_ptr(),
-                                                  t.threads, t.ctas_per_sm, stream))
-            out = torch.cat([torch.view_as_real(e).reshape(-1)[:1], self._gout[: self.n_params]]).cpu().numpy()
-        return float(out[0]), out[1:].copy()
+            if graph and self._graph is None and self._calls >= 1:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self._graph = g
+            if graph and self._graph is not None:
+                self._graph.replay()
+            else:
+                self._enqueue()
+            self._calls += 1
+            self._out_host.copy_(self._out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        out = self._out_host.numpy()
+        return float(out[0]), out[1:1 + self.n_params].copy()
