@@ -292,3 +292,26 @@ def test_large_state_invariants(cuda_device):
     psi, _, _ = eng._evolve(FakeCircuit(n, ops + inv), "state")
     assert abs(complex(psi[0].cpu()) - 1.0) < 1e-10
     assert abs(float(P.norm2(psi).cpu()[0]) - 1.0) < 1e-10
+
+
+def test_batched_ansatz_expval_and_sampling(cuda_device):
+    """Config 5 at test size: B parameter sets of the HWE-RY ansatz, Heisenberg Pauli sum, shots per state."""
+    import torch
+    from tyxonq_b200 import PauliSum
+    from tyxonq_b200.batched import BatchedAnsatz
+    n, L, B, shots = 12, 3, 6, 512
+    rng = np.random.default_rng(7)
+    params = rng.random((B, (L + 1) * n))
+    terms, w = O.heisenberg_terms(n, [(i, i + 1) for i in range(n - 1)], hzz=1.0, hxx=0.5, hyy=0.5, hx=-0.3)
+    ham = PauliSum.from_codes(terms, w)
+    u = np.random.default_rng(99).random((B, shots))
+    for dt, tol in ((torch.complex128, 1e-10), (torch.complex64, 2e-5)):
+        ba = BatchedAnsatz(n, L, B, device=cuda_device, dtype=dt)
+        st = ba.run(params).cpu().numpy()
+        ev = ba.expvals(ham).cpu().numpy()
+        idx = ba.sample(torch.from_numpy(u)).cpu().numpy()
+        for b in range(B):
+            ref, _ = O.evolve_ops(n, O.hwe_ry_ops(n, L, params[b]))
+            assert np.abs(st[b] - ref).max() < tol
+            assert abs(ev[b] - O.expect_pauli_sum(ref, terms, w)) < tol * 50
+            assert np.array_equal(idx[b], O.sample_indices(O.probabilities(st[b]), u[b]))

@@ -27,11 +27,12 @@ _I2 = np.eye(2, dtype=C128)
 
 
 def _batched(g: LGate) -> bool:
-    return g.kind == DENSE and g.data.ndim == 2 and g.data.shape[0] != g.data.shape[1]
+    return bool(g.batched)
 
 
 def _is_1q(g: Optional[LGate]) -> bool:
-    return g is not None and g.kind in (DENSE, DIAG) and len(g.bits) == 1 and not _batched(g)
+    """1-qubit DENSE/DIAG gate (DENSE may carry one matrix per batch member)."""
+    return g is not None and g.kind in (DENSE, DIAG) and len(g.bits) == 1 and not (g.kind == DIAG and g.batched)
 
 
 def _is_cx(g: LGate) -> bool:
@@ -40,13 +41,19 @@ def _is_cx(g: LGate) -> bool:
 
 
 def _m1(g: LGate) -> np.ndarray:
-    return np.diag(g.data) if g.kind == DIAG else g.data
+    """2x2 matrix, or [B, 2, 2] for a batched gate (numpy matmul broadcasts over the batch axis)."""
+    if g.kind == DIAG:
+        return np.diag(g.data)
+    return g.data.reshape(-1, 2, 2) if g.batched else g.data
 
 
 def _mul_1q(later: LGate, earlier: LGate) -> LGate:
     if later.kind == DIAG and earlier.kind == DIAG:
         return LGate(DIAG, later.bits, later.data * earlier.data, name="fused")
-    return LGate(DENSE, later.bits, _m1(later) @ _m1(earlier), name="fused")
+    m = _m1(later) @ _m1(earlier)
+    if m.ndim == 3:
+        return LGate(DENSE, later.bits, np.ascontiguousarray(m.reshape(-1, 4)), batched=True, name="fused")
+    return LGate(DENSE, later.bits, m, name="fused")
 
 
 def _embed_1q(u: np.ndarray, j: int) -> np.ndarray:
@@ -72,7 +79,7 @@ def _merge_diag(a: LGate, b: LGate) -> LGate:
 def _simplify_mux(g: LGate) -> LGate:
     """A MUX whose two matrices are both diagonal is a 2-bit diagonal gate (cx.rz.cx = rzz):
     table index bit 0 = target, bit 1 = control."""
-    if g.kind != MUX:
+    if g.kind != MUX or g.batched:
         return g
     u0, u1 = g.data[:4].reshape(2, 2), g.data[4:].reshape(2, 2)
     if u0[0, 1] == 0 and u0[1, 0] == 0 and u1[0, 1] == 0 and u1[1, 0] == 0:
@@ -86,8 +93,16 @@ def _as_layer(g: LGate):
         m = _m1(g)
         return g.bits[0], None, m, m
     if g.kind == MUX:
-        return g.bits[0], g.bits[1], g.data[:4].reshape(2, 2), g.data[4:].reshape(2, 2)
+        u0, u1 = _mux_blocks(g)
+        return g.bits[0], g.bits[1], u0, u1
     return None
+
+
+def _mux_blocks(g: LGate):
+    """(U_control0, U_control1) of a MUX gate: 2x2 each, or [B, 2, 2] when batched."""
+    if g.batched:
+        return g.data[:, :4].reshape(-1, 2, 2), g.data[:, 4:].reshape(-1, 2, 2)
+    return g.data[:4].reshape(2, 2), g.data[4:].reshape(2, 2)
 
 
 def chain_fuse(gates: Sequence[LGate], R: int = 3) -> List[LGate]:
@@ -175,7 +190,7 @@ def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
             last[b] = j
 
     for g in gates:
-        if _batched(g) or g.data.ndim > 2:
+        if g.batched and not _is_1q(g):   # only batched 1-qubit gates take part in fusion
             out.append(g)
             touch(g, len(out) - 1)
             continue
@@ -183,16 +198,17 @@ def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
             t = g.bits[0]
             j = last.get(t)
             p = out[j] if j is not None else None
-            if p is not None and not _batched(p):
+            if p is not None:
                 if _is_1q(p):
                     out[j] = _mul_1q(g, p)
                     continue
-                if p.kind == DENSE and len(p.bits) == 2:
+                if p.kind == DENSE and len(p.bits) == 2 and not p.batched and not g.batched:
                     out[j] = LGate(DENSE, p.bits, _embed_1q(_m1(g), p.bits.index(t)) @ p.data, name="fused")
                     continue
                 if p.kind == MUX and p.bits[0] == t:      # 1q gate after a MUX on the same target
                     v = _m1(g)
-                    out[j] = mux_gate(v @ p.data[:4].reshape(2, 2), v @ p.data[4:].reshape(2, 2), t, p.bits[1], name="fused")
+                    u0, u1 = _mux_blocks(p)
+                    out[j] = mux_gate(v @ u0, v @ u1, t, p.bits[1], name="fused")
                     continue
                 if _is_cx(p) and p.bits[0] == t:          # 1q gate after cx on its target: V (c=0), V.X (c=1)
                     v = _m1(g)
@@ -207,7 +223,8 @@ def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
                 out[j] = None
                 g = mux_gate(u, X_MAT @ u, t, c, name="fused")
             elif p is not None and p.kind == MUX and p.bits == (t, c) and last.get(c) == j:
-                out[j] = _simplify_mux(mux_gate(p.data[:4].reshape(2, 2), X_MAT @ p.data[4:].reshape(2, 2), t, c, name="fused"))
+                u0, u1 = _mux_blocks(p)
+                out[j] = _simplify_mux(mux_gate(u0, X_MAT @ u1, t, c, name="fused"))
                 continue
         if g.kind == DIAG:
             js = [last[b] for b in g.bits if b in last]
@@ -223,7 +240,7 @@ def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
             for b in g.bits:
                 j = last.get(b)
                 p = out[j] if j is not None else None
-                if _is_1q(p):
+                if _is_1q(p) and not p.batched:
                     M = M @ _embed_1q(_m1(p), g.bits.index(b))
                     out[j] = None
             if M is not g.data:

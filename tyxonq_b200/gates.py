@@ -129,6 +129,7 @@ class LGate:
     # bookkeeping for gradients: (parameter slot, op name) of a parametrised gate
     param: Optional[int] = None
     name: str = ""
+    batched: bool = False   # data has a leading axis: one matrix per batch member
     mask: int = field(default=0, init=False)
     local_mask: int = field(default=0, init=False)
 
@@ -162,8 +163,9 @@ def dense_gate(mat: np.ndarray, qubits: Sequence[int], n: int, **kw: Any) -> LGa
     k = len(qubits)
     d = 1 << k
     m = np.asarray(mat, dtype=C128)
-    m = m.reshape(d, d) if m.size == d * d else m.reshape(-1, d * d)  # leading axis = batch of matrices
-    return LGate(DENSE, _bits_of(qubits, n), m, **kw)
+    if m.size == d * d:
+        return LGate(DENSE, _bits_of(qubits, n), m.reshape(d, d), **kw)
+    return LGate(DENSE, _bits_of(qubits, n), m.reshape(-1, d * d), batched=True, **kw)  # leading axis = batch
 
 
 def diag_gate(tab: np.ndarray, qubits: Sequence[int], n: int, **kw: Any) -> LGate:
@@ -185,8 +187,14 @@ def swap_gate(qubits: Sequence[int], n: int, pat_a: int, pat_b: int, **kw: Any) 
 
 def mux_gate(u0: np.ndarray, u1: np.ndarray, target_bit: int, control_bit: int, **kw: Any) -> LGate:
     """1-qubit gate on index bit ``target_bit``: u0 where index bit ``control_bit`` is 0, u1 where it is 1."""
-    d = np.concatenate([np.asarray(u0, dtype=C128).reshape(4), np.asarray(u1, dtype=C128).reshape(4)])
-    return LGate(MUX, (int(target_bit), int(control_bit)), d, **kw)
+    u0 = np.asarray(u0, dtype=C128)
+    u1 = np.asarray(u1, dtype=C128)
+    if u0.size == 4 and u1.size == 4:
+        d = np.concatenate([u0.reshape(4), u1.reshape(4)])
+        return LGate(MUX, (int(target_bit), int(control_bit)), d, **kw)
+    B = max(u0.size, u1.size) // 4   # one matrix pair per batch member
+    d = np.concatenate([np.broadcast_to(u0.reshape(-1, 4), (B, 4)), np.broadcast_to(u1.reshape(-1, 4), (B, 4))], axis=1)
+    return LGate(MUX, (int(target_bit), int(control_bit)), np.ascontiguousarray(d), batched=True, **kw)
 
 
 def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit: Optional[int] = None, **kw: Any) -> LGate:
@@ -194,11 +202,17 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
     ``control_bit`` (None: M_sel0 is used), layer i > 0 by the value of layer i-1's target bit."""
     assert 2 <= len(layers) <= 3
     bits = [int(t) for t, _, _ in layers]
-    data = np.concatenate([np.concatenate([np.asarray(a, dtype=C128).reshape(4), np.asarray(b, dtype=C128).reshape(4)])
-                           for _, a, b in layers])
+    B = max(max(np.asarray(a).size, np.asarray(b).size) for _, a, b in layers) // 4
+    blocks = []
+    for _, a, b in layers:
+        for m in (a, b):
+            blocks.append(np.broadcast_to(np.asarray(m, dtype=C128).reshape(-1, 4), (B, 4)))
+    data = np.ascontiguousarray(np.concatenate(blocks, axis=1))
     if control_bit is not None:
         bits.append(int(control_bit))
-    return LGate(CHAIN, tuple(bits), data, pat_a=1 if control_bit is not None else 0, **kw)
+    if B == 1:
+        return LGate(CHAIN, tuple(bits), data.reshape(-1), pat_a=1 if control_bit is not None else 0, **kw)
+    return LGate(CHAIN, tuple(bits), data, pat_a=1 if control_bit is not None else 0, batched=True, **kw)
 
 
 def classify_unitary(mat: np.ndarray, qubits: Sequence[int], n: int) -> LGate:

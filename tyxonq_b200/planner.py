@@ -138,7 +138,7 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
 
 def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_mats: int = 1, itemsize: int = 16) -> Program:
     """Pack scheduled gates into the ABI arrays.  ``batch_mats`` > 1: every gate's ``data`` has a
-    leading batch axis (one matrix per batch member).  (``itemsize`` is accepted for call-site
+    leading batch axis (one matrix per batch member) when ``gate.batched`` is set.  (``itemsize`` is accepted for call-site
     symmetry; the descriptors do not depend on the state dtype.)"""
     m_eff = min(tile.m, n)
     tile = TileConfig(m=m_eff, L=min(tile.L, m_eff), threads=tile.threads, ctas_per_sm=tile.ctas_per_sm,
@@ -170,6 +170,7 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
         for j, p in enumerate(hb):
             ps["hb"][j] = p
         maxk = 0
+        any_batched = False
         for idx in chosen:
             g = gates[idx]
             e = garr[gi]
@@ -208,7 +209,8 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
                 else:
                     maxk = max(maxk, g.k)
             d = np.asarray(g.data, dtype=C128)
-            if batch_mats > 1:
+            if batch_mats > 1 and g.batched:
+                any_batched = True
                 d = d.reshape(batch_mats, -1)
                 e["mat_off"] = mat_off
                 e["mat_bstride"] = d.shape[1]
@@ -223,6 +225,6 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
             gi += 1
         ps["max_dense_k"] = maxk
         cnt = mat_off - int(ps["mat_begin"])
-        ps["mat_count"] = cnt if (batch_mats == 1 and cnt <= 4096) else 0   # staged in shared memory
+        ps["mat_count"] = cnt if (not any_batched and cnt <= 4096) else 0   # staged in shared memory
     flat = np.concatenate(mats) if mats else np.zeros(0, dtype=C128)
     return Program(n=n, passes=passes, gates=garr, mats=flat, n_gates_in=len(gates), tile=tile, order=order)
