@@ -164,6 +164,25 @@ int tqb_grad_pair(const void *bra, const void *ket, int n, int dtype, const tqb_
 int tqb_grad_dense(const void *bra, const void *ket, int n, int dtype, int k, const int *bits,
                    const double *gen_host, double scale, double *out_dev, int slot, void *stream);
 
+/* Whole sweeps of PAIR rotations on a SMALL state (2^n amplitudes resident in L2) in ONE launch: a
+ * persistent grid walks the steps with a grid-wide barrier between them instead of one launch per gate.
+ * Step j rotates the pair (pattern A, pattern B) of its k target bits by [[c, -s], [s, c]] where the
+ * parity of popc(index & zmask) is even and by [[c, s], [-s, c]] where it is odd (UCC excitation
+ * exp(theta G), statevector_ops.py:140-168).  mode 0: apply steps 0..n_steps-1 to `ket` only (forward).
+ * mode 1: reverse sweep of the adjoint gradient (civector_ops.py:141-200): for every step,
+ * out_dev[slot] += scale * Re sum s(i) (conj(bra_A) ket_B - conj(bra_B) ket_A), then the rotation is
+ * applied to ket AND bra (pass the un-apply angles).  steps_dev: device array of tqb_pair_step.
+ * sync_dev: one zero-initialised 64-bit word in device memory per call (grid barrier counter).    */
+typedef struct tqb_pair_step {
+  int32_t k;
+  int32_t slot;
+  int8_t sbits[TQB_MAX_GATE_BITS]; /* target bits ascending (index bits: the whole state is the tile) */
+  uint64_t off_a, off_b, zmask;
+  double c, s, scale;
+} tqb_pair_step; /* 64 bytes */
+int tqb_pair_sweep(void *ket, void *bra, int n, int dtype, const tqb_pair_step *steps_dev, int n_steps,
+                   int mode, double *out_dev, unsigned long long *sync_dev, void *stream);
+
 /* ---- measurement --------------------------------------------------------------------- */
 /* replaces StatevectorEngine._project_z (engine.py:1075-1087): zero the half with
  * bit != keep, then scale by 1/sqrt(sum |psi|^2) when that sum is > 0.                      */

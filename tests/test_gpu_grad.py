@@ -96,6 +96,18 @@ def test_ucc_small_energy_grad(cuda_device):
     assert abs(e - e_ref) < 1e-10 and np.abs(g - g_ref).max() < 1e-8
     fd = O.central_fd_gradient(lambda p: U.energy(p, Hs, n, nes, ex_ops, pids), params, 1e-6)
     assert np.abs(g - fd).max() < 1e-6
+    # the per-gate path (fused passes + tqb_grad_pair; what states beyond the L2-resident regime use) agrees
+    sv2 = ucc.UCCStatevector(n, nes, ex_ops, pids, ham, device=cuda_device)
+    assert sv.use_sweep
+    sv2.use_sweep = False
+    for graph in (False, True, True):
+        e2, g2 = sv2.energy_and_grad(params, graph=graph)
+        assert abs(e2 - e_ref) < 1e-10 and np.abs(g2 - g_ref).max() < 1e-8
+    # complex64 state: 1e-5 tolerance
+    import torch as _t
+    sv3 = ucc.UCCStatevector(n, nes, ex_ops, pids, ham, device=cuda_device, dtype=_t.complex64)
+    e3, g3 = sv3.energy_and_grad(params)
+    assert abs(e3 - e_ref) < 1e-4 and np.abs(g3 - g_ref).max() < 1e-3
 
 
 def test_ucc_h2o_shape_energy_grad(cuda_device):

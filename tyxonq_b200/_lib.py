@@ -35,6 +35,11 @@ PASS_DTYPE = np.dtype([
     ("mat_begin", "<i4"), ("mat_count", "<i4"),
     ("hb", "i1", (MAX_TILE_HIGH,)),
 ], align=True)
+PAIR_STEP_DTYPE = np.dtype([
+    ("k", "<i4"), ("slot", "<i4"), ("sbits", "i1", (MAX_GATE_BITS,)),
+    ("off_a", "<u8"), ("off_b", "<u8"), ("zmask", "<u8"), ("c", "<f8"), ("s", "<f8"), ("scale", "<f8"),
+], align=True)
+assert PAIR_STEP_DTYPE.itemsize == 64, PAIR_STEP_DTYPE.itemsize
 assert GATE_DTYPE.itemsize == 48, GATE_DTYPE.itemsize
 assert PASS_DTYPE.itemsize == 44, PASS_DTYPE.itemsize
 
@@ -63,6 +68,7 @@ SIGNATURES = {
     "tqb_inner": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp]),
     "tqb_grad_pair": (_i, [_vp, _vp, _i, _i, _vp, _d, _vp, _i, _vp]),
     "tqb_grad_dense": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _d, _vp, _i, _vp]),
+    "tqb_pair_sweep": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "tqb_project_z": (_i, [_vp, _i, _i64, _i, _i, _i, _vp]),
     "tqb_scale": (_i, [_vp, _i, _i64, _i, _d, _vp]),
     "tqb_probabilities": (_i, [_vp, _i, _i64, _i, _vp, _vp]),

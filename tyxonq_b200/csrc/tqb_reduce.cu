@@ -286,6 +286,58 @@ __global__ void __launch_bounds__(RT) grad_dense_kernel(const cplx<T> *__restric
   if (threadIdx.x == 0) atomicAdd(out, scale * tot[0]);
 }
 
+// ---- persistent PAIR sweep for small states ------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1ull);
+    while (*((volatile unsigned long long *)counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RT) pair_sweep_kernel(cplx<T> *ket, cplx<T> *bra, int n, const tqb_pair_step *__restrict__ steps,
+                                                        int n_steps, int mode, double *out, unsigned long long *sync) {
+  __shared__ double sm[RT / 32];
+  __shared__ tqb_pair_step st;
+  const unsigned long long nblocks = gridDim.x;
+  for (int j = 0; j < n_steps; ++j) {
+    if (threadIdx.x < (int)(sizeof(tqb_pair_step) / 4))
+      reinterpret_cast<uint32_t *>(&st)[threadIdx.x] = reinterpret_cast<const uint32_t *>(steps + j)[threadIdx.x];
+    __syncthreads();
+    const int k = st.k;
+    const uint64_t ngroups = 1ull << (n - k);
+    const double c = st.c, s = st.s;
+    double v[1] = {0.0};
+    for (uint64_t g = (uint64_t)blockIdx.x * RT + threadIdx.x; g < ngroups; g += nblocks * RT) {
+      const uint64_t base = insert_zeros64(g, st.sbits, k);
+      const uint64_t ia = base + st.off_a, ib = base + st.off_b;
+      const bool odd = __popcll(base & st.zmask) & 1;
+      const double sg = odd ? -s : s;
+      cplx<T> ka = ket[ia], kb = ket[ib];
+      if (mode == 1) {
+        cplx<T> ba = bra[ia], bb = bra[ib];
+        double r = ((double)ba.x * kb.x + (double)ba.y * kb.y) - ((double)bb.x * ka.x + (double)bb.y * ka.y);
+        v[0] += odd ? -r : r;
+        bra[ia] = cplx<T>{(T)(c * ba.x - sg * bb.x), (T)(c * ba.y - sg * bb.y)};
+        bra[ib] = cplx<T>{(T)(sg * ba.x + c * bb.x), (T)(sg * ba.y + c * bb.y)};
+      }
+      ket[ia] = cplx<T>{(T)(c * ka.x - sg * kb.x), (T)(c * ka.y - sg * kb.y)};
+      ket[ib] = cplx<T>{(T)(sg * ka.x + c * kb.x), (T)(sg * ka.y + c * kb.y)};
+    }
+    if (mode == 1) {
+      double tot[1];
+      block_reduce<1>(v, sm, tot);
+      if (threadIdx.x == 0 && tot[0] != 0.0) atomicAdd(out + st.slot, st.scale * tot[0]);
+    }
+    if (j + 1 < n_steps) grid_barrier(sync, (unsigned long long)(j + 1) * nblocks);
+  }
+}
+
 // ---- projection / scaling / probabilities ----------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(RT) project_kernel(cplx<T> *state, Seg sg, int bit, int keep, double *partial) {
@@ -623,6 +675,26 @@ int tqb_grad_dense(const void *bra, const void *ket, int n, int dtype, int k, co
   if (by_dtype(dtype, [&] { grad_dense_kernel<double><<<(unsigned)bx, RT, 0, st>>>(CD(bra), CD(ket), dg, scale, out_dev + slot); },
                [&] { grad_dense_kernel<float><<<(unsigned)bx, RT, 0, st>>>(CF(bra), CF(ket), dg, scale, out_dev + slot); })) return -1;
   TQB_CHECK_LAUNCH("grad_dense_kernel");
+  return 0;
+}
+
+int tqb_pair_sweep(void *ket, void *bra, int n, int dtype, const tqb_pair_step *steps_dev, int n_steps, int mode,
+                   double *out_dev, unsigned long long *sync_dev, void *stream) {
+  TQB_REQUIRE(ket && steps_dev && sync_dev && n >= 1 && n <= 26 && n_steps >= 1 && (mode == 0 || (mode == 1 && bra && out_dev)),
+              "tqb_pair_sweep: bad arguments (n <= 26: the state must stay L2-resident)");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  cudaStream_t st = as_stream(stream);
+  TQB_CHECK_CUDA(cudaMemsetAsync(sync_dev, 0, sizeof(unsigned long long), st));
+  // all CTAs must be co-resident for the grid barrier: one CTA per SM at most
+  uint64_t want = ((1ull << (n > 2 ? n - 2 : 0)) + RT - 1) / RT;
+  int grid = (int)(want < (uint64_t)ws->sm_count ? want : (uint64_t)ws->sm_count);
+  if (grid < 1) grid = 1;
+  if (by_dtype(dtype,
+               [&] { pair_sweep_kernel<double><<<grid, RT, 0, st>>>(MD(ket), MD(bra), n, steps_dev, n_steps, mode, out_dev, sync_dev); },
+               [&] { pair_sweep_kernel<float><<<grid, RT, 0, st>>>(MF(ket), MF(bra), n, steps_dev, n_steps, mode, out_dev, sync_dev); }))
+    return -1;
+  TQB_CHECK_LAUNCH("pair_sweep_kernel");
   return 0;
 }
 

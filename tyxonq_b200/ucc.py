@@ -239,6 +239,25 @@ class UCCStatevector:
         self._grad_descs = np.ascontiguousarray(full.gates)
         self._kb = torch.empty((2, 1 << self.n), dtype=dtype, device=self.device)
         self._gout = torch.zeros(max(self.n_params, 1), dtype=torch.float64, device=self.device)
+        # small states: the whole forward / reverse sweep is ONE persistent launch each (tqb_pair_sweep)
+        self.use_sweep = self.n <= 26 and len(self._proto) > 0
+        N = len(self._proto)
+        self._steps_np = np.zeros(2 * N, dtype=_lib.PAIR_STEP_DTYPE)   # [forward steps | reverse steps]
+        fwd_full = compile_program(self._proto, self.n, TileConfig(m=self.n, L=min(self.tile.L, self.n), max_gates=1), itemsize=itemsize)
+        assert fwd_full.order == list(range(N))
+        for half, descs in ((0, fwd_full.gates), (1, self._grad_descs)):
+            for i in range(N):
+                e = self._steps_np[half * N + i]
+                d = descs[i]
+                j = i if half == 0 else N - 1 - i
+                e["k"] = d["k"]
+                e["slot"] = self.param_ids[j]
+                e["sbits"][:] = d["sbits"]
+                e["off_a"], e["off_b"], e["zmask"] = d["off_a"], d["off_b"], d["zmask"]
+                e["scale"] = -2.0 * float(self._signs[j])
+        self._steps_host = torch.zeros(self._steps_np.nbytes, dtype=torch.uint8).pin_memory()
+        self._steps_dev = torch.zeros(max(self._steps_np.nbytes, 8), dtype=torch.uint8, device=self.device)
+        self._sync = torch.zeros(2, dtype=torch.int64, device=self.device)
 
     # -- matrices for the current parameters -------------------------------------------------
     def _fill(self, prog, params: np.ndarray, reverse: bool) -> np.ndarray:
@@ -279,7 +298,12 @@ class UCCStatevector:
         kb = self._kb
         ptr, n, _, dt, stream = P._prep(kb[0])
         _lib.check(lib.tqb_init_basis(ptr, n, 1, dt, 0, self.hf_index, stream))
-        if self._proto:
+        N = len(self._proto)
+        if self.use_sweep:
+            self._steps_dev.copy_(self._steps_host, non_blocking=True)
+            _lib.check(lib.tqb_pair_sweep(kb[0].data_ptr(), 0, n, dt, self._steps_dev.data_ptr(), N, 0, 0,
+                                          self._sync.data_ptr(), stream))
+        elif self._proto:
             self._fwd_dev.upload()
             self._rev_dev.upload()
             self._fwd_dev.run(kb[0])
@@ -287,7 +311,11 @@ class UCCStatevector:
         _lib.check(lib.tqb_inner(kb[0].data_ptr(), kb[1].data_ptr(), n, 1, dt, self._e.data_ptr(), stream))
         self._gout.zero_()
         ket_ptr, bra_ptr = kb[0].data_ptr(), kb[1].data_ptr()
-        N = len(self._proto)
+        if self.use_sweep:
+            step_bytes = self._steps_np.dtype.itemsize
+            _lib.check(lib.tqb_pair_sweep(ket_ptr, bra_ptr, n, dt, self._steps_dev.data_ptr() + N * step_bytes, N, 1,
+                                          self._gout.data_ptr(), self._sync.data_ptr() + 8, stream))
+            N = 0  # the per-gate loop below is the large-state path
         t = self.tile
         passes = self._rev_dev._passes
         psz = passes.dtype.itemsize
@@ -314,7 +342,15 @@ class UCCStatevector:
             self._out_host = torch.zeros(1 + max(self.n_params, 1), dtype=torch.float64).pin_memory()
             self._graph = None
             self._calls = 0
-        if self._proto:
+        if self._proto and self.use_sweep:
+            N = len(self._proto)
+            th = params[np.asarray(self.param_ids)]
+            c, sn = np.cos(th), np.sin(th) * self._signs
+            st = self._steps_np
+            st["c"][:N], st["s"][:N] = c, sn                      # forward: rotation by +theta (sign folded in)
+            st["c"][N:], st["s"][N:] = c[::-1], -sn[::-1]         # reverse: un-apply, last excitation first
+            self._steps_host.copy_(torch.from_numpy(st.view(np.uint8).reshape(-1)))
+        elif self._proto:
             self._fwd_dev.fill_host(self._fill(self._fwd, params, False))
             self._rev_dev.fill_host(self._fill(self._rev, params, True))
         with torch.cuda.device(self.device):
