@@ -122,6 +122,8 @@ def ensure_device(device_index: int) -> None:
     check(load().tqb_init(int(device_index)))
     if os.environ.get("TQB_TMA"):  # tuning knob: 0 = LDG/STG, 2 / 3 = TMA ring depth, 1 = auto
         load().tqb_set_tma(int(os.environ["TQB_TMA"]))
+    if os.environ.get("TQB_DBG"):  # profiling only: 1 = no gate arithmetic, 2 = no bulk loads, 4 = no bulk stores
+        load().tqb_set_tma(256 + int(os.environ["TQB_DBG"]))
     _inited_devices.add(device_index)
 
 

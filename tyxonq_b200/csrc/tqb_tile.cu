@@ -143,7 +143,8 @@ __device__ __forceinline__ void consumer_sync(int count) { asm volatile("bar.syn
 template <typename T, int MAXK, int NB>
 __global__ void __launch_bounds__(288, 2)
 tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
-                     const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats) {
+                     const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats,
+                     const int dbg) {  // dbg (profiling only): 1 = skip gate arithmetic, 2 = skip bulk loads, 4 = skip bulk stores
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // layout: NB tiles | 8 mbarrier slots (full[NB], done[NB]) | staged matrices | run-offset table | descriptors
   const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
@@ -191,6 +192,10 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
       const int b = (int)(it % NB);
       cplx<T> *dst = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
       const cplx<T> *src = tile_ptr(it);
+      if (dbg & 2) {
+        if (lane == 0) mbar_arrive(&full[b]);
+        return;
+      }
       if (lane == 0) mbar_expect_tx(&full[b], (uint32_t)tile_bytes);
       __syncwarp();
       for (uint32_t j = lane; j < nruns; j += 32) bulk_load(dst + (size_t)j * run_elems, src + roff[j], run_bytes, &full[b]);
@@ -207,7 +212,8 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
       mbar_wait(&done[b], (uint32_t)((it / NB) & 1));  // consumers finished tile it (their fence.proxy.async precedes the arrive)
       cplx<T> *dstg = tile_ptr(it);
       const cplx<T> *srcs = reinterpret_cast<const cplx<T> *>(smem_raw + b * tile_bytes);
-      for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], srcs + (size_t)j * run_elems, run_bytes);
+      if (!(dbg & 4))
+        for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], srcs + (size_t)j * run_elems, run_bytes);
       bulk_commit();
     }
     bulk_wait_all0();
@@ -221,7 +227,8 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
     const unsigned long long bm = tt >> tb;
     const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
     cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
-    if (geo.mat_count > 0) {  // matrices staged in shared memory: keep the pointer's address space known (LDS, not LD)
+    if (dbg & 1) {
+    } else if (geo.mat_count > 0) {  // matrices staged in shared memory: keep the pointer's address space known (LDS, not LD)
       const cplx<T> *sm = smats - geo.mat_begin;
       for (int gi = 0; gi < n_gates; ++gi) {
         tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], sm, (size_t)0, tid, ncons);
@@ -394,6 +401,7 @@ static int launch_pass(void *state, const TileGeom &geo, int64_t batch, const tq
 }
 
 static std::atomic<int> g_use_tma{1};
+static std::atomic<int> g_dbg{0};  // profiling switches of the TMA kernel (tqb_set_tma(256 + flags))
 
 template <typename T, int MAXK, int NB>
 static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
@@ -421,7 +429,7 @@ static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, cons
   unsigned long long grid = (unsigned long long)ws.sm_count * per_sm;
   if (grid > total) grid = total;
   kern<<<(unsigned)grid, block, smem, st>>>(reinterpret_cast<cplx<T> *>(state), geo, (long long)batch, gates, n_gates,
-                                             reinterpret_cast<const cplx<T> *>(mats));
+                                             reinterpret_cast<const cplx<T> *>(mats), g_dbg.load());
   TQB_CHECK_LAUNCH("tile_pass_tma_kernel");
   *used = true;
   return 0;
@@ -468,6 +476,10 @@ using namespace tqb;
 extern "C" {
 
 int tqb_set_tma(int mode) {
+  if (mode >= 256) {  // 256 + flags: profiling switches (results are WRONG with any flag set)
+    g_dbg.store(mode - 256);
+    return g_use_tma.load();
+  }
   const int old = g_use_tma.exchange(mode < 0 ? 0 : (mode > 4 ? 1 : mode));
   return old;
 }
