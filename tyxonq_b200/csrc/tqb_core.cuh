@@ -346,26 +346,66 @@ TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, 
   const int nz = ctrl_local ? R + 1 : R;
   const uint32_t free_bits = (uint32_t)(m - nz);
   const uint32_t ngroups = 1u << (m - R);  // control value = top bit of the group counter when local
-  for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
-    uint32_t cv = cv_fixed, lo = gi;
+  auto locate = [&](uint32_t gi, uint32_t &base, uint32_t &cv) {
+    uint32_t lo = gi;
+    cv = cv_fixed;
     if (ctrl_local) {
       cv = gi >> free_bits;
       lo = gi & ((1u << free_bits) - 1u);
     }
-    uint32_t base = lo;
+    base = lo;
 #pragma unroll
     for (int j = 0; j < NZ; ++j)
       if (j < nz) base = ((base >> sb[j]) << (sb[j] + 1u)) | (base & ((1u << sb[j]) - 1u));
     if (ctrl_local) base |= cv << cb;
+  };
+  auto offset = [&](uint32_t base, int s) {
+    uint32_t o = base;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+      if (s & (1 << i)) o |= 1u << tb[i];
+    return o;
+  };
+  uint32_t gi = tid;
+  // two groups per iteration: two independent dependency chains keep the FP pipe fed (the sweep is latency bound
+  // with the 3-4 consumer warps per scheduler that the tile buffers leave room for)
+  if (sizeof(T) == 4 && ngroups % (2u * (uint32_t)nthreads) == 0) {  // complex64 only: complex128 would spill
+    for (; gi < ngroups; gi += 2u * nthreads) {
+      uint32_t ba, ca, bb, cb2;
+      locate(gi, ba, ca);
+      locate(gi + nthreads, bb, cb2);
+      cplx<T> va[1 << R], vb[1 << R];
+#pragma unroll
+      for (int s = 0; s < (1 << R); ++s) {
+        va[s] = tile[offset(ba, s)];
+        vb[s] = tile[offset(bb, s)];
+      }
+      chain_layer<T, R, 0, -1>(va, M + 4 * ca);
+      chain_layer<T, R, 0, -1>(vb, M + 4 * cb2);
+      chain_layer<T, R, 1, 0>(va, M + 8);
+      chain_layer<T, R, 1, 0>(vb, M + 8);
+      chain_layer<T, R, 1, 1>(va, M + 12);
+      chain_layer<T, R, 1, 1>(vb, M + 12);
+      if (R > 2) {
+        chain_layer<T, R, (R > 2 ? 2 : 1), 0>(va, M + 16);
+        chain_layer<T, R, (R > 2 ? 2 : 1), 0>(vb, M + 16);
+        chain_layer<T, R, (R > 2 ? 2 : 1), 1>(va, M + 20);
+        chain_layer<T, R, (R > 2 ? 2 : 1), 1>(vb, M + 20);
+      }
+#pragma unroll
+      for (int s = 0; s < (1 << R); ++s) {
+        tile[offset(ba, s)] = va[s];
+        tile[offset(bb, s)] = vb[s];
+      }
+    }
+    return;
+  }
+  for (; gi < ngroups; gi += nthreads) {
+    uint32_t base, cv;
+    locate(gi, base, cv);
     cplx<T> v[1 << R];
 #pragma unroll
-    for (int s = 0; s < (1 << R); ++s) {
-      uint32_t o = base;
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-        if (s & (1 << i)) o |= 1u << tb[i];
-      v[s] = tile[o];
-    }
+    for (int s = 0; s < (1 << R); ++s) v[s] = tile[offset(base, s)];
     chain_layer<T, R, 0, -1>(v, M + 4 * cv);
     chain_layer<T, R, 1, 0>(v, M + 8);
     chain_layer<T, R, 1, 1>(v, M + 12);
@@ -374,13 +414,7 @@ TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, 
       chain_layer<T, R, (R > 2 ? 2 : 1), 1>(v, M + 20);
     }
 #pragma unroll
-    for (int s = 0; s < (1 << R); ++s) {
-      uint32_t o = base;
-#pragma unroll
-      for (int i = 0; i < R; ++i)
-        if (s & (1 << i)) o |= 1u << tb[i];
-      tile[o] = v[s];
-    }
+    for (int s = 0; s < (1 << R); ++s) tile[offset(base, s)] = v[s];
   }
 }
 

@@ -141,7 +141,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void consumer_sync(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 
 template <typename T, int MAXK, int NB>
-__global__ void __launch_bounds__(288, 2)
+__global__ void __launch_bounds__(160, 3)
 tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                      const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats,
                      const int dbg) {  // dbg (profiling only): 1 = skip gate arithmetic, 2 = skip bulk loads, 4 = skip bulk stores
@@ -407,7 +407,7 @@ template <typename T, int MAXK, int NB>
 static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
                            const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st, bool *used) {
   *used = false;
-  const int max_threads = 256;
+  const int max_threads = 128;  // consumers; + 1 producer warp = 160 threads, <= 136 registers, 3 CTAs per SM
   if (threads > max_threads) threads = max_threads;
   const size_t smem = NB * (sizeof(cplx<T>) << geo.m) + 64 + (sizeof(uint64_t) << geo.h) +
                       (size_t)geo.mat_count * sizeof(cplx<T>) + (size_t)n_gates * sizeof(tqb_gate);
