@@ -330,6 +330,24 @@ TQB_HD void chain_layer(cplx<T> (&v)[1 << R], const cplx<T> *M) {
   }
 }
 
+// layer I > 0, both selector values in one unrolled block: 2^(R-1) independent pairs keep the FP pipe busy
+template <typename T, int R, int I>
+TQB_HD void chain_layer_sel(cplx<T> (&v)[1 << R], const cplx<T> *M) {
+  const cplx<T> a00 = M[0], a01 = M[1], a10 = M[2], a11 = M[3];
+  const cplx<T> b00 = M[4], b01 = M[5], b10 = M[6], b11 = M[7];
+#pragma unroll
+  for (int s = 0; s < (1 << R); ++s) {
+    if (s & (1 << I)) continue;
+    const bool sel = (s >> (I > 0 ? I - 1 : 0)) & 1;
+    const cplx<T> a = v[s], b = v[s | (1 << I)];
+    cplx<T> x{0, 0}, y{0, 0};
+    cmac(x, sel ? b00 : a00, a); cmac(x, sel ? b01 : a01, b);
+    cmac(y, sel ? b10 : a10, a); cmac(y, sel ? b11 : a11, b);
+    v[s] = x;
+    v[s | (1 << I)] = y;
+  }
+}
+
 template <typename T, int R>
 TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
   uint32_t tb[R];
@@ -382,15 +400,11 @@ TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, 
       }
       chain_layer<T, R, 0, -1>(va, M + 4 * ca);
       chain_layer<T, R, 0, -1>(vb, M + 4 * cb2);
-      chain_layer<T, R, 1, 0>(va, M + 8);
-      chain_layer<T, R, 1, 0>(vb, M + 8);
-      chain_layer<T, R, 1, 1>(va, M + 12);
-      chain_layer<T, R, 1, 1>(vb, M + 12);
+      chain_layer_sel<T, R, 1>(va, M + 8);
+      chain_layer_sel<T, R, 1>(vb, M + 8);
       if (R > 2) {
-        chain_layer<T, R, (R > 2 ? 2 : 1), 0>(va, M + 16);
-        chain_layer<T, R, (R > 2 ? 2 : 1), 0>(vb, M + 16);
-        chain_layer<T, R, (R > 2 ? 2 : 1), 1>(va, M + 20);
-        chain_layer<T, R, (R > 2 ? 2 : 1), 1>(vb, M + 20);
+        chain_layer_sel<T, R, (R > 2 ? 2 : 1)>(va, M + 16);
+        chain_layer_sel<T, R, (R > 2 ? 2 : 1)>(vb, M + 16);
       }
 #pragma unroll
       for (int s = 0; s < (1 << R); ++s) {
@@ -407,12 +421,8 @@ TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, 
 #pragma unroll
     for (int s = 0; s < (1 << R); ++s) v[s] = tile[offset(base, s)];
     chain_layer<T, R, 0, -1>(v, M + 4 * cv);
-    chain_layer<T, R, 1, 0>(v, M + 8);
-    chain_layer<T, R, 1, 1>(v, M + 12);
-    if (R > 2) {
-      chain_layer<T, R, (R > 2 ? 2 : 1), 0>(v, M + 16);
-      chain_layer<T, R, (R > 2 ? 2 : 1), 1>(v, M + 20);
-    }
+    chain_layer_sel<T, R, 1>(v, M + 8);
+    if (R > 2) chain_layer_sel<T, R, (R > 2 ? 2 : 1)>(v, M + 16);
 #pragma unroll
     for (int s = 0; s < (1 << R); ++s) tile[offset(base, s)] = v[s];
   }
