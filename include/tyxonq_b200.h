@@ -207,6 +207,21 @@ int tqb_sample(const void *state, int n, int64_t batch, int dtype, const double 
                const double *uniforms_dev, int64_t shots, int64_t *idx_dev, void *stream);
 
 /* ---- sharded states ------------------------------------------------------------------ */
+/* The sampler of a state sharded over ranks (rank = highest index bits; engine.py:377-418 at sizes
+ * one GPU cannot hold).  Same blocked CDF as above, bit for bit: every rank computes the totals
+ * of its own chunks (tqb_chunk_totals: batch * n_chunks doubles), the ranks all-gather them in
+ * rank order, every rank runs the sequential prefix over ALL chunks (tqb_chunk_prefix:
+ * batch * (n_chunks + 1) doubles) and resolves the uniforms whose chunk it owns
+ * (tqb_sample_shard: chunks [chunk_first, chunk_first + 2^n_local / TQB_SCAN_BLOCK) of the
+ * n_chunks_total the prefix covers; idx = GLOBAL index, -1 for samples owned by another rank,
+ * tail_index for u beyond the last chunk).  A max-reduction over ranks assembles the result.   */
+int tqb_chunk_totals(const void *state, int n, int64_t batch, int dtype, double *totals_dev,
+                     void *stream);
+int tqb_chunk_prefix(const double *totals_dev, int64_t n_chunks, int64_t batch,
+                     double *chunk_prefix_dev, void *stream);
+int tqb_sample_shard(const void *state, int n_local, int dtype, const double *chunk_prefix_dev,
+                     int64_t n_chunks_total, int64_t chunk_first, int64_t tail_index,
+                     const double *uniforms_dev, int64_t shots, int64_t *idx_dev, void *stream);
 /* Local half of a global<->local qubit exchange: dst/src are chunk views; copies `count`
  * complex elements (used to unpack received blocks back into the shard).                     */
 int tqb_copy(void *dst, const void *src, int64_t count, int dtype, void *stream);

@@ -106,3 +106,107 @@ def test_plan_needs_no_exchange_for_diagonal_or_control_use_of_global_bits():
     assert plan.n_exchanges == 0
     ops2 = ops + [("h", 0)]
     assert plan_sharded(lower_and_fuse(ops2, n), n, 2).n_exchanges == 1
+
+
+# ---- sharded sampling: restore the identity layout, all-gather the chunk totals, resolve locally ----
+_BLK = 16  # chunk length of the test executor (the CUDA library uses 4096); the contract is the same for any length
+
+
+class _EmuSampler(_EmuLocal):
+    def chunk_totals(self, state, n_local):
+        p = (state.numpy().real ** 2 + state.numpy().imag ** 2).reshape(-1, _BLK)
+        return torch.from_numpy(np.cumsum(p, axis=1)[:, -1].copy())
+
+    def chunk_prefix(self, totals_all):
+        return torch.from_numpy(np.concatenate([[0.0], np.cumsum(totals_all.numpy())]))
+
+    def sample_shard(self, state, n_local, prefix, chunk_first, tail_index, uniforms):
+        pre = prefix.numpy()
+        total = pre[-1]
+        nc = pre.size - 1
+        p = (state.numpy().real ** 2 + state.numpy().imag ** 2).reshape(-1, _BLK)
+        out = np.empty(uniforms.numel(), dtype=np.int64)
+        for s, u in enumerate(uniforms.numpy()):
+            c = int(np.searchsorted(pre[1:] / total, u, side="right"))
+            if c >= nc:
+                out[s] = tail_index
+            elif not (chunk_first <= c < chunk_first + p.shape[0]):
+                out[s] = -1
+            else:
+                within = pre[c] + np.cumsum(p[c - chunk_first])
+                out[s] = c * _BLK + int(np.searchsorted(within / total, u, side="right"))
+        return torch.from_numpy(out)
+
+
+def _sample_worker(rank, world, port, n, ops, uniforms, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tyxonq_b200.sharded import ShardedState, lower_and_fuse, plan_sharded
+        st = ShardedState(n, torch.complex128, torch.device("cpu"), backend=_EmuSampler())
+        plan = plan_sharded(lower_and_fuse(ops, n), n, st.g)
+        st.init_zero()
+        st.run(plan)
+        moved = st.phys != list(range(n))
+        idx = st.sample(torch.from_numpy(uniforms))
+        assert st.phys == list(range(n))
+        np.save(os.path.join(out_dir, f"idx{rank}.npy"), idx.numpy())
+        np.save(os.path.join(out_dir, f"shard{rank}.npy"), st.state.numpy())
+        counts = st.counts(torch.from_numpy(uniforms))   # a collective: every rank calls it
+        if rank == 0:
+            np.save(os.path.join(out_dir, "moved.npy"), np.array([int(moved)]))
+            import json
+            with open(os.path.join(out_dir, "counts.json"), "w") as f:
+                json.dump(counts, f)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,kind", [(2, 8, "hea"), (4, 9, "trotter"), (4, 8, "random")])
+def test_sharded_sampling_is_bit_exact_with_the_oracle(tmp_path, world, n, kind):
+    rng = np.random.default_rng(world * 100 + n)
+    if kind == "hea":
+        ops = O.hea_ops(n, 3, rng.uniform(-3, 3, 6 * n))
+    elif kind == "trotter":
+        ops = O.trotter_ops(*O.tfim_terms(n), 1.0, 2)
+    else:
+        from tests.conftest import random_ops
+        ops = random_ops(rng, n, 80)
+    u = rng.random(300)
+    u[:3] = [0.0, 0.5, 1.0 - 2 ** -53]
+    mp.spawn(_sample_worker, args=(world, _free_port(), n, ops, u, str(tmp_path)), nprocs=world, join=True)
+    ref, _ = O.evolve_ops(n, ops, mode="run")
+    # after restore_layout the shards ARE the logical state, rank-major
+    full = np.concatenate([np.load(tmp_path / f"shard{r}.npy") for r in range(world)])
+    assert np.abs(full - ref).max() < 1e-12
+    want = O.sample_indices(full.real ** 2 + full.imag ** 2, u, block=_BLK)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"idx{r}.npy"), want)
+    assert int(np.load(tmp_path / "moved.npy")[0]) == 1   # the layout really had to be restored
+    import json
+    counts = json.load(open(tmp_path / "counts.json"))
+    assert counts == O.counts_from_indices(want, n)
+
+
+def test_plan_restore_reaches_identity_from_any_layout():
+    from tyxonq_b200.sharded import plan_restore
+    rng = np.random.default_rng(5)
+    for n, g in [(8, 1), (9, 2), (10, 3), (7, 0)]:
+        for _ in range(20):
+            phys = list(rng.permutation(n))
+            plan = plan_restore(phys, n, g)
+            assert plan.final_phys == list(range(n)) and plan.n_exchanges <= 2
+            # replay on an index table: apply bit swaps / exchanges to the physical positions
+            cur = list(phys)
+            n_local = n - g
+            for seg in plan.segments:
+                for gt in seg.gates:
+                    a, b = gt.bits
+                    assert a < n_local and b < n_local
+                    cur = [b if p == a else a if p == b else p for p in cur]
+                if seg.exchange_after:
+                    m = {n_local - g + i: n_local + i for i in range(g)}
+                    m.update({v: k for k, v in m.items()})
+                    cur = [m.get(p, p) for p in cur]
+            assert cur == list(range(n))

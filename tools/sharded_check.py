@@ -38,16 +38,31 @@ def main():
             z = st.expect_z_all().cpu().numpy()
             nrm = P.norm2(st.state)
             dist.all_reduce(nrm)
+            # sharded sampling: restore the identity layout, then the blocked-CDF sampler across ranks.  It must return
+            # exactly what the single-GPU sampler returns on the gathered state (same contract, bit for bit).
+            u = torch.from_numpy(np.random.default_rng(3).random(4096))
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            idx = st.sample(u)
+            t1.record(); torch.cuda.synchronize()
+            sample_ms = t0.elapsed_time(t1)
+            parts = [torch.empty_like(st.state) for _ in range(world)] if rank == 0 else None
+            dist.gather(torch.view_as_real(st.state), [torch.view_as_real(x) for x in parts] if rank == 0 else None, dst=0)
             if rank == 0:
+                full = torch.cat(parts)
+                del parts
+                same = bool(torch.equal(P.sample(full, u), idx))
                 eng = StatevectorEngine("b200", device=dev, dtype=dt)
                 ref, _, _ = eng._evolve(Circuit(n, ops), "run")
                 zr = P.expect_z_bits(ref)[0].cpu().numpy()
                 err = float(np.abs(z - zr).max())
-                good = err < tol and abs(float(nrm[0]) - 1.0) < tol
+                amp_err = float((full - ref).abs().max())
+                good = err < tol and abs(float(nrm[0]) - 1.0) < tol and same and amp_err < tol
                 ok &= good
                 print(f"{name} n={n} world={world} {dt}: exchanges={plan.n_exchanges} segments={len(plan.segments)} max|dZ|={err:.2e} "
-                      f"norm-1={float(nrm[0]) - 1.0:.2e} {'OK' if good else 'FAIL'}", flush=True)
-                del ref
+                      f"norm-1={float(nrm[0]) - 1.0:.2e} restored-state max|d|={amp_err:.2e} sharded sampler == single-GPU sampler: {same} "
+                      f"(restore + 4096 shots {sample_ms:.1f} ms) {'OK' if good else 'FAIL'}", flush=True)
+                del ref, full
             del st
             torch.cuda.empty_cache()
             dist.barrier()

@@ -80,12 +80,43 @@ __global__ void __launch_bounds__(RT) expect_z_bits_kernel(const cplx<T> *__rest
 #pragma unroll
   for (int j = 0; j < MID; ++j) ones[j] = 0.0;
   const int nmid = sg.seg_bits > LT ? sg.seg_bits - LT : 0;
-  for (size_t it = 0; it * RT + threadIdx.x < len; ++it) {
-    const double p = prob_of(s[it * RT + threadIdx.x]);
-    tot += p;
+  constexpr int U = 3;  // 2^U loads in flight per thread; the low U bits of `it` are register indices
+  if (nmid >= U) {
+    double acc[1 << U];
 #pragma unroll
-    for (int j = 0; j < MID; ++j)
-      if (j < nmid && ((it >> j) & 1)) ones[j] += p;
+    for (int u = 0; u < (1 << U); ++u) acc[u] = 0.0;
+    const size_t iters = len / RT;
+    for (size_t it0 = 0; it0 < iters; it0 += (1 << U)) {
+      cplx<T> a[1 << U];
+#pragma unroll
+      for (int u = 0; u < (1 << U); ++u) a[u] = s[(it0 + u) * RT + threadIdx.x];
+      double blk = 0.0;
+#pragma unroll
+      for (int u = 0; u < (1 << U); ++u) {
+        const double p = prob_of(a[u]);
+        acc[u] += p;
+        blk += p;
+      }
+      const uint32_t hi = (uint32_t)(it0 >> U);  // uniform across the CTA: the adds below are branch-free selects
+#pragma unroll
+      for (int j = U; j < MID; ++j)
+        if (j < nmid) ones[j] += ((hi >> (j - U)) & 1u) ? blk : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < (1 << U); ++u) {
+      tot += acc[u];
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if ((u >> j) & 1) ones[j] += acc[u];
+    }
+  } else {
+    for (size_t it = 0; it * RT + threadIdx.x < len; ++it) {
+      const double p = prob_of(s[it * RT + threadIdx.x]);
+      tot += p;
+#pragma unroll
+      for (int j = 0; j < MID; ++j)
+        if (j < nmid && ((it >> j) & 1)) ones[j] += p;
+    }
   }
   // combine into per-bit contributions, MAX_ACC at most
   double v[MAX_ACC];
@@ -102,26 +133,85 @@ __global__ void __launch_bounds__(RT) expect_z_bits_kernel(const cplx<T> *__rest
   block_reduce<MAX_ACC>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MAX_ACC);
 }
 
+// Sum_i p_i (-1)^popc(idx_i & mask_t) for up to 32 masks per launch.  The parities of all masks are kept as ONE
+// 32-bit sign word: sw(idx) = XOR over the set bits b of idx of col[b], col[b] bit t = bit b of mask t.  A thread
+// visits idx = fixed | (it << LT); stepping it -> it+1 flips bits 0..ctz(it+1) of it, i.e. one XOR with a
+// prefix word.  Per amplitude and mask that leaves a predicated add (ones[t] += p where the sign bit is set) instead
+// of a 64-bit popc; result = total - 2 * ones[t].
 template <typename T>
-__global__ void __launch_bounds__(RT) expect_zmasks_kernel(const cplx<T> *__restrict__ state, Seg sg, uint64_t global_base,
-                                                           const uint64_t *__restrict__ masks, int n_masks, double *partial) {
+__global__ void __launch_bounds__(RT, 2) expect_zmasks_kernel(const cplx<T> *__restrict__ state, Seg sg, uint64_t global_base,
+                                                              const uint64_t *__restrict__ masks, int n_masks, double *partial) {
   __shared__ double sm[(RT / 32) * MASKS_PER_LAUNCH];
-  __shared__ uint64_t smask[MASKS_PER_LAUNCH];
-  if (threadIdx.x < MASKS_PER_LAUNCH) smask[threadIdx.x] = threadIdx.x < n_masks ? masks[threadIdx.x] : 0ull;
-  __syncthreads();
+  __shared__ uint32_t col[64];
+  __shared__ uint32_t pre[64];  // pre[k] = col[LT+U] ^ .. ^ col[LT+U+k]
+  constexpr int LT = 8;         // log2(RT)
+  constexpr int U = 2;          // 2^U loads in flight per thread
   const size_t off = (size_t)blockIdx.x << sg.seg_bits;
   const cplx<T> *s = state + ((size_t)blockIdx.y << sg.n) + off;
   const size_t len = (size_t)1 << sg.seg_bits;
+  const bool blocked = len >= ((size_t)RT << U);
+  const int first = LT + (blocked ? U : 0);
+  if (threadIdx.x < 64) {
+    uint32_t w = 0;
+    for (int t = 0; t < n_masks; ++t) w |= (uint32_t)((masks[t] >> threadIdx.x) & 1ull) << t;
+    col[threadIdx.x] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    uint32_t w = 0;
+    for (int j = 0; j <= (int)threadIdx.x && first + j < 64; ++j) w ^= col[first + j];
+    pre[threadIdx.x] = w;
+  }
+  __syncthreads();
+  const uint64_t fixed = global_base | (off + threadIdx.x);
+  uint32_t sw0 = 0;
+  for (int b = 0; b < 64; ++b)
+    if ((fixed >> b) & 1ull) sw0 ^= col[b];
+  double tot = 0.0;
+  double ones[MASKS_PER_LAUNCH];
+#pragma unroll
+  for (int t = 0; t < MASKS_PER_LAUNCH; ++t) ones[t] = 0.0;
+  if (blocked) {
+    uint32_t eu[1 << U];
+#pragma unroll
+    for (int u = 0; u < (1 << U); ++u) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if ((u >> j) & 1) w ^= col[LT + j];
+      eu[u] = w;
+    }
+    const size_t nblk = (len / RT) >> U;
+    uint32_t g = sw0;
+    for (size_t blk = 0; blk < nblk; ++blk) {
+      if (blk) g ^= pre[__ffsll((long long)blk) - 1];
+      cplx<T> a[1 << U];
+#pragma unroll
+      for (int u = 0; u < (1 << U); ++u) a[u] = s[((blk << U) + u) * RT + threadIdx.x];
+#pragma unroll
+      for (int u = 0; u < (1 << U); ++u) {
+        const double p = prob_of(a[u]);
+        const uint32_t sw = g ^ eu[u];
+        tot += p;
+#pragma unroll
+        for (int t = 0; t < MASKS_PER_LAUNCH; ++t)
+          if (sw & (1u << t)) ones[t] += p;
+      }
+    }
+  } else {
+    uint32_t g = sw0;
+    for (size_t it = 0; it * RT + threadIdx.x < len; ++it) {
+      if (it) g ^= pre[__ffsll((long long)it) - 1];
+      const double p = prob_of(s[it * RT + threadIdx.x]);
+      tot += p;
+#pragma unroll
+      for (int t = 0; t < MASKS_PER_LAUNCH; ++t)
+        if (g & (1u << t)) ones[t] += p;
+    }
+  }
   double v[MASKS_PER_LAUNCH];
 #pragma unroll
-  for (int t = 0; t < MASKS_PER_LAUNCH; ++t) v[t] = 0.0;
-  for (size_t i = threadIdx.x; i < len; i += RT) {
-    const double p = prob_of(s[i]);
-    const uint64_t idx = global_base | (off + i);
-#pragma unroll
-    for (int t = 0; t < MASKS_PER_LAUNCH; ++t)
-      if (t < n_masks) v[t] += (__popcll(idx & smask[t]) & 1) ? -p : p;
-  }
+  for (int t = 0; t < MASKS_PER_LAUNCH; ++t) v[t] = tot - 2.0 * ones[t];
   block_reduce<MASKS_PER_LAUNCH>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * MASKS_PER_LAUNCH);
 }
 
@@ -438,8 +528,13 @@ __global__ void __launch_bounds__(RT) chunk_prefix_kernel(const double *totals, 
   }
 }
 
+// A state array holds chunks [c_first, c_first + c_count) of the nc chunks the prefix covers (a shard of a state
+// distributed over ranks; the whole state when c_first = 0, c_count = nc).  Samples that fall into other chunks
+// are written as -1; `tail_index` >= 0 is written for u beyond the last chunk (the owner of the last chunk passes
+// the dimension, everyone else -1).
 template <typename T>
 __global__ void __launch_bounds__(128) sample_kernel(const cplx<T> *__restrict__ state, int n, int chunk_bits, long long nc,
+                                                     long long c_first, long long c_count, long long tail_index,
                                                      const double *__restrict__ prefix, const double *__restrict__ uniforms,
                                                      long long shots, long long *idx_out) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,10 +551,12 @@ __global__ void __launch_bounds__(128) sample_kernel(const cplx<T> *__restrict__
   }
   long long idx;
   if (lo >= nc) {
-    idx = (long long)1 << n;
+    idx = tail_index;
+  } else if (lo < c_first || lo >= c_first + c_count) {
+    idx = -1;
   } else {
     const size_t clen = (size_t)1 << chunk_bits;
-    const cplx<T> *sc = state + ((size_t)b << n) + ((size_t)lo << chunk_bits);
+    const cplx<T> *sc = state + ((size_t)b << n) + ((size_t)(lo - c_first) << chunk_bits);
     const double pre = p[lo];
     double run = 0.0;
     size_t cnt = 0;
@@ -755,22 +852,40 @@ int tqb_probabilities(const void *state, int n, int64_t batch, int dtype, double
   return 0;
 }
 
+static int launch_chunk_totals(const void *state, int n, int64_t batch, int dtype, double *totals, cudaStream_t st) {
+  const int chunk_bits = n < 12 ? n : 12;  // TQB_SCAN_BLOCK = 4096
+  const long long nct = (1ll << (n - chunk_bits)) * batch;
+  const long long groups = (nct + 31) / 32;
+  const long long blocks = (groups + CW - 1) / CW;
+  if (by_dtype(dtype, [&] { chunk_totals_kernel<double><<<(unsigned)blocks, CW * 32, 0, st>>>(CD(state), n, chunk_bits, nct, totals); },
+               [&] { chunk_totals_kernel<float><<<(unsigned)blocks, CW * 32, 0, st>>>(CF(state), n, chunk_bits, nct, totals); })) return -1;
+  TQB_CHECK_LAUNCH("chunk_totals_kernel");
+  return 0;
+}
+
 int tqb_cdf_chunks(const void *state, int n, int64_t batch, int dtype, double *chunk_prefix_dev, void *stream) {
   TQB_REQUIRE(state && chunk_prefix_dev && n >= 0 && n < 48 && batch >= 1, "tqb_cdf_chunks: bad arguments");
   Workspace *ws = workspace();
   if (!ws) return -1;
-  const int chunk_bits = n < 12 ? n : 12;  // TQB_SCAN_BLOCK = 4096
+  const int chunk_bits = n < 12 ? n : 12;
   const long long nc = 1ll << (n - chunk_bits);
-  const long long nct = nc * batch;
-  TQB_REQUIRE((size_t)nct * sizeof(double) <= ws->bytes, "tqb_cdf_chunks: workspace too small for the chunk totals");
+  TQB_REQUIRE((size_t)(nc * batch) * sizeof(double) <= ws->bytes, "tqb_cdf_chunks: workspace too small for the chunk totals");
   double *totals = (double *)ws->ptr;
-  const long long groups = (nct + 31) / 32;
-  const long long blocks = (groups + CW - 1) / CW;
   cudaStream_t st = as_stream(stream);
-  if (by_dtype(dtype, [&] { chunk_totals_kernel<double><<<(unsigned)blocks, CW * 32, 0, st>>>(CD(state), n, chunk_bits, nct, totals); },
-               [&] { chunk_totals_kernel<float><<<(unsigned)blocks, CW * 32, 0, st>>>(CF(state), n, chunk_bits, nct, totals); })) return -1;
-  TQB_CHECK_LAUNCH("chunk_totals_kernel");
+  if (launch_chunk_totals(state, n, batch, dtype, totals, st)) return -1;
   chunk_prefix_kernel<<<(unsigned)batch, RT, 0, st>>>(totals, nc, chunk_prefix_dev);
+  TQB_CHECK_LAUNCH("chunk_prefix_kernel");
+  return 0;
+}
+
+int tqb_chunk_totals(const void *state, int n, int64_t batch, int dtype, double *totals_dev, void *stream) {
+  TQB_REQUIRE(state && totals_dev && n >= 0 && n < 48 && batch >= 1, "tqb_chunk_totals: bad arguments");
+  return launch_chunk_totals(state, n, batch, dtype, totals_dev, as_stream(stream));
+}
+
+int tqb_chunk_prefix(const double *totals_dev, int64_t n_chunks, int64_t batch, double *chunk_prefix_dev, void *stream) {
+  TQB_REQUIRE(totals_dev && chunk_prefix_dev && n_chunks >= 1 && batch >= 1 && batch <= 65535, "tqb_chunk_prefix: bad arguments");
+  chunk_prefix_kernel<<<(unsigned)batch, RT, 0, as_stream(stream)>>>(totals_dev, (long long)n_chunks, chunk_prefix_dev);
   TQB_CHECK_LAUNCH("chunk_prefix_kernel");
   return 0;
 }
@@ -784,8 +899,27 @@ int tqb_sample(const void *state, int n, int64_t batch, int dtype, const double 
   dim3 grid((unsigned)((shots + 127) / 128), (unsigned)batch);
   cudaStream_t st = as_stream(stream);
   if (by_dtype(dtype,
-               [&] { sample_kernel<double><<<grid, 128, 0, st>>>(CD(state), n, chunk_bits, nc, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
-               [&] { sample_kernel<float><<<grid, 128, 0, st>>>(CF(state), n, chunk_bits, nc, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
+               [&] { sample_kernel<double><<<grid, 128, 0, st>>>(CD(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
+               [&] { sample_kernel<float><<<grid, 128, 0, st>>>(CF(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
+    return -1;
+  TQB_CHECK_LAUNCH("sample_kernel");
+  return 0;
+}
+
+int tqb_sample_shard(const void *state, int n_local, int dtype, const double *chunk_prefix_dev, int64_t n_chunks_total,
+                     int64_t chunk_first, int64_t tail_index, const double *uniforms_dev, int64_t shots, int64_t *idx_dev,
+                     void *stream) {
+  TQB_REQUIRE(state && chunk_prefix_dev && uniforms_dev && idx_dev && n_local >= 12 && n_local < 48 && shots >= 1 &&
+                  n_chunks_total >= 1 && chunk_first >= 0,
+              "tqb_sample_shard: bad arguments (shards hold whole 4096-amplitude chunks: n_local >= 12)");
+  const int chunk_bits = 12;
+  const long long c_count = 1ll << (n_local - chunk_bits);
+  TQB_REQUIRE(chunk_first + c_count <= n_chunks_total, "tqb_sample_shard: shard chunks exceed the prefix");
+  dim3 grid((unsigned)((shots + 127) / 128), 1);
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype,
+               [&] { sample_kernel<double><<<grid, 128, 0, st>>>(CD(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
+               [&] { sample_kernel<float><<<grid, 128, 0, st>>>(CF(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
     return -1;
   TQB_CHECK_LAUNCH("sample_kernel");
   return 0;

@@ -152,6 +152,63 @@ def plan_sharded(gates: Sequence[LGate], n: int, g: int) -> ShardPlan:
     return ShardPlan(n, g, segments, phys, n_ex)
 
 
+def plan_restore(phys_in: Sequence[int], n: int, g: int) -> ShardPlan:
+    """Segments that bring an arbitrary logical->physical map back to the identity (needed before sampling: the
+    blocked CDF of the reference runs over LOGICAL index order = rank-major order of an identity layout).
+    At most two exchanges: one that brings every currently-global bit home when a target bit is global in
+    the wrong place, one that sends the g highest logical bits to their rank positions; then in-tile bit swaps
+    sort the local bits."""
+    n_local = n - g
+    phys = list(phys_in)
+    inv = {p: l for l, p in enumerate(phys)}
+    segments: List[Segment] = []
+    n_ex = 0
+
+    def swap_phys(seg: Segment, pa: int, pb: int) -> None:
+        if pa == pb:
+            return
+        seg.gates.append(LGate(SWAP, (pa, pb), X_MAT.reshape(4).copy(), pat_a=0b01, pat_b=0b10, name="bitswap"))
+        la, lb = inv[pa], inv[pb]
+        phys[la], phys[lb] = pb, pa
+        inv[pa], inv[pb] = lb, la
+
+    def do_exchange(seg: Segment) -> None:
+        seg.exchange_after = True
+        for i in range(g):
+            a, b = n_local - g + i, n_local + i
+            la, lb = inv[a], inv[b]
+            phys[la], phys[lb] = b, a
+            inv[a], inv[b] = lb, la
+
+    targets = [n_local + i for i in range(g)]
+    if g and any(phys[t] != t for t in targets):
+        if any(phys[t] >= n_local for t in targets):
+            # a target sits on a rank bit: the all-to-all swaps ALL g rank bits, so first bring them all home,
+            # sending g local non-target bits away
+            seg = Segment([])
+            fillers = [l for l in range(n) if phys[l] < n_local and l not in targets][:g]
+            if len(fillers) < g:
+                raise RuntimeError("not enough local qubits to restore the layout")
+            for i, f in enumerate(fillers):
+                swap_phys(seg, phys[f], n_local - g + i)
+            do_exchange(seg)
+            segments.append(seg)
+            n_ex += 1
+        seg = Segment([])
+        for i, t in enumerate(targets):
+            swap_phys(seg, phys[t], n_local - g + i)
+        do_exchange(seg)
+        segments.append(seg)
+        n_ex += 1
+    seg = Segment([])
+    for l in range(n_local):
+        swap_phys(seg, phys[l], l)
+    if seg.gates:
+        segments.append(seg)
+    assert phys == list(range(n)), phys
+    return ShardPlan(n, g, segments, phys, n_ex)
+
+
 # ------------------------------------------------------------------------------------------
 # the exchange
 # ------------------------------------------------------------------------------------------
@@ -210,16 +267,58 @@ class ShardedState:
         self.backend.init_local(self.state, self.n_local, self.global_base)
         self.phys = list(range(self.n))
 
-    def run(self, plan: ShardPlan) -> None:
+    def run(self, plan: ShardPlan, cache: bool = True) -> None:
+        """``cache``: keep the compiled per-segment programs (slot = segment index) for the next run of the SAME plan."""
         for si, seg in enumerate(plan.segments):
             if seg.gates:
-                self.backend.run_local(self.state, seg.gates, self.n_local, self.global_base, si)
+                self.backend.run_local(self.state, seg.gates, self.n_local, self.global_base, si if cache else None)
             if seg.exchange_after:
                 t0 = time.perf_counter()
                 exchange(self.scratch, self.state, self.group)
                 self.state, self.scratch = self.scratch, self.state
                 self.exchange_s += time.perf_counter() - t0
         self.phys = list(plan.final_phys)
+
+    # -- sampling -------------------------------------------------------------------------
+    def restore_layout(self) -> int:
+        """Bring the shard layout back to the identity map (logical bit l = physical bit l); returns the number
+        of exchanges it took (0-2)."""
+        if self.phys == list(range(self.n)):
+            return 0
+        plan = plan_restore(self.phys, self.n, self.g)
+        self.run(plan, cache=False)
+        return plan.n_exchanges
+
+    def sample(self, uniforms: torch.Tensor) -> torch.Tensor:
+        """Basis-state indices (int64 [shots], logical index, identical on every rank) drawn with the given host
+        uniforms: the blocked-CDF contract of the single-GPU sampler (oracle/sv_oracle.py sample_indices; reference
+        engine.py:377-418), bit for bit.  Every rank sums its own chunks, the chunk totals are all-gathered in rank
+        order, every rank runs the same sequential prefix over all chunks and resolves the samples that fall into
+        its shard; a max-reduction assembles the result."""
+        self.restore_layout()
+        be = self.backend
+        u = uniforms.to(device=self.device, dtype=torch.float64).contiguous().reshape(-1)
+        totals = be.chunk_totals(self.state, self.n_local)
+        ncl = int(totals.numel())
+        if self.world > 1:
+            parts = [torch.empty_like(totals) for _ in range(self.world)]
+            dist.all_gather(parts, totals, group=self.group)
+            totals_all = torch.cat(parts)
+        else:
+            totals_all = totals
+        prefix = be.chunk_prefix(totals_all)
+        last = self.rank == self.world - 1
+        idx = be.sample_shard(self.state, self.n_local, prefix, self.rank * ncl, (1 << self.n) if last else -1, u)
+        if self.world > 1:
+            dist.all_reduce(idx, op=dist.ReduceOp.MAX, group=self.group)
+        return idx
+
+    def counts(self, uniforms: torch.Tensor) -> dict:
+        """{bitstring: count} over all n qubits (big-endian, engine.py:418-463) from ``sample``."""
+        idx = self.sample(uniforms).cpu().numpy()
+        idx = np.minimum(idx, (1 << self.n) - 1)
+        vals, cnt = np.unique(idx, return_counts=True)
+        return {format(int(v), f"0{self.n}b"): int(c) for v, c in zip(vals, cnt)}
 
     # -- reductions -----------------------------------------------------------------------
     def expect_z_all(self) -> torch.Tensor:
@@ -249,6 +348,10 @@ class _CudaLocal:
     def run_local(self, state: torch.Tensor, gates: List[LGate], n_local: int, global_base: int, cache_slot: int) -> None:
         from . import program as P
         from .planner import compile_program, default_tile
+        if cache_slot is None:
+            prog = compile_program(gates, n_local, default_tile(n_local, state.element_size(), 1), itemsize=state.element_size())
+            P.DeviceProgram(prog, state.device, state.dtype).run(state, global_base=global_base)
+            return
         progs = self.owner.programs
         while len(progs) <= cache_slot:
             progs.append(None)
@@ -260,6 +363,36 @@ class _CudaLocal:
     def reduce_local(self, state: torch.Tensor, n_local: int) -> Tuple[torch.Tensor, torch.Tensor]:
         from . import program as P
         return P.expect_z_bits(state)[0], P.norm2(state)[0]
+
+    def chunk_totals(self, state: torch.Tensor, n_local: int) -> torch.Tensor:
+        from . import _lib
+        from . import program as P
+        if n_local < 12:
+            raise _lib.TqbError("sharded sampling needs shards of at least one 4096-amplitude chunk (n_local >= 12)")
+        ptr, n_, _, dt, stream = P._prep(state)
+        out = torch.empty(1 << (n_local - 12), dtype=torch.float64, device=state.device)
+        with torch.cuda.device(state.device):
+            _lib.check(_lib.load().tqb_chunk_totals(ptr, n_, 1, dt, out.data_ptr(), stream))
+        return out
+
+    def chunk_prefix(self, totals_all: torch.Tensor) -> torch.Tensor:
+        from . import _lib
+        nc = int(totals_all.numel())
+        out = torch.empty(nc + 1, dtype=torch.float64, device=totals_all.device)
+        with torch.cuda.device(totals_all.device):
+            _lib.check(_lib.load().tqb_chunk_prefix(totals_all.data_ptr(), nc, 1, out.data_ptr(), _lib.current_stream_ptr(totals_all.device)))
+        return out
+
+    def sample_shard(self, state: torch.Tensor, n_local: int, prefix: torch.Tensor, chunk_first: int, tail_index: int,
+                     uniforms: torch.Tensor) -> torch.Tensor:
+        from . import _lib
+        from . import program as P
+        ptr, n_, _, dt, stream = P._prep(state)
+        idx = torch.empty(uniforms.numel(), dtype=torch.int64, device=state.device)
+        with torch.cuda.device(state.device):
+            _lib.check(_lib.load().tqb_sample_shard(ptr, n_, dt, prefix.data_ptr(), int(prefix.numel()) - 1, int(chunk_first),
+                                                    int(tail_index), uniforms.data_ptr(), int(uniforms.numel()), idx.data_ptr(), stream))
+        return idx
 
 
 def lower_and_fuse(ops: Sequence[tuple], n: int, mode: str = "run") -> List[LGate]:
