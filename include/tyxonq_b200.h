@@ -206,6 +206,18 @@ int tqb_cdf_chunks(const void *state, int n, int64_t batch, int dtype, double *c
 int tqb_sample(const void *state, int n, int64_t batch, int dtype, const double *chunk_prefix_dev,
                const double *uniforms_dev, int64_t shots, int64_t *idx_dev, void *stream);
 
+/* replaces term_expectation_from_counts / expval_pauli_sum (postprocessing/counts_expval.py:7-20,
+ * 87-112) for the shots > 0 VQE path (applications/chem/runtimes/hea_device_runtime.py:120-262):
+ * idx_dev holds `batch` rows of `shots` sampled indices (tqb_sample); row b belongs to measurement
+ * group b % n_groups, whose terms are term_ptr[g] .. term_ptr[g+1].  zmask = index bits of the
+ * term's qubits (qubit q -> bit n-1-q).  <Z_S> = (shots - 2 * #odd-parity samples) / shots, the
+ * exact value the reference gets from the counts dict; energy_dev[b] = sum_t coef_t <Z_S_t> in
+ * term order; expvals_dev (optional, NULL to skip) [b * expvals_stride + local term index].      */
+int tqb_expval_from_samples(const int64_t *idx_dev, int64_t batch, int64_t shots, int n_groups,
+                            const int32_t *term_ptr_dev, const uint64_t *term_z_dev,
+                            const double *term_coef_dev, double *energy_dev, double *expvals_dev,
+                            int64_t expvals_stride, void *stream);
+
 /* ---- sharded states ------------------------------------------------------------------ */
 /* The sampler of a state sharded over ranks (rank = highest index bits; engine.py:377-418 at sizes
  * one GPU cannot hold).  Same blocked CDF as above, bit for bit: every rank computes the totals

@@ -137,3 +137,31 @@ def test_ucc_h2o_shape_energy_grad(cuda_device):
     assert abs(e3 - e3_ref) < 1e-8 and np.abs(g3 - g3_ref).max() < 1e-8
     e4, g4 = sv.energy_and_grad(params * -0.3, graph=False)
     assert abs(e4 - e3) < 1e-12 and np.abs(g4 - g3).max() < 1e-10
+
+
+def test_b200_backend_value_and_grad(cuda_device):
+    """Seam B3: tq.set_backend(B200Backend()) style use -- arrays live on the device, value_and_grad runs the
+    adjoint sweep (reference pytorch_backend.py:446-564 returns (float, ndarray))."""
+    import torch
+    from tyxonq_b200 import B200Backend, StatevectorEngine
+    K = B200Backend(cuda_device)
+    w = K.array(np.arange(1, 9, dtype=np.float64))
+    assert w.is_cuda and K.to_numpy(K.kron(K.eye(2), K.ones((2, 2)))).shape == (4, 4)
+    eng = StatevectorEngine(K, device=cuda_device)
+    assert eng.backend_name == "b200"
+
+    def loss(theta):
+        psi = eng.state(_torch_circuit(3, theta))
+        assert psi.is_cuda
+        return K.sum(w * K.abs(psi) ** 2) + K.real(psi[1] * K.conj(psi[6]))
+
+    theta0 = np.array([0.3, -0.7, 1.1, 0.5, -0.2, 0.9])
+    val, grad = K.value_and_grad(loss)(theta0)
+    assert isinstance(val, float) and isinstance(grad, np.ndarray) and grad.shape == (6,)
+    assert abs(val - _loss_np(theta0)) < 1e-10
+    assert np.abs(grad - O.central_fd_gradient(_loss_np, theta0, 1e-6)).max() < 1e-7
+    # sampling helper: numpy Generator.choice with explicit uniforms
+    p = np.abs(O.evolve_ops(3, [("h", 0), ("rx", 1, 0.4), ("cx", 0, 2)])[0]) ** 2
+    got = K.to_numpy(K.choice(np.random.default_rng(5), 8, size=64, p=K.array(p)))
+    want = np.random.default_rng(5).choice(8, size=64, p=p / p.sum())
+    assert np.array_equal(got, want)

@@ -42,3 +42,55 @@ def test_install_rebinds_and_restores():
         assert driver._select_engine("statevector") is ref_cls
     finally:
         sys.path.remove(REF)
+
+
+def test_backend_declares_the_whole_array_protocol():
+    """numerics/api.py:19-121: every attribute and method of ArrayBackend exists on B200Backend (class level: no GPU
+    needed); when the reference is mounted the list is checked against the live Protocol as well."""
+    from tyxonq_b200.backend import PROTOCOL_ATTRS, PROTOCOL_METHODS, B200Backend
+    for a in PROTOCOL_ATTRS:
+        assert hasattr(B200Backend, a), a
+    for m in PROTOCOL_METHODS + ["value_and_grad", "vmap", "jit", "set_dtype", "dot", "copy", "allclose", "isclose"]:
+        assert callable(getattr(B200Backend, m)), m
+    assert B200Backend.name == "b200"
+    if os.path.isdir(REF):
+        sys.path.insert(0, REF)
+        try:
+            from tyxonq.numerics.api import ArrayBackend
+            declared = [k for k, v in vars(ArrayBackend).items() if callable(v) and not k.startswith("_")]
+            assert declared and set(declared) <= set(PROTOCOL_METHODS), set(declared) - set(PROTOCOL_METHODS)
+        finally:
+            sys.path.remove(REF)
+
+
+def test_backend_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tyxonq_b200 import B200Backend, TqbError
+    with pytest.raises(TqbError):
+        B200Backend()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not mounted")
+def test_engine_follows_the_global_backend_of_a_live_install():
+    """StatevectorEngine(backend_name=None) resolves through tq's process-global backend (api.py:230-234)."""
+    sys.path.insert(0, REF)
+    sys.dont_write_bytecode = True
+    try:
+        import tyxonq as tq
+        from tyxonq_b200.engine import StatevectorEngine
+
+        class _Fake:
+            name = "b200"
+        try:
+            tq.set_backend("pytorch")
+            assert StatevectorEngine().backend_name == "pytorch"
+            tq.set_backend(_Fake())
+            assert StatevectorEngine().backend_name == "b200"
+            assert StatevectorEngine(backend_name="numpy").backend_name == "numpy"
+        finally:
+            tq.set_backend("numpy")
+        assert StatevectorEngine().backend_name == "numpy"
+    finally:
+        sys.path.remove(REF)

@@ -9,6 +9,7 @@ Public surface (mirrors the reference's names):
   StatevectorEngine           devices/simulators/statevector/engine.py
   kernels.*                   libs/quantum_library/kernels/statevector.py
   PauliSum                    libs/quantum_library/kernels/pauli.py + dynamics.expectation
+  B200Backend                 numerics/api.py ArrayBackend, for ``tq.set_backend(B200Backend())``
   install()                   route ``device="statevector"`` of a live TyxonQ install to this engine
 """
 from __future__ import annotations
@@ -20,6 +21,7 @@ __version__ = "0.1.0"
 _LAZY = {
     "StatevectorEngine": ("engine", "StatevectorEngine"),
     "PauliSum": ("pauli", "PauliSum"),
+    "B200Backend": ("backend", "B200Backend"),
     "install": ("install", "install"),
     "uninstall": ("install", "uninstall"),
 }
@@ -30,7 +32,7 @@ def __getattr__(name: str):
         import importlib
         mod, attr = _LAZY[name]
         return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
-    if name in ("kernels", "engine", "pauli", "program", "planner", "gates", "autograd", "ucc", "vqe", "sharded", "circuits"):
+    if name in ("kernels", "engine", "pauli", "program", "planner", "gates", "autograd", "ucc", "vqe", "sharded", "circuits", "backend", "batched"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -569,6 +569,41 @@ __global__ void __launch_bounds__(128) sample_kernel(const cplx<T> *__restrict__
   idx_out[(size_t)b * shots + s] = idx;
 }
 
+// ---- Pauli-Z products from sampled indices (postprocessing/counts_expval.py:7-20, 87-112) -------------------
+// Member b (one basis-rotated copy of a state, measured `shots` times) evaluates the terms of group b % n_groups:
+// <Z_S> = (shots - 2 * #{s : popc(idx_s & zmask) odd}) / shots -- integer counting, so the value is exactly what
+// the reference computes from the counts dict; energy[b] = sum_t coef_t * <Z_S_t> in term order.
+__global__ void __launch_bounds__(RT) expval_samples_kernel(const long long *__restrict__ idx, long long shots, int n_groups,
+                                                            const int *__restrict__ term_ptr, const uint64_t *__restrict__ term_z,
+                                                            const double *__restrict__ term_coef, double *energy,
+                                                            double *expvals, long long expvals_stride) {
+  __shared__ long long sm[RT / 32];
+  __shared__ double acc;
+  const long long b = blockIdx.x;
+  const int g = (int)(b % n_groups);
+  const long long *ib = idx + b * shots;
+  if (threadIdx.x == 0) acc = 0.0;
+  __syncthreads();
+  for (int t = term_ptr[g]; t < term_ptr[g + 1]; ++t) {
+    const uint64_t z = term_z[t];
+    long long odd = 0;
+    for (long long s = threadIdx.x; s < shots; s += RT) odd += __popcll((uint64_t)ib[s] & z) & 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) odd += __shfl_down_sync(0xffffffffu, odd, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = odd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long tot = 0;
+      for (int w = 0; w < RT / 32; ++w) tot += sm[w];
+      const double ev = __ddiv_rn((double)(shots - 2 * tot), (double)shots);
+      if (expvals) expvals[b * expvals_stride + (t - term_ptr[g])] = ev;
+      acc = __dadd_rn(acc, __dmul_rn(term_coef[t], ev));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) energy[b] = acc;
+}
+
 // ---- host helpers ----------------------------------------------------------------------------
 static int pick_seg(const Workspace &ws, int n, int64_t batch, int nv, int max_seg_bits, Seg *sg, int *nbx) {
   // power-of-two number of segments per batch member, ~8 CTAs per SM overall
@@ -903,6 +938,18 @@ int tqb_sample(const void *state, int n, int64_t batch, int dtype, const double 
                [&] { sample_kernel<float><<<grid, 128, 0, st>>>(CF(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
     return -1;
   TQB_CHECK_LAUNCH("sample_kernel");
+  return 0;
+}
+
+int tqb_expval_from_samples(const int64_t *idx_dev, int64_t batch, int64_t shots, int n_groups, const int32_t *term_ptr_dev,
+                            const uint64_t *term_z_dev, const double *term_coef_dev, double *energy_dev, double *expvals_dev,
+                            int64_t expvals_stride, void *stream) {
+  TQB_REQUIRE(idx_dev && term_ptr_dev && term_z_dev && term_coef_dev && energy_dev && batch >= 1 && shots >= 1 && n_groups >= 1,
+              "tqb_expval_from_samples: bad arguments");
+  expval_samples_kernel<<<(unsigned)batch, RT, 0, as_stream(stream)>>>((const long long *)idx_dev, (long long)shots, n_groups, term_ptr_dev,
+                                                                        term_z_dev, term_coef_dev, energy_dev, expvals_dev,
+                                                                        (long long)expvals_stride);
+  TQB_CHECK_LAUNCH("expval_samples_kernel");
   return 0;
 }
 

@@ -42,6 +42,18 @@ class StatevectorEngine:
         """backend_name decides what ``state()`` hands back, like the reference's numerics backend:
         None/"numpy" -> numpy array, "pytorch" -> CPU torch tensor (autograd kept), "b200"/"cuda"
         -> the device tensor itself (no copy; use this for n >= 28)."""
+        if backend_name is None:
+            # the reference resolves None through its process-global backend (numerics/api.py:230-234); honour it when
+            # a TyxonQ install is live in this process (tq.set_backend("pytorch") / tq.set_backend(B200Backend()))
+            import sys
+            api = sys.modules.get("tyxonq.numerics.api")
+            if api is not None:
+                try:
+                    backend_name = str(getattr(api.get_backend(None), "name", "numpy"))
+                except Exception:  # noqa: BLE001 -- a half-initialised reference package must not break the engine
+                    backend_name = None
+        elif not isinstance(backend_name, str):
+            backend_name = str(getattr(backend_name, "name", backend_name))
         self.backend_name = backend_name or "numpy"
         if self.backend_name not in ("numpy", "pytorch", "torch", "b200", "cuda"):
             raise ValueError(f"unknown backend {backend_name!r}")

@@ -7,6 +7,7 @@
     ``Circuit.state``, core/ir/circuit.py:492-494)
   * the kernel functions of ``libs.quantum_library.kernels.statevector`` (looked up lazily by
     ``Circuit._expectation_statevector`` and the chem numerics)
+  * optionally (seam B3) the process-global numerics backend -> ``B200Backend``
 TyxonQ itself is not a dependency of this package; ``install()`` raises ImportError without it.
 """
 from __future__ import annotations
@@ -16,7 +17,10 @@ from typing import Any, Dict
 _saved: Dict[str, Any] = {}
 
 
-def install() -> None:
+def install(set_backend: bool = False) -> None:
+    """``set_backend=True`` additionally makes ``B200Backend`` the process-global numerics backend (seam B3,
+    numerics/__init__.py:20-36), so that ``Circuit.state()`` returns device tensors and ``K.value_and_grad`` runs the
+    adjoint sweep."""
     import importlib
     drv = importlib.import_module("tyxonq.devices.simulators.driver")
     eng_mod = importlib.import_module("tyxonq.devices.simulators.statevector.engine")
@@ -42,6 +46,11 @@ def install() -> None:
     eng_mod.StatevectorEngine = StatevectorEngine
     for k in K.__all__:
         setattr(ker_mod, k, getattr(K, k))
+    if set_backend:
+        from .backend import B200Backend
+        num = importlib.import_module("tyxonq.numerics")
+        num.set_backend(B200Backend())
+        _saved["backend"] = True
 
 
 def uninstall() -> None:
@@ -55,4 +64,6 @@ def uninstall() -> None:
     eng_mod.StatevectorEngine = _saved["engine"]
     for k, v in _saved["kernels"].items():
         setattr(ker_mod, k, v)
+    if _saved.get("backend"):
+        importlib.import_module("tyxonq.numerics").set_backend("numpy")
     _saved.clear()
