@@ -33,6 +33,7 @@ extern "C" {
 
 #define TQB_C64 0
 #define TQB_C128 1
+#define TQB_F64 2 /* tqb_cdf_chunks / tqb_chunk_totals / tqb_sample only: the array holds float64 PROBABILITIES */
 
 #define TQB_GATE_DENSE 0 /* dense 2^k x 2^k matrix, k <= 4, row-major, row = output index      */
 #define TQB_GATE_DIAG 1  /* diagonal: table of 2^k entries indexed by k GLOBAL index bits       */
@@ -182,6 +183,13 @@ typedef struct tqb_pair_step {
 } tqb_pair_step; /* 64 bytes */
 int tqb_pair_sweep(void *ket, void *bra, int n, int dtype, const tqb_pair_step *steps_dev, int n_steps,
                    int mode, double *out_dev, unsigned long long *sync_dev, void *stream);
+
+/* Reduced density matrix of index bit `bit`, per batch member: out_dev[4b..4b+4) = rho00, rho11,
+ * Re rho01, Im rho01 with rho01 = sum psi_0 conj(psi_1).  Gives the Born probabilities
+ * p_i = tr(K_i^+ K_i rho) of a 1-qubit Kraus channel in ONE read of the state (replaces the m
+ * trial applications of apply_kraus_statevector, libs/quantum_library/kernels/statevector.py:176-186). */
+int tqb_reduced_1q(const void *state, int n, int64_t batch, int dtype, int bit, double *out_dev,
+                   void *stream);
 
 /* ---- measurement --------------------------------------------------------------------- */
 /* replaces StatevectorEngine._project_z (engine.py:1075-1087): zero the half with

@@ -16,7 +16,7 @@ import numpy as np
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libtyxonq_b200.so"
 
-TQB_C64, TQB_C128 = 0, 1
+TQB_C64, TQB_C128, TQB_F64 = 0, 1, 2
 GATE_DENSE, GATE_DIAG, GATE_PAIR, GATE_SWAP = 0, 1, 2, 3
 GATE_MUX, GATE_CHAIN = 4, 5
 MAX_GATE_BITS = 8
@@ -74,6 +74,7 @@ SIGNATURES = {
     "tqb_probabilities": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_cdf_chunks": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_sample": (_i, [_vp, _i, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
+    "tqb_reduced_1q": (_i, [_vp, _i, _i64, _i, _i, _vp, _vp]),
     "tqb_expval_from_samples": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "tqb_chunk_totals": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_chunk_prefix": (_i, [_vp, _i64, _i64, _vp, _vp]),

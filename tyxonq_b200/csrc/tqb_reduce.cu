@@ -54,6 +54,9 @@ __device__ __forceinline__ double prob_of(const cplx<T> a) {
   return __dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im));
 }
 
+// a float64 array of probabilities can stand in for a state in the sampler (TQB_F64: noise-mixed distributions)
+__device__ __forceinline__ double prob_of(const double p) { return p; }
+
 // partial[(y*nbx + x)*nv + j]
 template <typename T>
 __global__ void __launch_bounds__(RT) norm2_kernel(const cplx<T> *__restrict__ state, Seg sg, double *partial) {
@@ -307,6 +310,29 @@ __global__ void __launch_bounds__(RT) inner_kernel(const cplx<T> *__restrict__ a
   block_reduce<2>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2);
 }
 
+// Reduced density matrix of one index bit per batch member: rho00 = sum |psi_0|^2, rho11 = sum |psi_1|^2,
+// rho01 = sum psi_0 conj(psi_1), over all pairs (i, i | 1 << bit).  The segment covers PAIR indices (n - 1 bits).
+template <typename T>
+__global__ void __launch_bounds__(RT) reduced_1q_kernel(const cplx<T> *__restrict__ state, int n, int bit, Seg sg, double *partial) {
+  __shared__ double sm[(RT / 32) * 4];
+  const cplx<T> *s = state + ((size_t)blockIdx.y << n);
+  const size_t p0 = (size_t)blockIdx.x << sg.seg_bits;
+  const size_t len = (size_t)1 << sg.seg_bits;
+  const size_t low = ((size_t)1 << bit) - 1;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (size_t i = threadIdx.x; i < len; i += RT) {
+    const size_t p = p0 + i;
+    const size_t i0 = ((p & ~low) << 1) | (p & low);
+    const cplx<T> a = s[i0], b = s[i0 | ((size_t)1 << bit)];
+    const double ar = a.x, ai = a.y, br = b.x, bi = b.y;
+    v[0] += ar * ar + ai * ai;
+    v[1] += br * br + bi * bi;
+    v[2] += ar * br + ai * bi;
+    v[3] += ai * br - ar * bi;
+  }
+  block_reduce<4>(v, sm, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4);
+}
+
 // ---- adjoint-gradient reductions ------------------------------------------------------------
 struct PairGen {
   int n, k;
@@ -481,8 +507,8 @@ __global__ void __launch_bounds__(RT) probs_kernel(const cplx<T> *__restrict__ s
 // one chunk per instruction) and transposed through shared memory so that lane l adds the
 // elements of chunk l in index order.
 constexpr int CW = 4;  // warps per CTA
-template <typename T>
-__global__ void __launch_bounds__(CW * 32) chunk_totals_kernel(const cplx<T> *__restrict__ state, int n, int chunk_bits,
+template <typename E>
+__global__ void __launch_bounds__(CW * 32) chunk_totals_kernel(const E *__restrict__ state, int n, int chunk_bits,
                                                                long long n_chunks_total, double *totals) {
   __shared__ double buf[CW][32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -532,8 +558,8 @@ __global__ void __launch_bounds__(RT) chunk_prefix_kernel(const double *totals, 
 // distributed over ranks; the whole state when c_first = 0, c_count = nc).  Samples that fall into other chunks
 // are written as -1; `tail_index` >= 0 is written for u beyond the last chunk (the owner of the last chunk passes
 // the dimension, everyone else -1).
-template <typename T>
-__global__ void __launch_bounds__(128) sample_kernel(const cplx<T> *__restrict__ state, int n, int chunk_bits, long long nc,
+template <typename E>
+__global__ void __launch_bounds__(128) sample_kernel(const E *__restrict__ state, int n, int chunk_bits, long long nc,
                                                      long long c_first, long long c_count, long long tail_index,
                                                      const double *__restrict__ prefix, const double *__restrict__ uniforms,
                                                      long long shots, long long *idx_out) {
@@ -556,7 +582,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const cplx<T> *__restrict__
     idx = -1;
   } else {
     const size_t clen = (size_t)1 << chunk_bits;
-    const cplx<T> *sc = state + ((size_t)b << n) + ((size_t)(lo - c_first) << chunk_bits);
+    const E *sc = state + ((size_t)b << n) + ((size_t)(lo - c_first) << chunk_bits);
     const double pre = p[lo];
     double run = 0.0;
     size_t cnt = 0;
@@ -758,6 +784,23 @@ int tqb_inner(const void *a, const void *b, int n, int64_t batch, int dtype, dou
   return 0;
 }
 
+int tqb_reduced_1q(const void *state, int n, int64_t batch, int dtype, int bit, double *out_dev, void *stream) {
+  TQB_REQUIRE(state && out_dev && n >= 1 && n < 48 && batch >= 1 && bit >= 0 && bit < n, "tqb_reduced_1q: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  Seg sg; int nbx;
+  if (pick_seg(*ws, n - 1, batch, 4, 40, &sg, &nbx)) return -1;
+  double *partial = (double *)ws->ptr;
+  dim3 grid(nbx, (unsigned)batch);
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { reduced_1q_kernel<double><<<grid, RT, 0, st>>>(CD(state), n, bit, sg, partial); },
+               [&] { reduced_1q_kernel<float><<<grid, RT, 0, st>>>(CF(state), n, bit, sg, partial); })) return -1;
+  TQB_CHECK_LAUNCH("reduced_1q_kernel");
+  finish_kernel<<<(unsigned)batch, 32, 0, st>>>(partial, nbx, 4, 4, out_dev, 4);
+  TQB_CHECK_LAUNCH("finish_kernel");
+  return 0;
+}
+
 int tqb_grad_pair(const void *bra, const void *ket, int n, int dtype, const tqb_gate *gate_host, double scale,
                   double *out_dev, int slot, void *stream) {
   TQB_REQUIRE(bra && ket && gate_host && out_dev && n >= 1 && n < 48 && slot >= 0, "tqb_grad_pair: bad arguments");
@@ -892,8 +935,11 @@ static int launch_chunk_totals(const void *state, int n, int64_t batch, int dtyp
   const long long nct = (1ll << (n - chunk_bits)) * batch;
   const long long groups = (nct + 31) / 32;
   const long long blocks = (groups + CW - 1) / CW;
-  if (by_dtype(dtype, [&] { chunk_totals_kernel<double><<<(unsigned)blocks, CW * 32, 0, st>>>(CD(state), n, chunk_bits, nct, totals); },
-               [&] { chunk_totals_kernel<float><<<(unsigned)blocks, CW * 32, 0, st>>>(CF(state), n, chunk_bits, nct, totals); })) return -1;
+  if (dtype == TQB_F64) {
+    chunk_totals_kernel<double><<<(unsigned)blocks, CW * 32, 0, st>>>((const double *)state, n, chunk_bits, nct, totals);
+  } else
+  if (by_dtype(dtype, [&] { chunk_totals_kernel<cplx<double>><<<(unsigned)blocks, CW * 32, 0, st>>>(CD(state), n, chunk_bits, nct, totals); },
+               [&] { chunk_totals_kernel<cplx<float>><<<(unsigned)blocks, CW * 32, 0, st>>>(CF(state), n, chunk_bits, nct, totals); })) return -1;
   TQB_CHECK_LAUNCH("chunk_totals_kernel");
   return 0;
 }
@@ -933,9 +979,12 @@ int tqb_sample(const void *state, int n, int64_t batch, int dtype, const double 
   const long long nc = 1ll << (n - chunk_bits);
   dim3 grid((unsigned)((shots + 127) / 128), (unsigned)batch);
   cudaStream_t st = as_stream(stream);
+  if (dtype == TQB_F64) {
+    sample_kernel<double><<<grid, 128, 0, st>>>((const double *)state, n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev);
+  } else
   if (by_dtype(dtype,
-               [&] { sample_kernel<double><<<grid, 128, 0, st>>>(CD(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
-               [&] { sample_kernel<float><<<grid, 128, 0, st>>>(CF(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
+               [&] { sample_kernel<cplx<double>><<<grid, 128, 0, st>>>(CD(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
+               [&] { sample_kernel<cplx<float>><<<grid, 128, 0, st>>>(CF(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
     return -1;
   TQB_CHECK_LAUNCH("sample_kernel");
   return 0;
@@ -965,8 +1014,8 @@ int tqb_sample_shard(const void *state, int n_local, int dtype, const double *ch
   dim3 grid((unsigned)((shots + 127) / 128), 1);
   cudaStream_t st = as_stream(stream);
   if (by_dtype(dtype,
-               [&] { sample_kernel<double><<<grid, 128, 0, st>>>(CD(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
-               [&] { sample_kernel<float><<<grid, 128, 0, st>>>(CF(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
+               [&] { sample_kernel<cplx<double>><<<grid, 128, 0, st>>>(CD(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
+               [&] { sample_kernel<cplx<float>><<<grid, 128, 0, st>>>(CF(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
     return -1;
   TQB_CHECK_LAUNCH("sample_kernel");
   return 0;

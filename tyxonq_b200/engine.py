@@ -7,9 +7,10 @@ dicts, op names and quirks (unknown ops skipped, ``cry`` only in ``run``, ``run`
 initial state) -- but the circuit is compiled to fused passes and executed by the CUDA
 kernels of libtyxonq_b200.so on one device buffer.  There is no CPU fallback.
 
-Out of scope (raise NotImplementedError): pulse / pulse_inline ops, three-level mode,
-ZZ-crosstalk and readout-calibration noise (tiny-n physics that
-stays with the reference).
+Noise handled on the device: ``kraus`` ops (Monte-Carlo trajectory), depolarizing attenuation /
+mixing and readout calibration of the sampled distribution (engine.py:389-410, via noise.py).
+Out of scope (raise NotImplementedError): pulse / pulse_inline ops, three-level mode and
+ZZ crosstalk (tiny-n physics that stays with the reference).
 """
 from __future__ import annotations
 
@@ -164,8 +165,6 @@ class StatevectorEngine:
         use_noise = bool(kwargs.get("use_noise", False))
         noise = kwargs.get("noise") if use_noise else None
         ntype = str((noise or {}).get("type", "")).lower() if noise else ""
-        if ntype == "readout":
-            raise NotImplementedError("readout-calibration noise is outside the B200 hot path")
         state, measures, _ = self._evolve(circuit, "run")
         if shots > 0 and len(measures) > 0:
             # host-supplied uniforms (kwarg) or a fresh unseeded generator, like nb.rng(None) (engine.py:381)
@@ -173,11 +172,19 @@ class StatevectorEngine:
             if u is None:
                 u = np.random.default_rng(kwargs.get("seed")).random(shots)
             u = np.asarray(u, dtype=np.float64).reshape(-1)
-            if ntype == "depolarizing":
-                # engine.py:403-410 mixes p with the uniform distribution; equivalent two-branch draw
-                raise NotImplementedError("sampling with depolarizing mixing is not supported on the device path")
             u_pin = torch.from_numpy(u).pin_memory()
-            idx = P.sample(state, u_pin.to(self.device, non_blocking=True)).cpu().numpy()
+            u_dev = u_pin.to(self.device, non_blocking=True)
+            if ntype in ("readout", "depolarizing"):
+                # engine.py:389-410: the noise acts on the probability vector; it stays on the device (noise.py)
+                from . import noise as NZ
+                probs = P.probabilities(state)
+                if ntype == "readout":
+                    probs = NZ.apply_readout(probs, (noise or {}).get("cals", {}) or {}, n, tile=self.tile)
+                else:
+                    probs = NZ.mix_depolarizing(probs, float((noise or {}).get("p", 0.0)))
+                idx = NZ.sample_probabilities(probs, u_dev).cpu().numpy()
+            else:
+                idx = P.sample(state, u_dev).cpu().numpy()
             self.last_h2d_bytes += u.nbytes
             self.last_d2h_bytes += idx.nbytes
             vals, cnts = np.unique(idx, return_counts=True)
