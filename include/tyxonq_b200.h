@@ -33,7 +33,9 @@ extern "C" {
 
 #define TQB_C64 0
 #define TQB_C128 1
-#define TQB_F64 2 /* tqb_cdf_chunks / tqb_chunk_totals / tqb_sample only: the array holds float64 PROBABILITIES */
+#define TQB_F64 2 /* tqb_norm2 / tqb_expect_z_bits / tqb_cdf_chunks / tqb_chunk_totals / tqb_sample only: */
+                  /* the array holds float64 PROBABILITIES (a noise-mixed distribution, a density-matrix  */
+                  /* diagonal) instead of amplitudes: p_i is the entry itself                            */
 
 #define TQB_GATE_DENSE 0 /* dense 2^k x 2^k matrix, k <= 4, row-major, row = output index      */
 #define TQB_GATE_DIAG 1  /* diagonal: table of 2^k entries indexed by k GLOBAL index bits       */
@@ -190,6 +192,14 @@ int tqb_pair_sweep(void *ket, void *bra, int n, int dtype, const tqb_pair_step *
  * trial applications of apply_kraus_statevector, libs/quantum_library/kernels/statevector.py:176-186). */
 int tqb_reduced_1q(const void *state, int n, int64_t batch, int dtype, int bit, double *out_dev,
                    void *stream);
+
+/* Density matrices ride on the same kernels as a 2n-bit vector, row bits high (rho[r, c] at index
+ * r * 2^n + c): U rho U^+ is U on the row bit and conj(U) on the column bit, a Kraus channel is
+ * the 4x4 sum_i K_i (x) conj(K_i) on (row bit, column bit) -- replaces apply_1q_density /
+ * apply_2q_density / apply_kraus_density (libs/quantum_library/kernels/density_matrix.py:20-140).
+ * tqb_dm_diag: out_dev[b * 2^n + i] = Re rho_b[i, i] (the probabilities DensityMatrixEngine.run
+ * samples from and takes <Z> of, devices/simulators/density_matrix/engine.py:108-148).        */
+int tqb_dm_diag(const void *rho, int n, int64_t batch, int dtype, double *out_dev, void *stream);
 
 /* ---- measurement --------------------------------------------------------------------- */
 /* replaces StatevectorEngine._project_z (engine.py:1075-1087): zero the half with

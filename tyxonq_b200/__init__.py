@@ -9,6 +9,9 @@ Public surface (mirrors the reference's names):
   StatevectorEngine           devices/simulators/statevector/engine.py
   kernels.*                   libs/quantum_library/kernels/statevector.py
   PauliSum                    libs/quantum_library/kernels/pauli.py + dynamics.expectation
+  DensityMatrixEngine         devices/simulators/density_matrix/engine.py (rho as a 2n-bit vector on the same kernels)
+  measure.GroupedMeasurement  shots > 0 energies: hamiltonian_grouping.py + counts_expval.py + the device runtimes' loops
+  noise.TrajectoryBatch       batched Monte-Carlo Kraus trajectories (kernels/statevector.py:132-218)
   B200Backend                 numerics/api.py ArrayBackend, for ``tq.set_backend(B200Backend())``
   install()                   route ``device="statevector"`` of a live TyxonQ install to this engine
 """
@@ -22,6 +25,7 @@ _LAZY = {
     "StatevectorEngine": ("engine", "StatevectorEngine"),
     "PauliSum": ("pauli", "PauliSum"),
     "B200Backend": ("backend", "B200Backend"),
+    "DensityMatrixEngine": ("density", "DensityMatrixEngine"),
     "install": ("install", "install"),
     "uninstall": ("install", "uninstall"),
 }
@@ -32,7 +36,7 @@ def __getattr__(name: str):
         import importlib
         mod, attr = _LAZY[name]
         return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
-    if name in ("kernels", "engine", "pauli", "program", "planner", "gates", "autograd", "ucc", "vqe", "sharded", "circuits", "backend", "batched"):
+    if name in ("kernels", "engine", "pauli", "program", "planner", "gates", "autograd", "ucc", "vqe", "sharded", "circuits", "backend", "batched", "measure", "noise", "density"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -58,10 +58,10 @@ __device__ __forceinline__ double prob_of(const cplx<T> a) {
 __device__ __forceinline__ double prob_of(const double p) { return p; }
 
 // partial[(y*nbx + x)*nv + j]
-template <typename T>
-__global__ void __launch_bounds__(RT) norm2_kernel(const cplx<T> *__restrict__ state, Seg sg, double *partial) {
+template <typename E>
+__global__ void __launch_bounds__(RT) norm2_kernel(const E *__restrict__ state, Seg sg, double *partial) {
   __shared__ double sm[RT / 32];
-  const cplx<T> *s = state + ((size_t)blockIdx.y << sg.n) + ((size_t)blockIdx.x << sg.seg_bits);
+  const E *s = state + ((size_t)blockIdx.y << sg.n) + ((size_t)blockIdx.x << sg.seg_bits);
   const size_t len = (size_t)1 << sg.seg_bits;
   double v[1] = {0.0};
   for (size_t i = threadIdx.x; i < len; i += RT) v[0] += prob_of(s[i]);
@@ -71,10 +71,10 @@ __global__ void __launch_bounds__(RT) norm2_kernel(const cplx<T> *__restrict__ s
 // <Z> on every local bit.  Elements visited by one thread are i = it*RT + tid, so bits below
 // log2(RT) are fixed per thread, bits in [8, seg_bits) vary with `it`, bits >= seg_bits are
 // fixed per CTA.
-template <typename T>
-__global__ void __launch_bounds__(RT) expect_z_bits_kernel(const cplx<T> *__restrict__ state, Seg sg, double *partial) {
+template <typename E>
+__global__ void __launch_bounds__(RT) expect_z_bits_kernel(const E *__restrict__ state, Seg sg, double *partial) {
   __shared__ double sm[(RT / 32) * MAX_ACC];
-  const cplx<T> *s = state + ((size_t)blockIdx.y << sg.n) + ((size_t)blockIdx.x << sg.seg_bits);
+  const E *s = state + ((size_t)blockIdx.y << sg.n) + ((size_t)blockIdx.x << sg.seg_bits);
   const size_t len = (size_t)1 << sg.seg_bits;
   constexpr int LT = 8;  // log2(RT)
   constexpr int MID = 16;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(RT) expect_z_bits_kernel(const cplx<T> *__rest
     for (int u = 0; u < (1 << U); ++u) acc[u] = 0.0;
     const size_t iters = len / RT;
     for (size_t it0 = 0; it0 < iters; it0 += (1 << U)) {
-      cplx<T> a[1 << U];
+      E a[1 << U];
 #pragma unroll
       for (int u = 0; u < (1 << U); ++u) a[u] = s[(it0 + u) * RT + threadIdx.x];
       double blk = 0.0;
@@ -501,6 +501,16 @@ __global__ void __launch_bounds__(RT) probs_kernel(const cplx<T> *__restrict__ s
   for (size_t i = (size_t)blockIdx.x * RT + threadIdx.x; i < total; i += (size_t)gridDim.x * RT) out[i] = prob_of(state[i]);
 }
 
+// Diagonal of a density matrix stored as a 2n-bit vector (row bits high): out[b * 2^n + i] = Re rho_b[i, i].
+template <typename T>
+__global__ void __launch_bounds__(RT) dm_diag_kernel(const cplx<T> *__restrict__ rho, int n, size_t total, double *out) {
+  const size_t dim = (size_t)1 << n;
+  for (size_t j = (size_t)blockIdx.x * RT + threadIdx.x; j < total; j += (size_t)gridDim.x * RT) {
+    const size_t b = j >> n, i = j & (dim - 1);
+    out[j] = (double)rho[(b << (2 * n)) + i * (dim + 1)].x;
+  }
+}
+
 // ---- sampler ---------------------------------------------------------------------------------
 // Chunk totals in the documented order: strictly sequential float64 sum of p_i over the chunk.
 // One warp owns 32 consecutive chunks; global loads are coalesced (32 consecutive amplitudes of
@@ -675,8 +685,11 @@ int tqb_norm2(const void *state, int n, int64_t batch, int dtype, double *out_de
   double *partial = (double *)ws->ptr;
   dim3 grid(nbx, (unsigned)batch);
   cudaStream_t st = as_stream(stream);
-  if (by_dtype(dtype, [&] { norm2_kernel<double><<<grid, RT, 0, st>>>(CD(state), sg, partial); },
-               [&] { norm2_kernel<float><<<grid, RT, 0, st>>>(CF(state), sg, partial); })) return -1;
+  if (dtype == TQB_F64) {
+    norm2_kernel<double><<<grid, RT, 0, st>>>((const double *)state, sg, partial);
+  } else
+  if (by_dtype(dtype, [&] { norm2_kernel<cplx<double>><<<grid, RT, 0, st>>>(CD(state), sg, partial); },
+               [&] { norm2_kernel<cplx<float>><<<grid, RT, 0, st>>>(CF(state), sg, partial); })) return -1;
   TQB_CHECK_LAUNCH("norm2_kernel");
   finish_kernel<<<(unsigned)batch, 32, 0, st>>>(partial, nbx, 1, 1, out_dev, 1);
   TQB_CHECK_LAUNCH("finish_kernel");
@@ -692,8 +705,11 @@ int tqb_expect_z_bits(const void *state, int n, int64_t batch, int dtype, double
   double *partial = (double *)ws->ptr;
   dim3 grid(nbx, (unsigned)batch);
   cudaStream_t st = as_stream(stream);
-  if (by_dtype(dtype, [&] { expect_z_bits_kernel<double><<<grid, RT, 0, st>>>(CD(state), sg, partial); },
-               [&] { expect_z_bits_kernel<float><<<grid, RT, 0, st>>>(CF(state), sg, partial); })) return -1;
+  if (dtype == TQB_F64) {
+    expect_z_bits_kernel<double><<<grid, RT, 0, st>>>((const double *)state, sg, partial);
+  } else
+  if (by_dtype(dtype, [&] { expect_z_bits_kernel<cplx<double>><<<grid, RT, 0, st>>>(CD(state), sg, partial); },
+               [&] { expect_z_bits_kernel<cplx<float>><<<grid, RT, 0, st>>>(CF(state), sg, partial); })) return -1;
   TQB_CHECK_LAUNCH("expect_z_bits_kernel");
   finish_kernel<<<(unsigned)batch, 64, 0, st>>>(partial, nbx, MAX_ACC, n, out_dev, n);
   TQB_CHECK_LAUNCH("finish_kernel");
@@ -941,6 +957,21 @@ static int launch_chunk_totals(const void *state, int n, int64_t batch, int dtyp
   if (by_dtype(dtype, [&] { chunk_totals_kernel<cplx<double>><<<(unsigned)blocks, CW * 32, 0, st>>>(CD(state), n, chunk_bits, nct, totals); },
                [&] { chunk_totals_kernel<cplx<float>><<<(unsigned)blocks, CW * 32, 0, st>>>(CF(state), n, chunk_bits, nct, totals); })) return -1;
   TQB_CHECK_LAUNCH("chunk_totals_kernel");
+  return 0;
+}
+
+int tqb_dm_diag(const void *rho, int n, int64_t batch, int dtype, double *out_dev, void *stream) {
+  TQB_REQUIRE(rho && out_dev && n >= 0 && n <= 20 && batch >= 1, "tqb_dm_diag: bad arguments (n <= 20 qubits)");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  const size_t total = (size_t)batch << n;
+  size_t bx = (total + RT - 1) / RT;
+  const size_t cap = (size_t)ws->sm_count * 16;
+  if (bx > cap) bx = cap;
+  cudaStream_t st = as_stream(stream);
+  if (by_dtype(dtype, [&] { dm_diag_kernel<double><<<(unsigned)bx, RT, 0, st>>>(CD(rho), n, total, out_dev); },
+               [&] { dm_diag_kernel<float><<<(unsigned)bx, RT, 0, st>>>(CF(rho), n, total, out_dev); })) return -1;
+  TQB_CHECK_LAUNCH("dm_diag_kernel");
   return 0;
 }
 

@@ -17,10 +17,11 @@ from typing import Any, Dict
 _saved: Dict[str, Any] = {}
 
 
-def install(set_backend: bool = False) -> None:
+def install(set_backend: bool = False, density: bool = False) -> None:
     """``set_backend=True`` additionally makes ``B200Backend`` the process-global numerics backend (seam B3,
     numerics/__init__.py:20-36), so that ``Circuit.state()`` returns device tensors and ``K.value_and_grad`` runs the
-    adjoint sweep."""
+    adjoint sweep.  ``density=True`` also routes ``device="density_matrix"`` (driver.py:20-30) to the
+    density-matrix engine that rides on the same kernels (density.py; at most 17 qubits)."""
     import importlib
     drv = importlib.import_module("tyxonq.devices.simulators.driver")
     eng_mod = importlib.import_module("tyxonq.devices.simulators.statevector.engine")
@@ -40,6 +41,9 @@ def install(set_backend: bool = False) -> None:
         name = device.split("::")[-1] if "::" in device else device
         if name in ("simulator:statevector", "statevector"):
             return StatevectorEngine
+        if density and name in ("simulator:density_matrix", "density_matrix"):
+            from .density import DensityMatrixEngine
+            return DensityMatrixEngine
         return ref_select(device)
 
     drv._select_engine = _select_engine
