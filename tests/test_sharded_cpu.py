@@ -31,6 +31,11 @@ class _EmuLocal:
         out = run_program_emulated(prog, state.numpy(), global_base=global_base)
         state.copy_(torch.from_numpy(out))
 
+    def zmasks_local(self, state, masks, global_base):
+        p = np.abs(state.numpy()) ** 2
+        idx = np.arange(p.size, dtype=np.int64) | int(global_base)
+        return torch.tensor([float(np.sum(p * (1 - 2 * (np.array([bin(int(i) & m).count("1") & 1 for i in idx]))))) for m in masks], dtype=torch.float64)
+
     def reduce_local(self, state, n_local):
         p = np.abs(state.numpy()) ** 2
         idx = np.arange(p.size)
@@ -50,7 +55,10 @@ def _worker(rank, world, port, n, ops, out_dir):
         st.init_zero()
         st.run(plan)
         z = st.expect_z_all().numpy()
+        zz = st.expect_zmasks([(1 << b) | (1 << (b + 1)) for b in range(n - 1)] + [(1 << n) - 1]).numpy()
         np.save(os.path.join(out_dir, f"shard{rank}.npy"), st.state.numpy())
+        if rank == 0:
+            np.save(os.path.join(out_dir, "zz.npy"), zz)
         if rank == 0:
             np.save(os.path.join(out_dir, "z.npy"), z)
             np.save(os.path.join(out_dir, "phys.npy"), np.array(plan.final_phys))
@@ -95,6 +103,13 @@ def test_sharded_matches_oracle(tmp_path, world, n, kind):
     z = np.load(tmp_path / "z.npy")
     for q in range(n):
         assert abs(z[n - 1 - q] - O.expect_z(ref, q, n)) < 1e-12
+    zz = np.load(tmp_path / "zz.npy")
+    p = np.abs(ref) ** 2
+    for b in range(n - 1):
+        sgn = 1 - 2 * (((idx >> b) & 1) ^ ((idx >> (b + 1)) & 1))
+        assert abs(zz[b] - np.sum(p * sgn)) < 1e-12
+    par = np.array([bin(int(i)).count("1") & 1 for i in idx])
+    assert abs(zz[n - 1] - np.sum(p * (1 - 2 * par))) < 1e-12
     assert int(np.load(tmp_path / "nex.npy")[0]) >= 1  # the circuits touch the global qubits
 
 

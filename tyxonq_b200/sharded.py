@@ -333,8 +333,23 @@ class ShardedState:
         return zphys[torch.tensor(self.phys, device=self.device)]
 
 
+    def expect_zmasks(self, masks: Sequence[int]) -> torch.Tensor:
+        """<prod_{b in mask} Z_b> for masks over LOGICAL index bits (qubit q = bit n-1-q), float64 [len(masks)] on every
+        rank: the masks are remapped to physical bits (rank bits included: their parity comes from global_base), one
+        local read + one all-reduce.  Covers diagonal Hamiltonians (ZZ couplings, fields) without any exchange."""
+        pm = [_remap_mask(int(m), self.phys) for m in masks]
+        out = self.backend.zmasks_local(self.state, pm, self.global_base)
+        if self.world > 1:
+            dist.all_reduce(out, group=self.group)
+        return out
+
+
 class _CudaLocal:
     """Local work of one rank on its GPU: the fused passes and reductions of libtyxonq_b200.so."""
+
+    def zmasks_local(self, state: torch.Tensor, masks: Sequence[int], global_base: int) -> torch.Tensor:
+        from . import program as P
+        return P.expect_zmasks(state, list(masks), global_base=global_base)[0]
 
     def __init__(self, owner: "ShardedState") -> None:
         self.owner = owner
