@@ -130,3 +130,20 @@ def test_planner_fuses_layers():
     prog = P.compile_program(lg, n, P.TileConfig(m=11, L=5))
     assert prog.n_passes < len(lg) / 3  # many gates per state sweep
     assert sorted(prog.order) == list(range(len(lg)))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_chains_grouped_after_scheduling_only_take_tile_local_targets(seed):
+    """Diagonal 1-qubit gates ride along in any pass (no tile-local bit needed); when chains are grouped per pass such
+    a gate must not become a chain layer unless its bit IS in the tile (regression: KeyError in compile_program)."""
+    from tyxonq_b200.fuse import fuse
+    rng = np.random.default_rng(100 + seed)
+    n = 11
+    ops = random_ops(rng, n, 160)
+    ref, _ = O.evolve_ops(n, ops, mode="run")
+    prog = P.compile_program(fuse(_lower(ops, n)), n, P.TileConfig(m=7, L=3))
+    psi0 = np.zeros(1 << n, dtype=np.complex128)
+    psi0[0] = 1
+    assert np.abs(run_program_emulated(prog, psi0) - ref).max() < 1e-12
+    kinds = {(int(g["kind"]), int(g["k"]), int(g["off_a"])) for g in prog.gates if int(g["kind"]) == 5}
+    assert kinds  # the random circuits do produce chains

@@ -27,7 +27,7 @@ class _EmuLocal:
     def run_local(self, state, gates, n_local, global_base, cache_slot):
         from tests.emu.emu import run_program_emulated
         from tyxonq_b200.planner import TileConfig, compile_program
-        prog = compile_program(gates, n_local, TileConfig(m=min(n_local, 6), L=2))
+        prog = compile_program(gates, n_local, TileConfig(m=min(n_local, 6), L=2), chain=True)
         out = run_program_emulated(prog, state.numpy(), global_base=global_base)
         state.copy_(torch.from_numpy(out))
 

@@ -22,7 +22,7 @@ import torch
 
 from . import _lib
 from . import program as P
-from .gates import DENSE, DIAG, GEN, PAIR, SWAP, LGate, lower_op, _to_np
+from .gates import CHAIN, DENSE, DIAG, GEN, MUX, PAIR, SWAP, LGate, lower_op, _to_np
 from .planner import compile_program, default_tile
 
 
@@ -44,7 +44,10 @@ def dagger(g: LGate) -> LGate:
         d = g.data.copy()
     else:
         d = np.concatenate([b.reshape(2, 2).conj().T.reshape(4) for b in g.data.reshape(-1, 4)])
-    return LGate(g.kind, g.bits, d, pat_a=g.pat_a, pat_b=g.pat_b, zmask=g.zmask, name=g.name + "^")
+    # MUX / CHAIN carry a structure tag in pat_b that does not survive the dagger ((U, X.U)^+ = (U^+, U^+.X))
+    pat_b = 0 if g.kind in (MUX, CHAIN) else g.pat_b
+    assert g.kind != CHAIN or g.pat_b == 0, "daggering a rotation-form CHAIN is not supported: dagger before fusion"
+    return LGate(g.kind, g.bits, d, pat_a=g.pat_a, pat_b=pat_b, zmask=g.zmask, name=g.name + "^")
 
 
 def grad_dense(bra: torch.Tensor, ket: torch.Tensor, bits: Sequence[int], gen: np.ndarray, scale: float,

@@ -428,6 +428,127 @@ TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, 
   }
 }
 
+// CHAIN in rotation form (g.off_a = 4 + 2*TYPE + MUXED).  A 1-qubit unitary whose column ratio is imaginary
+// (rz.rx products: every layer of a hardware-efficient or Trotter circuit) factors as U = M.D with
+// M = [[a, i r], [i r, a]] (TYPE 0) and D diagonal; a real-ratio unitary (ry, h) as M = [[a, -r], [r, a]]
+// (TYPE 1).  Inside a chain every D acts on a bit no earlier layer touches, so all of them commute to the FRONT
+// as one table P over the 2^R register indices, and M commutes with the fused cx (X.M = M.X for TYPE 0,
+// X.M = M^T.X for TYPE 1), which therefore is an input rename.  Per amplitude: one complex multiply by P and
+// R real rotations = 4 + 4R multiply-adds instead of 8R, and 2^R + R matrix entries instead of 8R.
+// Data: M[0 .. 2^R) = P, M[2^R + i] = (a_i, r_i).  MUXED: layers i > 0 are selected by bit bits[i-1] (cx after
+// the gate); layer 0 by the outer control when bits[R] != 127 (run-time: loads and P index flip with its value).
+template <typename T, int R, int I, int TYPE, bool MUXED>
+TQB_HD void rot_layer(cplx<T> (&v)[1 << R], const T a, const T r) {
+#pragma unroll
+  for (int s = 0; s < (1 << R); ++s) {
+    if (s & (1 << I)) continue;
+    const bool sel = MUXED && I > 0 && ((s >> (I > 0 ? I - 1 : 0)) & 1);
+    const int lo = s, hi = s | (1 << I);
+    const cplx<T> x0 = v[sel ? hi : lo], x1 = v[sel ? lo : hi];
+    const T rr = (TYPE == 1 && sel) ? -r : r;
+    cplx<T> y0, y1;
+    if (TYPE == 0) {
+      y0.x = a * x0.x - rr * x1.y;
+      y0.y = a * x0.y + rr * x1.x;
+      y1.x = a * x1.x - rr * x0.y;
+      y1.y = a * x1.y + rr * x0.x;
+    } else {
+      y0.x = a * x0.x - rr * x1.x;
+      y0.y = a * x0.y - rr * x1.y;
+      y1.x = a * x1.x + rr * x0.x;
+      y1.y = a * x1.y + rr * x0.y;
+    }
+    v[lo] = y0;
+    v[hi] = y1;
+  }
+}
+
+template <typename T, int R, int TYPE, bool MUXED>
+TQB_HD void gate_chain_rot(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  uint32_t tb[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) tb[i] = (uint32_t)g.bits[i];
+  const uint32_t cb = (uint32_t)(uint8_t)g.bits[R];
+  const bool ctrl_local = cb < 64u;
+  uint32_t cv_fixed = 0;
+  if (!ctrl_local && cb != 127u) cv_fixed = (uint32_t)((gbase >> (cb & 63u)) & 1ull);
+  constexpr int NZ = R + 1;
+  uint32_t sb[NZ];
+#pragma unroll
+  for (int j = 0; j < NZ; ++j) sb[j] = (uint32_t)g.sbits[j];
+  const int nz = ctrl_local ? R + 1 : R;
+  const uint32_t free_bits = (uint32_t)(m - nz);
+  const uint32_t ngroups = 1u << (m - R);
+  T a[R], r[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const cplx<T> c = M[(1 << R) + i];
+    a[i] = c.x;
+    r[i] = c.y;
+  }
+  auto offset = [&](uint32_t base, int s) {
+    uint32_t o = base;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+      if (s & (1 << i)) o |= 1u << tb[i];
+    return o;
+  };
+  auto locate = [&](uint32_t gi, uint32_t &base, uint32_t &cv) {
+    uint32_t lo = gi;
+    cv = cv_fixed;
+    if (ctrl_local) {
+      cv = gi >> free_bits;
+      lo = gi & ((1u << free_bits) - 1u);
+    }
+    base = lo;
+#pragma unroll
+    for (int j = 0; j < NZ; ++j)
+      if (j < nz) base = ((base >> sb[j]) << (sb[j] + 1u)) | (base & ((1u << sb[j]) - 1u));
+    if (ctrl_local) base |= cv << cb;
+  };
+  // (two groups per iteration was measured slower here as well: profiles/r01_tile_sweep.md)
+  uint32_t gi = tid;
+  for (; gi < ngroups; gi += nthreads) {
+    uint32_t base, cv;
+    locate(gi, base, cv);
+    const uint32_t flip = cv << tb[0];
+    const int icv = (int)cv;
+    cplx<T> v[1 << R];
+#pragma unroll
+    for (int s = 0; s < (1 << R); ++s) v[s] = cmul(tile[offset(base, s) ^ flip], M[(s & 1) ? s - icv : s + icv]);
+    rot_layer<T, R, 0, TYPE, false>(v, a[0], (TYPE == 1 && cv) ? -r[0] : r[0]);
+    rot_layer<T, R, 1, TYPE, MUXED>(v, a[1], r[1]);
+    if (R > 2) rot_layer<T, R, (R > 2 ? 2 : 1), TYPE, MUXED>(v, a[R > 2 ? 2 : 1], r[R > 2 ? 2 : 1]);
+    if (R > 3) rot_layer<T, R, (R > 3 ? 3 : 1), TYPE, MUXED>(v, a[R > 3 ? 3 : 1], r[R > 3 ? 3 : 1]);
+#pragma unroll
+    for (int s = 0; s < (1 << R); ++s) tile[offset(base, s)] = v[s];
+  }
+}
+
+// R = 4 exists in rotation form only (16 amplitudes + 4 coefficient pairs fit the register budget; the general
+// form would need 32 matrix registers on top)
+template <typename T>
+TQB_HD void gate_chain4(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  switch (g.off_a) {
+    case 4: gate_chain_rot<T, 4, 0, false>(tile, m, gbase, g, M, tid, nthreads); break;
+    case 5: gate_chain_rot<T, 4, 0, true>(tile, m, gbase, g, M, tid, nthreads); break;
+    case 6: gate_chain_rot<T, 4, 1, false>(tile, m, gbase, g, M, tid, nthreads); break;
+    case 7: gate_chain_rot<T, 4, 1, true>(tile, m, gbase, g, M, tid, nthreads); break;
+    default: break;
+  }
+}
+
+template <typename T, int R>
+TQB_HD void gate_chain_any(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  switch (g.off_a) {
+    case 4: gate_chain_rot<T, R, 0, false>(tile, m, gbase, g, M, tid, nthreads); break;
+    case 5: gate_chain_rot<T, R, 0, true>(tile, m, gbase, g, M, tid, nthreads); break;
+    case 6: gate_chain_rot<T, R, 1, false>(tile, m, gbase, g, M, tid, nthreads); break;
+    case 7: gate_chain_rot<T, R, 1, true>(tile, m, gbase, g, M, tid, nthreads); break;
+    default: gate_chain<T, R>(tile, m, gbase, g, M, tid, nthreads); break;
+  }
+}
+
 // gbase = global_base | tile base: the state index of tile element 0, high shard bits included.
 // MAXK bounds the dense gate size this instantiation can execute (2 = light, few registers;
 // 4 = heavy): the host picks the variant per pass.  mats = base of the matrix buffer (staged in
@@ -451,8 +572,9 @@ TQB_HD void tile_apply_gate(cplx<T> *tile, const TileGeom &geo, const uint64_t *
     case TQB_GATE_SWAP: gate_pair<T, true>(tile, geo, roff, gbase, g, mat, tid, nthreads); break;
     case TQB_GATE_MUX: gate_mux<T>(tile, geo.m, gbase, g, mat, tid, nthreads); break;
     case TQB_GATE_CHAIN:
-      if (g.k == 2) gate_chain<T, 2>(tile, geo.m, gbase, g, mat, tid, nthreads);
-      else if (g.k == 3) gate_chain<T, 3>(tile, geo.m, gbase, g, mat, tid, nthreads);
+      if (g.k == 2) gate_chain_any<T, 2>(tile, geo.m, gbase, g, mat, tid, nthreads);
+      else if (g.k == 3) gate_chain_any<T, 3>(tile, geo.m, gbase, g, mat, tid, nthreads);
+      else if (g.k == 4) gate_chain4<T>(tile, geo.m, gbase, g, mat, tid, nthreads);
       break;
     default: break;
   }

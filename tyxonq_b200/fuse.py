@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from .gates import DENSE, DIAG, MUX, SWAP, X_MAT, LGate, chain_gate, mux_gate
+from .gates import DENSE, DIAG, LAYER_PLAIN, MUX, MUX_XU, SWAP, X_MAT, LGate, chain_gate, mux_gate, rot_decompose, rot_plan
 
 C128 = np.complex128
 _I2 = np.eye(2, dtype=C128)
@@ -88,14 +88,22 @@ def _simplify_mux(g: LGate) -> LGate:
 
 
 def _as_layer(g: LGate):
-    """(target_bit, control_bit | None, M_sel0, M_sel1) for gates a CHAIN layer can carry."""
+    """(target_bit, control_bit | None, M_sel0, M_sel1, structure tag) for gates a CHAIN layer can carry."""
     if _is_1q(g):
         m = _m1(g)
-        return g.bits[0], None, m, m
+        return g.bits[0], None, m, m, LAYER_PLAIN, _rot_of(g, m)
     if g.kind == MUX:
         u0, u1 = _mux_blocks(g)
-        return g.bits[0], g.bits[1], u0, u1
+        return g.bits[0], g.bits[1], u0, u1, g.pat_b, _rot_of(g, u0)
     return None
+
+
+def _rot_of(g: LGate, u0: np.ndarray):
+    d = g.__dict__.get("_rot")
+    if d is None:
+        d = rot_decompose(u0)
+        g.__dict__["_rot"] = d
+    return d
 
 
 def _mux_blocks(g: LGate):
@@ -105,10 +113,12 @@ def _mux_blocks(g: LGate):
     return g.data[:4].reshape(2, 2), g.data[4:].reshape(2, 2)
 
 
-def chain_fuse(gates: Sequence[LGate], R: int = 3) -> List[LGate]:
+def chain_fuse(gates: Sequence[LGate], R: int = 3, R_rot: int = 4, local_bits: Optional[set] = None) -> List[LGate]:
     """Group ADJACENT 1-qubit / MUX gates into CHAIN gates of up to R layers: one shared-memory round
     trip for R gates.  Layer i > 0 must be uncontrolled or controlled by layer i-1's target (the shape
-    of a cx ladder); layer 0 may carry any control."""
+    of a cx ladder); layer 0 may carry any control.  Chains whose layers all factor as rotation x diagonal
+    (gates.rot_plan) may grow to R_rot layers: the rotation form needs few registers per layer.  ``local_bits``: the
+    index bits that are tile-local (grouping after scheduling); layers must have their target among them."""
     out: List[LGate] = []
     cur: List[tuple] = []   # (layer, original gate)
 
@@ -117,11 +127,14 @@ def chain_fuse(gates: Sequence[LGate], R: int = 3) -> List[LGate]:
             out.append(cur[0][1])
         elif cur:
             c0 = cur[0][0][1]
-            out.append(chain_gate([(l[0], l[2], l[3]) for l, _ in cur], control_bit=c0, name="chain"))
+            out.append(chain_gate([(l[0], l[2], l[3]) for l, _ in cur], control_bit=c0,
+                                  structure=[l[4] for l, _ in cur], decs=[l[5] for l, _ in cur], name="chain"))
         cur.clear()
 
     for g in gates:
         lay = _as_layer(g)
+        if lay is not None and local_bits is not None and lay[0] not in local_bits:
+            lay = None   # a diagonal 1-qubit gate riding along on a bit outside the tile: it cannot be a chain layer
         if lay is None:
             flush()
             out.append(g)
@@ -130,9 +143,14 @@ def chain_fuse(gates: Sequence[LGate], R: int = 3) -> List[LGate]:
         if cur:
             tgts = [l[0] for l, _ in cur]
             c0 = cur[0][0][1]
-            if len(cur) < R and t not in tgts and t != c0 and (c is None or c == tgts[-1]):
-                cur.append((lay, g))
-                continue
+            if t not in tgts and t != c0 and (c is None or c == tgts[-1]):
+                if len(cur) < R:
+                    cur.append((lay, g))
+                    continue
+                if len(cur) < R_rot and rot_plan([l[5] for l, _ in cur] + [lay[5]], [l[4] for l, _ in cur] + [lay[4]],
+                                                 c0 is not None) is not None:
+                    cur.append((lay, g))
+                    continue
             flush()
         cur.append((lay, g))
     flush()
@@ -174,11 +192,20 @@ def _conjugated_diagonals(gates: Sequence[LGate]) -> List[LGate]:
     return [g for i, g in enumerate(gates) if not dead[i]]
 
 
-def fuse(gates: Sequence[LGate], max_diag_k: int = 6, chain: int = 3) -> List[LGate]:
-    """Algebraic merges (see module docstring), then CHAIN grouping of up to ``chain`` layers
-    (0/1 disables it)."""
-    merged = _merge(_conjugated_diagonals(gates), max_diag_k)
-    return chain_fuse(merged, chain) if chain >= 2 else merged
+class FusedGates(list):
+    """Output of ``fuse`` when CHAIN grouping is deferred: ``compile_program`` groups the gates of every pass into
+    chains AFTER scheduling (a chain needs all its targets tile-local at once; grouping first would tie the
+    scheduler's hands: 605 instead of 400 passes for a 30-qubit depth-100 hardware-efficient ansatz)."""
+    chain_after_schedule = True
+
+
+def fuse(gates: Sequence[LGate], max_diag_k: int = 6, chain: int = 0) -> List[LGate]:
+    """Algebraic merges (see module docstring).  ``chain`` >= 2 groups CHAINs of up to that many layers right away
+    (the round-1 first version); the default 0 leaves the grouping to ``compile_program`` (per pass, after scheduling)."""
+    merged = _merge(_conjugated_diagonals(list(gates)), max_diag_k)
+    if chain >= 2:
+        return chain_fuse(merged, chain, chain)
+    return FusedGates(merged)
 
 
 def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
@@ -221,7 +248,7 @@ def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
             if _is_1q(p):                                  # cx after a 1q gate on its target: U (c=0), X.U (c=1)
                 u = _m1(p)
                 out[j] = None
-                g = mux_gate(u, X_MAT @ u, t, c, name="fused")
+                g = mux_gate(u, X_MAT @ u, t, c, structure=MUX_XU, name="fused")
             elif p is not None and p.kind == MUX and p.bits == (t, c) and last.get(c) == j:
                 u0, u1 = _mux_blocks(p)
                 out[j] = _simplify_mux(mux_gate(u0, X_MAT @ u1, t, c, name="fused"))

@@ -185,31 +185,113 @@ def swap_gate(qubits: Sequence[int], n: int, pat_a: int, pat_b: int, **kw: Any) 
     return LGate(SWAP, _bits_of(qubits, n), X_MAT.reshape(4).copy(), pat_a=int(pat_a), pat_b=int(pat_b), **kw)
 
 
-def mux_gate(u0: np.ndarray, u1: np.ndarray, target_bit: int, control_bit: int, **kw: Any) -> LGate:
-    """1-qubit gate on index bit ``target_bit``: u0 where index bit ``control_bit`` is 0, u1 where it is 1."""
+MUX_GENERAL, MUX_XU, LAYER_PLAIN = 0, 2, 3   # how a chain layer was BUILT: arbitrary pair | u1 = X.u0 (cx after the gate) | u1 = u0
+
+
+def mux_gate(u0: np.ndarray, u1: np.ndarray, target_bit: int, control_bit: int, structure: int = MUX_GENERAL, **kw: Any) -> LGate:
+    """1-qubit gate on index bit ``target_bit``: u0 where index bit ``control_bit`` is 0, u1 where it is 1.
+    ``structure`` (kept in ``pat_b``) records that the pair is a gate followed by a fused cx (u1 = X.u0)."""
     u0 = np.asarray(u0, dtype=C128)
     u1 = np.asarray(u1, dtype=C128)
     if u0.size == 4 and u1.size == 4:
         d = np.concatenate([u0.reshape(4), u1.reshape(4)])
-        return LGate(MUX, (int(target_bit), int(control_bit)), d, **kw)
+        return LGate(MUX, (int(target_bit), int(control_bit)), d, pat_b=int(structure), **kw)
     B = max(u0.size, u1.size) // 4   # one matrix pair per batch member
     d = np.concatenate([np.broadcast_to(u0.reshape(-1, 4), (B, 4)), np.broadcast_to(u1.reshape(-1, 4), (B, 4))], axis=1)
-    return LGate(MUX, (int(target_bit), int(control_bit)), np.ascontiguousarray(d), batched=True, **kw)
+    return LGate(MUX, (int(target_bit), int(control_bit)), np.ascontiguousarray(d), pat_b=int(structure), batched=True, **kw)
 
 
-def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit: Optional[int] = None, **kw: Any) -> LGate:
-    """R = 2 or 3 one-qubit layers [(target_bit, M_sel0, M_sel1), ...]: layer 0 is selected by
-    ``control_bit`` (None: M_sel0 is used), layer i > 0 by the value of layer i-1's target bit."""
-    assert 2 <= len(layers) <= 3
+def rot_decompose(u: np.ndarray) -> Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]]:
+    """U = M.diag(d0, d1) with M = [[a, i r], [i r, a]] (type 0: rz.rx products) or M = [[a, -r], [r, a]] (type 1: ry, h),
+    a and r real, for every member of u [B, 2, 2].  Returns {type: (a, r, d0, d1)} for the types that reproduce U to
+    1e-13 on ALL members (tqb_core.cuh gate_chain_rot runs such layers with half the multiply-adds)."""
+    u = np.asarray(u, dtype=C128).reshape(-1, 2, 2)
+    if u.shape[0] == 1:
+        return _rot_decompose_scalar(*[complex(x) for x in u.reshape(4)])
+    u00, u01, u10, u11 = u[:, 0, 0], u[:, 0, 1], u[:, 1, 0], u[:, 1, 1]
+    av, rv = np.abs(u00), np.abs(u10)
+    big = av >= rv
+    sa, sr = np.where(av > 0, av, 1.0), np.where(rv > 0, rv, 1.0)
+    out: Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = {}
+    for typ, f10, f01 in ((0, 1j, 1j), (1, 1.0, -1.0)):      # M10 = f10 * r, M01 = f01 * r
+        d0 = np.where(big, u00 / sa, u10 / (f10 * sr))
+        d1 = np.where(big, u11 / sa, u01 / (f01 * sr))
+        with np.errstate(all="ignore"):                       # a zero d0 fails the |d| = 1 check below
+            a = (u00 / d0).real
+            r = (u10 / (f10 * d0)).real
+        rec = np.stack([a * d0, f01 * r * d1, f10 * r * d0, a * d1], axis=1)
+        if np.all(np.abs(np.abs(d0) - 1) < 1e-13) and np.all(np.abs(np.abs(d1) - 1) < 1e-13) and \
+                np.abs(rec - u.reshape(-1, 4)).max() < 1e-13:
+            out[typ] = (a, r, d0, d1)
+    return out
+
+
+def _rot_decompose_scalar(u00: complex, u01: complex, u10: complex, u11: complex):
+    """rot_decompose for one matrix in plain Python complex arithmetic (the planner calls it once per gate)."""
+    av, rv = abs(u00), abs(u10)
+    out = {}
+    for typ, f10, f01 in ((0, 1j, 1j), (1, 1.0, -1.0)):
+        if av >= rv:
+            if av == 0.0:
+                continue
+            d0, d1 = u00 / av, u11 / av
+        else:
+            d0, d1 = u10 / (f10 * rv), u01 / (f01 * rv)
+        if abs(abs(d0) - 1) > 1e-13 or abs(abs(d1) - 1) > 1e-13:
+            continue
+        a = (u00 / d0).real
+        r = (u10 / (f10 * d0)).real
+        if max(abs(a * d0 - u00), abs(f01 * r * d1 - u01), abs(f10 * r * d0 - u10), abs(a * d1 - u11)) < 1e-13:
+            out[typ] = (np.array([a]), np.array([r]), np.array([d0], dtype=C128), np.array([d1], dtype=C128))
+    return out
+
+
+def rot_plan(decs: Sequence[Dict[int, Any]], tags: Sequence[int], has_control: bool):
+    """(type, muxed, decompositions) when a chain whose selector-0 matrices decompose as ``decs`` (rot_decompose) with
+    structure ``tags`` can run in rotation form (tqb_core.cuh gate_chain_rot), else None."""
+    tags = [int(t) for t in tags]
+    rest = set(tags[1:])
+    if tags[0] != (MUX_XU if has_control else LAYER_PLAIN) or len(rest) != 1 or not rest <= {MUX_XU, LAYER_PLAIN}:
+        return None
+    for typ in (0, 1):
+        if all(typ in d for d in decs):
+            return typ, (1 if tags[1] == MUX_XU else 0), [d[typ] for d in decs]
+    return None
+
+
+def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit: Optional[int] = None,
+               structure: Optional[Sequence[int]] = None, decs: Optional[Sequence[Dict[int, Any]]] = None, **kw: Any) -> LGate:
+    """R = 2..4 one-qubit layers [(target_bit, M_sel0, M_sel1), ...]: layer 0 is selected by
+    ``control_bit`` (None: M_sel0 is used), layer i > 0 by the value of layer i-1's target bit.
+    ``structure``: per layer MUX_GENERAL / MUX_XU / LAYER_PLAIN.  When every layer is plain or a gate followed by a
+    fused cx, and all selector-0 matrices factor as rotation x diagonal of one type (``rot_decompose``), the gate is
+    emitted in rotation form: data = [P (2^R entries), (a_i + i r_i) per layer], pat_b = 4 + 2*type + muxed
+    (R = 4 exists in rotation form only)."""
+    assert 2 <= len(layers) <= 4
+    R = len(layers)
     bits = [int(t) for t, _, _ in layers]
     B = max(max(np.asarray(a).size, np.asarray(b).size) for _, a, b in layers) // 4
-    blocks = []
-    for _, a, b in layers:
-        for m in (a, b):
-            blocks.append(np.broadcast_to(np.asarray(m, dtype=C128).reshape(-1, 4), (B, 4)))
-    data = np.ascontiguousarray(np.concatenate(blocks, axis=1))
     if control_bit is not None:
         bits.append(int(control_bit))
+    if structure is not None and decs is None:
+        decs = [rot_decompose(a) for _, a, _ in layers]
+    rot = rot_plan(decs, structure, control_bit is not None) if structure is not None else None
+    assert R <= 3 or rot is not None, "4-layer chains need the rotation form"
+    if rot is not None:
+        typ, muxed, dec = rot
+        P = np.ones((B, 1 << R), dtype=C128)
+        for s in range(1 << R):
+            for i in range(R):
+                P[:, s] *= dec[i][3] if (s >> i) & 1 else dec[i][2]
+        coef = np.stack([np.broadcast_to(dec[i][0] + 1j * dec[i][1], (B,)) for i in range(R)], axis=1)
+        data = np.ascontiguousarray(np.concatenate([P, coef], axis=1))
+        kw["pat_b"] = 4 + 2 * typ + muxed
+    else:
+        blocks = []
+        for _, a, b in layers:
+            for m in (a, b):
+                blocks.append(np.broadcast_to(np.asarray(m, dtype=C128).reshape(-1, 4), (B, 4)))
+        data = np.ascontiguousarray(np.concatenate(blocks, axis=1))
     if B == 1:
         return LGate(CHAIN, tuple(bits), data.reshape(-1), pat_a=1 if control_bit is not None else 0, **kw)
     return LGate(CHAIN, tuple(bits), data, pat_a=1 if control_bit is not None else 0, batched=True, **kw)

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import os
 from dataclasses import dataclass
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -136,7 +136,8 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
     return out
 
 
-def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_mats: int = 1, itemsize: int = 16) -> Program:
+def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_mats: int = 1, itemsize: int = 16,
+                    chain: Optional[bool] = None) -> Program:
     """Pack scheduled gates into the ABI arrays.  ``batch_mats`` > 1: every gate's ``data`` has a
     leading batch axis (one matrix per batch member) when ``gate.batched`` is set.  (``itemsize`` is accepted for call-site
     symmetry; the descriptors do not depend on the state dtype.)"""
@@ -144,6 +145,19 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
     tile = TileConfig(m=m_eff, L=min(tile.L, m_eff), threads=tile.threads, ctas_per_sm=tile.ctas_per_sm,
                       max_gates=tile.max_gates)
     sched = schedule(gates, n, tile)
+    if chain is None:
+        chain = bool(getattr(gates, "chain_after_schedule", False))
+    if chain:
+        # group the 1-qubit / MUX gates of every pass into CHAIN gates now that their targets are known to be
+        # tile-local together (``order`` then no longer maps compiled gates to input gates)
+        from .fuse import chain_fuse
+        grouped: List[LGate] = []
+        sched2 = []
+        for hb, chosen in sched:
+            sub = chain_fuse([gates[i] for i in chosen], local_bits=set(range(tile.L)) | set(int(p) for p in hb))
+            sched2.append((hb, list(range(len(grouped), len(grouped) + len(sub)))))
+            grouped += sub
+        gates, sched = grouped, sched2
     ng = sum(len(c) for _, c in sched)
     passes = np.zeros(len(sched), dtype=_lib.PASS_DTYPE)
     garr = np.zeros(ng, dtype=_lib.GATE_DTYPE)
@@ -192,6 +206,7 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
                     e["bits"][j] = b
                 ctrl = enc(g.bits[r]) if g.pat_a else 127
                 e["bits"][r] = ctrl
+                e["off_a"] = g.pat_b          # 0 = two matrices per layer; 4..7 = rotation form (tqb_core.cuh gate_chain_rot)
                 zs = sorted(loc + ([ctrl] if ctrl < 64 else []))
                 for j, b in enumerate(zs):
                     e["sbits"][j] = b

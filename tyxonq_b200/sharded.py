@@ -364,14 +364,14 @@ class _CudaLocal:
         from . import program as P
         from .planner import compile_program, default_tile
         if cache_slot is None:
-            prog = compile_program(gates, n_local, default_tile(n_local, state.element_size(), 1), itemsize=state.element_size())
+            prog = compile_program(gates, n_local, default_tile(n_local, state.element_size(), 1), itemsize=state.element_size(), chain=True)
             P.DeviceProgram(prog, state.device, state.dtype).run(state, global_base=global_base)
             return
         progs = self.owner.programs
         while len(progs) <= cache_slot:
             progs.append(None)
         if progs[cache_slot] is None:
-            prog = compile_program(gates, n_local, default_tile(n_local, state.element_size(), 1), itemsize=state.element_size())
+            prog = compile_program(gates, n_local, default_tile(n_local, state.element_size(), 1), itemsize=state.element_size(), chain=True)
             progs[cache_slot] = P.DeviceProgram(prog, state.device, state.dtype)
         progs[cache_slot].run(state, global_base=global_base)
 
