@@ -479,10 +479,17 @@ TQB_HD void gate_chain_rot(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate 
   const int nz = ctrl_local ? R + 1 : R;
   const uint32_t free_bits = (uint32_t)(m - nz);
   const uint32_t ngroups = 1u << (m - R);
+  // g.off_b: bits 0-1 = E, the number of extra index bits of the pre-diagonal table (bits[R+1 ..]: absorbed
+  // diagonal gates may reach beyond the targets), bit 7 = the table is all ones (plain rotations: skip the multiply)
+  const uint32_t E = g.off_b & 3u;
+  const bool unit_p = (g.off_b & 128u) != 0u;
+  uint32_t xb[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) xb[j] = (uint32_t)(uint8_t)g.bits[R + 1 + j];
   T a[R], r[R];
 #pragma unroll
   for (int i = 0; i < R; ++i) {
-    const cplx<T> c = M[(1 << R) + i];
+    const cplx<T> c = M[((size_t)1 << (R + E)) + i];
     a[i] = c.x;
     r[i] = c.y;
   }
@@ -512,10 +519,21 @@ TQB_HD void gate_chain_rot(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate 
     uint32_t base, cv;
     locate(gi, base, cv);
     const uint32_t flip = cv << tb[0];
-    const int icv = (int)cv;
+    const int icv = (int)cv;  // register s holds input amplitude s ^ cv (cv toggles bit 0 = layer 0's bit)
     cplx<T> v[1 << R];
+    if (unit_p) {
 #pragma unroll
-    for (int s = 0; s < (1 << R); ++s) v[s] = cmul(tile[offset(base, s) ^ flip], M[(s & 1) ? s - icv : s + icv]);
+      for (int s = 0; s < (1 << R); ++s) v[s] = tile[offset(base, s) ^ flip];
+    } else {
+      uint32_t x = 0;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if ((uint32_t)j < E)
+          x |= (xb[j] < 64u ? ((base >> xb[j]) & 1u) : (uint32_t)((gbase >> (xb[j] & 63u)) & 1ull)) << j;
+      const cplx<T> *P = M + ((size_t)x << R);
+#pragma unroll
+      for (int s = 0; s < (1 << R); ++s) v[s] = cmul(tile[offset(base, s) ^ flip], P[(s & 1) ? s - icv : s + icv]);
+    }
     rot_layer<T, R, 0, TYPE, false>(v, a[0], (TYPE == 1 && cv) ? -r[0] : r[0]);
     rot_layer<T, R, 1, TYPE, MUXED>(v, a[1], r[1]);
     if (R > 2) rot_layer<T, R, (R > 2 ? 2 : 1), TYPE, MUXED>(v, a[R > 2 ? 2 : 1], r[R > 2 ? 2 : 1]);

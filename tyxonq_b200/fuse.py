@@ -202,13 +202,14 @@ class FusedGates(list):
 def fuse(gates: Sequence[LGate], max_diag_k: int = 6, chain: int = 0) -> List[LGate]:
     """Algebraic merges (see module docstring).  ``chain`` >= 2 groups CHAINs of up to that many layers right away
     (the round-1 first version); the default 0 leaves the grouping to ``compile_program`` (per pass, after scheduling)."""
-    merged = _merge(_conjugated_diagonals(list(gates)), max_diag_k)
     if chain >= 2:
-        return chain_fuse(merged, chain, chain)
-    return FusedGates(merged)
+        return chain_fuse(_merge(_conjugated_diagonals(list(gates)), max_diag_k), chain, chain)
+    # deferred mode: multi-bit diagonal gates stay small as well -- group_pass absorbs them into the chains of their
+    # pass or merges what is left into tables there
+    return FusedGates(_merge(_conjugated_diagonals(list(gates)), max_diag_k, merge_diag=False))
 
 
-def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
+def _merge(gates: Sequence[LGate], max_diag_k: int = 6, merge_diag: bool = True) -> List[LGate]:
     out: List[Optional[LGate]] = []
     last: Dict[int, int] = {}
 
@@ -253,7 +254,7 @@ def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
                 u0, u1 = _mux_blocks(p)
                 out[j] = _simplify_mux(mux_gate(u0, X_MAT @ u1, t, c, name="fused"))
                 continue
-        if g.kind == DIAG:
+        if g.kind == DIAG and merge_diag:
             js = [last[b] for b in g.bits if b in last]
             if js:
                 j = max(js)
@@ -275,3 +276,141 @@ def _merge(gates: Sequence[LGate], max_diag_k: int = 6) -> List[LGate]:
         out.append(g)
         touch(g, len(out) - 1)
     return [x for x in out if x is not None]
+
+
+# ------------------------------------------------------------------------------------------
+# per-pass grouping (after scheduling)
+# ------------------------------------------------------------------------------------------
+def sink_diagonals(gates: Sequence[LGate], sched: List[tuple]) -> List[tuple]:
+    """Move every diagonal gate forward to just before the next non-diagonal gate that touches one of its bits (it
+    commutes with everything in between), so that it lands in the pass -- and next to the chain -- that can absorb
+    it.  The scheduler hands diagonal gates out as early as possible because they need no tile bit."""
+    flat = [(pi, gi) for pi, (_, chosen) in enumerate(sched) for gi in chosen]
+    new_lists: List[List[int]] = [[] for _ in sched]
+    waiting: List[int] = []          # diagonal gates (indices) not yet placed, in order
+    for pi, gi in flat:
+        g = gates[gi]
+        if g.kind == DIAG and not g.batched:
+            waiting.append(gi)
+            continue
+        if waiting:
+            keep = []
+            for d in waiting:
+                if gates[d].mask & g.mask:
+                    new_lists[pi].append(d)
+                else:
+                    keep.append(d)
+            waiting = keep
+        new_lists[pi].append(gi)
+    if waiting:                      # nothing touches them any more: the last pass takes them
+        new_lists[-1].extend(waiting)
+    return [(hb, lst) for (hb, _), lst in zip(sched, new_lists)]
+
+
+def _merge_diag_run(diags: List[LGate], max_k: int = 6) -> List[LGate]:
+    out: List[LGate] = []
+    for d in diags:
+        if out and not out[-1].batched and not d.batched and len(set(out[-1].bits) | set(d.bits)) <= max_k:
+            out[-1] = _merge_diag(out[-1], d)
+        else:
+            out.append(d)
+    return out
+
+
+def group_pass(gates: Sequence[LGate], local_bits: set, R: int = 3, R_rot: int = 4, E_max: int = 2) -> List[LGate]:
+    """Gates of ONE pass (execution order) -> chains + leftover gates.  1-qubit / MUX gates on tile-local bits become
+    CHAIN layers like in ``chain_fuse``; diagonal gates that sit right before a rotation-form chain (or between its
+    layers without touching an earlier layer's target) are multiplied into the chain's pre-diagonal table when their
+    bits are chain targets plus at most ``E_max`` other bits -- the ZZ terms of a Trotter / QAOA layer then cost no
+    sweep of their own.  Leftover diagonal gates are merged into tables of <= 6 bits."""
+    out: List[LGate] = []
+    pend: List[LGate] = []           # diagonal gates waiting right before the next non-diagonal gate
+    N = len(gates)
+
+    def layer_of(g: LGate):
+        lay = _as_layer(g)
+        if lay is not None and lay[0] not in local_bits:
+            return None
+        return lay
+
+    i = 0
+    while i < N:
+        g = gates[i]
+        if g.kind == DIAG and not g.batched and len(g.bits) > 1:
+            pend.append(g)
+            i += 1
+            continue
+        lay = layer_of(g)
+        if lay is None:
+            out.extend(_merge_diag_run(pend))
+            pend = []
+            out.append(g)
+            i += 1
+            continue
+        cur = [(lay, g)]
+        tmask = 1 << lay[0]
+        hoist: List[LGate] = []      # diagonal gates between layers that commute to the front of the chain
+        n_hoist_ok = 0
+        j = i + 1
+        end = j
+        while j < N:
+            h = gates[j]
+            if h.kind == DIAG and not h.batched and len(h.bits) > 1:
+                if h.mask & tmask:
+                    break
+                hoist.append(h)
+                j += 1
+                continue
+            l2 = layer_of(h)
+            if l2 is None:
+                break
+            t, c = l2[0], l2[1]
+            tgts = [l[0] for l, _ in cur]
+            c0 = cur[0][0][1]
+            if not (t not in tgts and t != c0 and (c is None or c == tgts[-1])):
+                break
+            if len(cur) >= R and not (len(cur) < R_rot and rot_plan([l[5] for l, _ in cur] + [l2[5]],
+                                                                     [l[4] for l, _ in cur] + [l2[4]], c0 is not None) is not None):
+                break
+            cur.append((l2, h))
+            tmask |= 1 << t
+            j += 1
+            end = j
+            n_hoist_ok = len(hoist)
+        hoist = hoist[:n_hoist_ok]   # diagonal gates after the last accepted layer stay where they are (i resumes at ``end``)
+        if len(cur) == 1:
+            # no chain: emit the pending diagonals, the hoisted ones never moved (n_hoist_ok == 0 here)
+            out.extend(_merge_diag_run(pend))
+            pend = []
+            out.append(g)
+            i += 1
+            continue
+        c0 = cur[0][0][1]
+        tags = [l[4] for l, _ in cur]
+        decs = [l[5] for l, _ in cur]
+        cands = pend + hoist
+        absorbed: List[LGate] = []
+        extras: List[int] = []
+        if cands and not any(gt.batched for _, gt in cur) and rot_plan(decs, tags, c0 is not None) is not None:
+            targets = [l[0] for l, _ in cur]
+            tset = set(targets)
+            need = [tuple(b for b in d.bits if b not in tset) for d in cands]
+            pool = sorted({b for nb in need for b in nb})
+            best = (-1, ())
+            combos = [()] + [(x,) for x in pool] + [(x, y) for ix, x in enumerate(pool) for y in pool[ix + 1:]]
+            for cb in combos:
+                if len(cb) > E_max:
+                    continue
+                cnt = sum(1 for nb in need if set(nb) <= set(cb))
+                if cnt > best[0] or (cnt == best[0] and len(cb) < len(best[1])):
+                    best = (cnt, cb)
+            extras = list(best[1])
+            absorbed = [d for d, nb in zip(cands, need) if set(nb) <= set(extras)]
+        ab_ids = {id(d) for d in absorbed}
+        out.extend(_merge_diag_run([d for d in cands if id(d) not in ab_ids]))
+        pend = []
+        out.append(chain_gate([(l[0], l[2], l[3]) for l, _ in cur], control_bit=c0, structure=tags, decs=decs,
+                              pre_diags=absorbed, extra_bits=extras, name="chain"))
+        i = end
+    out.extend(_merge_diag_run(pend))
+    return out

@@ -142,8 +142,8 @@ class LGate:
             self.local_mask = 0
         elif self.kind == MUX:
             self.local_mask = 1 << int(self.bits[0])
-        elif self.kind == CHAIN:   # bits = targets in layer order (+ outer control when pat_a == 1)
-            nt = len(self.bits) - (1 if self.pat_a else 0)
+        elif self.kind == CHAIN:   # bits = targets in layer order (+ outer control when pat_a & 1) (+ pat_a >> 1 extra table bits)
+            nt = len(self.bits) - (self.pat_a & 1) - (self.pat_a >> 1)
             self.local_mask = 0
             for b in self.bits[:nt]:
                 self.local_mask |= 1 << int(b)
@@ -260,13 +260,16 @@ def rot_plan(decs: Sequence[Dict[int, Any]], tags: Sequence[int], has_control: b
 
 
 def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit: Optional[int] = None,
-               structure: Optional[Sequence[int]] = None, decs: Optional[Sequence[Dict[int, Any]]] = None, **kw: Any) -> LGate:
+               structure: Optional[Sequence[int]] = None, decs: Optional[Sequence[Dict[int, Any]]] = None,
+               pre_diags: Sequence["LGate"] = (), extra_bits: Sequence[int] = (), **kw: Any) -> LGate:
     """R = 2..4 one-qubit layers [(target_bit, M_sel0, M_sel1), ...]: layer 0 is selected by
     ``control_bit`` (None: M_sel0 is used), layer i > 0 by the value of layer i-1's target bit.
     ``structure``: per layer MUX_GENERAL / MUX_XU / LAYER_PLAIN.  When every layer is plain or a gate followed by a
     fused cx, and all selector-0 matrices factor as rotation x diagonal of one type (``rot_decompose``), the gate is
     emitted in rotation form: data = [P (2^R entries), (a_i + i r_i) per layer], pat_b = 4 + 2*type + muxed
-    (R = 4 exists in rotation form only)."""
+    (R = 4 exists in rotation form only).  ``pre_diags``: diagonal gates that act right BEFORE the chain, on chain
+    targets plus the ``extra_bits`` (<= 2): they are multiplied into the table, which then has 2^(R+E) entries
+    (index = register index + extras << R); the extras are appended to ``bits`` and counted in pat_a >> 1."""
     assert 2 <= len(layers) <= 4
     R = len(layers)
     bits = [int(t) for t, _, _ in layers]
@@ -277,24 +280,50 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
         decs = [rot_decompose(a) for _, a, _ in layers]
     rot = rot_plan(decs, structure, control_bit is not None) if structure is not None else None
     assert R <= 3 or rot is not None, "4-layer chains need the rotation form"
+    assert not pre_diags or (rot is not None and B == 1), "diagonal gates can only be absorbed by unbatched rotation-form chains"
+    E = len(extra_bits)
+    assert E <= 2
+    unit = False
     if rot is not None:
         typ, muxed, dec = rot
-        P = np.ones((B, 1 << R), dtype=C128)
-        for s in range(1 << R):
-            for i in range(R):
-                P[:, s] *= dec[i][3] if (s >> i) & 1 else dec[i][2]
-        coef = np.stack([np.broadcast_to(dec[i][0] + 1j * dec[i][1], (B,)) for i in range(R)], axis=1)
-        data = np.ascontiguousarray(np.concatenate([P, coef], axis=1))
-        kw["pat_b"] = 4 + 2 * typ + muxed
+        if B == 1:   # plain Python complex arithmetic: the planner builds one of these per chain
+            tab = [1.0 + 0.0j]
+            for i in range(R):   # register index bit i <-> layer i
+                d0, d1 = complex(dec[i][2][0]), complex(dec[i][3][0])
+                tab = [p * d0 for p in tab] + [p * d1 for p in tab]
+            if E or pre_diags:
+                tab = tab * (1 << E)                      # index = register index + (extras << R)
+                targets = bits[:R]
+                for d in pre_diags:
+                    src = [("t", targets.index(b)) if b in targets else ("x", list(extra_bits).index(b)) for b in d.bits]
+                    for idx in range(len(tab)):
+                        sv, xv = idx & ((1 << R) - 1), idx >> R
+                        di = 0
+                        for j, (kind, pos) in enumerate(src):
+                            di |= (((sv >> pos) if kind == "t" else (xv >> pos)) & 1) << j
+                        tab[idx] *= complex(d.data[di])
+            unit = all(t == 1.0 for t in tab)
+            tab += [complex(float(dec[i][0][0]), float(dec[i][1][0])) for i in range(R)]
+            data = np.array(tab, dtype=C128).reshape(1, -1)
+        else:
+            P = np.ones((B, 1 << R), dtype=C128)
+            for s in range(1 << R):
+                for i in range(R):
+                    P[:, s] *= dec[i][3] if (s >> i) & 1 else dec[i][2]
+            coef = np.stack([np.broadcast_to(dec[i][0] + 1j * dec[i][1], (B,)) for i in range(R)], axis=1)
+            data = np.ascontiguousarray(np.concatenate([P, coef], axis=1))
+        kw["pat_b"] = (4 + 2 * typ + muxed) | (E << 4) | (128 if unit else 0)
     else:
         blocks = []
         for _, a, b in layers:
             for m in (a, b):
                 blocks.append(np.broadcast_to(np.asarray(m, dtype=C128).reshape(-1, 4), (B, 4)))
         data = np.ascontiguousarray(np.concatenate(blocks, axis=1))
+    bits += [int(b) for b in extra_bits]
+    pat_a = (1 if control_bit is not None else 0) | (E << 1)
     if B == 1:
-        return LGate(CHAIN, tuple(bits), data.reshape(-1), pat_a=1 if control_bit is not None else 0, **kw)
-    return LGate(CHAIN, tuple(bits), data, pat_a=1 if control_bit is not None else 0, batched=True, **kw)
+        return LGate(CHAIN, tuple(bits), data.reshape(-1), pat_a=pat_a, **kw)
+    return LGate(CHAIN, tuple(bits), data, pat_a=pat_a, batched=True, **kw)
 
 
 def classify_unitary(mat: np.ndarray, qubits: Sequence[int], n: int) -> LGate:

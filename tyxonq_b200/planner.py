@@ -185,11 +185,12 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
     if chain:
         # group the 1-qubit / MUX gates of every pass into CHAIN gates now that their targets are known to be
         # tile-local together (``order`` then no longer maps compiled gates to input gates)
-        from .fuse import chain_fuse
+        from .fuse import group_pass, sink_diagonals
+        sched = sink_diagonals(gates, sched)
         grouped: List[LGate] = []
         sched2 = []
         for hb, chosen in sched:
-            sub = chain_fuse([gates[i] for i in chosen], local_bits=set(range(tile.L)) | set(int(p) for p in hb))
+            sub = group_pass([gates[i] for i in chosen], set(range(tile.L)) | set(int(p) for p in hb))
             sched2.append((hb, list(range(len(grouped), len(grouped) + len(sub)))))
             grouped += sub
         gates, sched = grouped, sched2
@@ -234,14 +235,19 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
                 e["bits"][0] = local_of[g.bits[0]]
                 e["bits"][1] = enc(g.bits[1])
             elif g.kind == CHAIN:
-                r = len(g.bits) - (1 if g.pat_a else 0)
+                has_c, E = g.pat_a & 1, g.pat_a >> 1
+                r = len(g.bits) - has_c - E
                 e["k"] = r
                 loc = [local_of[b] for b in g.bits[:r]]
                 for j, b in enumerate(loc):
                     e["bits"][j] = b
-                ctrl = enc(g.bits[r]) if g.pat_a else 127
+                ctrl = enc(g.bits[r]) if has_c else 127
                 e["bits"][r] = ctrl
-                e["off_a"] = g.pat_b          # 0 = two matrices per layer; 4..7 = rotation form (tqb_core.cuh gate_chain_rot)
+                for j in range(2):      # extra index bits of the pre-diagonal table (rotation form only)
+                    if r + 1 + j < 8:
+                        e["bits"][r + 1 + j] = enc(g.bits[r + has_c + j]) if j < E else 127
+                e["off_a"] = g.pat_b & 15          # 0 = two matrices per layer; 4..7 = rotation form (tqb_core.cuh gate_chain_rot)
+                e["off_b"] = (E & 3) | (g.pat_b & 128)
                 zs = sorted(loc + ([ctrl] if ctrl < 64 else []))
                 for j, b in enumerate(zs):
                     e["sbits"][j] = b
