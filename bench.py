@@ -202,7 +202,9 @@ def own_arm(args) -> None:
                 pass_ev.append((e0, e1))
             return P.expect_z_bits(state)
 
-        info = {"passes": prog.n_passes, "gates_per_pass": n_gates / prog.n_passes, "fused_gate_sweeps": len(lg), "plan_ms": plan_ms,
+        from tyxonq_b200.planner import fp_ops_per_amplitude
+        info = {"passes": prog.n_passes, "gates_per_pass": n_gates / prog.n_passes, "fused_gate_sweeps": len(prog.gates), "plan_ms": plan_ms,
+                "fp_ops_per_amplitude": fp_ops_per_amplitude(prog),
                 "tile_m": prog.tile.m, "tile_L": prog.tile.L, "threads": prog.tile.threads, "swaps": 0}
         n_local = n
 
@@ -248,6 +250,16 @@ def own_arm(args) -> None:
     roof = {"bound": "hbm", "kernel": "tile_pass_tma_kernel<double,2,2>" if args.dtype == "complex128" else "tile_pass_tma_kernel<float,2,2>", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"], "traffic": None,
             "alg_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms, "pass_share_of_step": pass_ms / ms_per_step}
+    if "fp_ops_per_amplitude" in info:
+        # the arithmetic side: the fused passes carry ~44 gates each, so the pass is bound by its in-tile compute phase.
+        # Peak = measured DFMA / FFMA lane rate of this GPU (tools/micro/fp64_peak.cu: 32.6 / 69.3 TFLOP/s = 16.3 / 34.6 T instr/s).
+        lane_ops = info["fp_ops_per_amplitude"] * (1 << n_local)
+        peak_t = 16.3 if args.dtype == "complex128" else 34.6
+        ach_t = lane_ops / (pass_ms * 1e-3) / 1e12
+        roof["compute"] = {"bound": "fp64 pipe" if args.dtype == "complex128" else "fp32 pipe", "achieved": ach_t, "peak": peak_t,
+                           "unit": "T lane-instr/s (mul / add / fma)", "frac": ach_t / peak_t,
+                           "fp_instr_per_amplitude_per_step": info["fp_ops_per_amplitude"],
+                           "peak_source": "tools/micro/fp64_peak.cu on this pool's B200 (register-resident FMA chains, 64 warps/SM)"}
     prof = ROOT / "profiles" / "r01_tile_pass_traffic.json"
     if prof.exists():
         try:

@@ -284,3 +284,29 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
         ps["mat_count"] = cnt if (not any_batched and cnt <= 4096) else 0   # staged in shared memory
     flat = np.concatenate(mats) if mats else np.zeros(0, dtype=C128)
     return Program(n=n, passes=passes, gates=garr, mats=flat, n_gates_in=len(gates), tile=tile, order=order)
+
+
+def fp_ops_per_amplitude(prog: Program) -> float:
+    """Floating-point pipe instructions (multiply, add or fused multiply-add, one lane each) the tile kernel issues per
+    amplitude over the whole program: the arithmetic side of the roofline (bench.py reports it against the measured
+    FP64 / FP32 instruction rate).  DENSE k: 2^k complex MACs per amplitude = 4 * 2^k; DIAG / MUX-selected 2x2 /
+    general CHAIN layer: 4 / 8 / 8; rotation-form CHAIN: 4 per layer + 4 for the pre-diagonal table unless it is all
+    ones; PAIR touches 2 of 2^k patterns with a 2x2; SWAP moves data only."""
+    from . import _lib
+    total = 0.0
+    for g in prog.gates:
+        kind, k = int(g["kind"]), int(g["k"])
+        if kind == _lib.GATE_DENSE:
+            total += 4.0 * (1 << k)
+        elif kind == _lib.GATE_DIAG:
+            total += 4.0
+        elif kind == _lib.GATE_PAIR:
+            total += 8.0 * 2.0 / (1 << k)
+        elif kind == _lib.GATE_MUX:
+            total += 8.0
+        elif kind == _lib.GATE_CHAIN:
+            if int(g["off_a"]) >= 4:
+                total += 4.0 * k + (0.0 if int(g["off_b"]) & 128 else 4.0)
+            else:
+                total += 8.0 * k
+    return total
