@@ -435,8 +435,14 @@ TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, 
 // as one table P over the 2^R register indices, and M commutes with the fused cx (X.M = M.X for TYPE 0,
 // X.M = M^T.X for TYPE 1), which therefore is an input rename.  Per amplitude: one complex multiply by P and
 // R real rotations = 4 + 4R multiply-adds instead of 8R, and 2^R + R matrix entries instead of 8R.
-// Data: M[0 .. 2^R) = P, M[2^R + i] = (a_i, r_i).  MUXED: layers i > 0 are selected by bit bits[i-1] (cx after
-// the gate); layer 0 by the outer control when bits[R] != 127 (run-time: loads and P index flip with its value).
+// Layers i > 0 run in SCALED form: the larger of (a_i, r_i) is divided out -- M_i = a_i [[1, i t], [i t, 1]] with
+// t = r_i / a_i (mode 0, |a_i| >= |r_i|) or M_i = r_i [[c, i], [i, c]] with c = a_i / r_i (mode 1) -- and the host
+// multiplies the product of those real factors into layer 0's pair (a_0, r_0): one fused multiply-add per real
+// component instead of a multiply and a multiply-add, 4 + 4 + 2(R-1) instructions per amplitude instead of 4 + 4R.
+// Data: M[0 .. 2^R) = P (followed by a copy with index bit 0 flipped when the gate has an outer control),
+// then (S a_0, S r_0) and (t_i or c_i, mode_i) for i > 0.  MUXED: layers i > 0
+// are selected by bit bits[i-1] (cx after the gate); layer 0 by the outer control when bits[R] != 127 (run-time:
+// loads and P index flip with its value).
 template <typename T, int R, int I, int TYPE, bool MUXED>
 TQB_HD void rot_layer(cplx<T> (&v)[1 << R], const T a, const T r) {
 #pragma unroll
@@ -463,84 +469,205 @@ TQB_HD void rot_layer(cplx<T> (&v)[1 << R], const T a, const T r) {
   }
 }
 
-template <typename T, int R, int TYPE, bool MUXED>
-TQB_HD void gate_chain_rot(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
-  uint32_t tb[R];
+// scaled form of layer I > 0: k = t (inv false) or c (inv true); the branch is uniform over the tile
+template <typename T, int R, int I, int TYPE, bool MUXED>
+TQB_HD void rot_layer_scaled(cplx<T> (&v)[1 << R], const T k, const bool inv) {
+  if (!inv) {
 #pragma unroll
-  for (int i = 0; i < R; ++i) tb[i] = (uint32_t)g.bits[i];
-  const uint32_t cb = (uint32_t)(uint8_t)g.bits[R];
-  const bool ctrl_local = cb < 64u;
-  uint32_t cv_fixed = 0;
-  if (!ctrl_local && cb != 127u) cv_fixed = (uint32_t)((gbase >> (cb & 63u)) & 1ull);
-  constexpr int NZ = R + 1;
-  uint32_t sb[NZ];
+    for (int s = 0; s < (1 << R); ++s) {
+      if (s & (1 << I)) continue;
+      const bool sel = MUXED && ((s >> (I > 0 ? I - 1 : 0)) & 1);
+      const int lo = s, hi = s | (1 << I);
+      const cplx<T> x0 = v[sel ? hi : lo], x1 = v[sel ? lo : hi];
+      cplx<T> y0, y1;
+      if (TYPE == 0) {
+        y0.x = x0.x - k * x1.y;
+        y0.y = x0.y + k * x1.x;
+        y1.x = x1.x - k * x0.y;
+        y1.y = x1.y + k * x0.x;
+      } else if (sel) {
+        y0.x = x0.x + k * x1.x;
+        y0.y = x0.y + k * x1.y;
+        y1.x = x1.x - k * x0.x;
+        y1.y = x1.y - k * x0.y;
+      } else {
+        y0.x = x0.x - k * x1.x;
+        y0.y = x0.y - k * x1.y;
+        y1.x = x1.x + k * x0.x;
+        y1.y = x1.y + k * x0.y;
+      }
+      v[lo] = y0;
+      v[hi] = y1;
+    }
+  } else {
 #pragma unroll
-  for (int j = 0; j < NZ; ++j) sb[j] = (uint32_t)g.sbits[j];
-  const int nz = ctrl_local ? R + 1 : R;
-  const uint32_t free_bits = (uint32_t)(m - nz);
-  const uint32_t ngroups = 1u << (m - R);
-  // g.off_b: bits 0-1 = E, the number of extra index bits of the pre-diagonal table (bits[R+1 ..]: absorbed
-  // diagonal gates may reach beyond the targets), bit 7 = the table is all ones (plain rotations: skip the multiply)
-  const uint32_t E = g.off_b & 3u;
-  const bool unit_p = (g.off_b & 128u) != 0u;
-  uint32_t xb[2];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) xb[j] = (uint32_t)(uint8_t)g.bits[R + 1 + j];
-  T a[R], r[R];
-#pragma unroll
-  for (int i = 0; i < R; ++i) {
-    const cplx<T> c = M[((size_t)1 << (R + E)) + i];
-    a[i] = c.x;
-    r[i] = c.y;
+    for (int s = 0; s < (1 << R); ++s) {
+      if (s & (1 << I)) continue;
+      const bool sel = MUXED && ((s >> (I > 0 ? I - 1 : 0)) & 1);
+      const int lo = s, hi = s | (1 << I);
+      const cplx<T> x0 = v[sel ? hi : lo], x1 = v[sel ? lo : hi];
+      cplx<T> y0, y1;
+      if (TYPE == 0) {
+        y0.x = k * x0.x - x1.y;
+        y0.y = k * x0.y + x1.x;
+        y1.x = k * x1.x - x0.y;
+        y1.y = k * x1.y + x0.x;
+      } else if (sel) {
+        y0.x = k * x0.x + x1.x;
+        y0.y = k * x0.y + x1.y;
+        y1.x = k * x1.x - x0.x;
+        y1.y = k * x1.y - x0.y;
+      } else {
+        y0.x = k * x0.x - x1.x;
+        y0.y = k * x0.y - x1.y;
+        y1.x = k * x1.x + x0.x;
+        y1.y = k * x1.y + x0.y;
+      }
+      v[lo] = y0;
+      v[hi] = y1;
+    }
   }
-  auto offset = [&](uint32_t base, int s) {
-    uint32_t o = base;
+}
+
+// index of the lowest set bit of s in 1..15 (s is a compile-time constant after unrolling)
+#define TQB_LOW_BIT(s) (((s) & 1) ? 0 : ((s) & 2) ? 1 : ((s) & 4) ? 2 : 3)
+
+// A rotation-form CHAIN descriptor decoded for the sweep (48 bytes, three 16-byte loads): the lean kernel decodes
+// every gate of the pass ONCE per CTA into shared memory (tile_pass_lean_kernel), the general kernel decodes in place.
+//   flags: bit 0 control is tile-local, bit 1 has a control, bit 2 table is all ones, bits 3-4 E, bit 5 MUXED,
+//          bit 6 TYPE, bits 8-13 control position (tile-local bit, or index bit outside the tile), bits 16-20 number
+//          of free bits (m - targets - local control), bits 24-28 m, bits 29-30 R - 1
+//   d[i]:  byte stride of target i;  lm[j]: (1 << p_j) - 1 for the ascending positions p_j where a zero bit is
+//          inserted into the group counter (targets + local control), all ones beyond the last one
+struct alignas(16) RotDesc {
+  int32_t d[4];
+  uint32_t lm[5];
+  uint32_t flags;
+  uint32_t xb;   // extra table bits: xb0 | xb1 << 8 (encoding of tqb_gate.bits: < 64 tile-local, 64 + p outside)
+  uint32_t mat;  // tqb_gate.mat_off
+};
+
+template <typename T>
+TQB_HD RotDesc rot_decode(const tqb_gate &g, int m) {
+  RotDesc r;
+  const int R = g.k;
+  const uint32_t cb = (uint32_t)(uint8_t)g.bits[R];
+  const bool ctrl_local = cb < 64u, has_ctrl = cb != 127u;
+  const int nz = ctrl_local ? R + 1 : R;
 #pragma unroll
-    for (int i = 0; i < R; ++i)
-      if (s & (1 << i)) o |= 1u << tb[i];
-    return o;
-  };
-  auto locate = [&](uint32_t gi, uint32_t &base, uint32_t &cv) {
-    uint32_t lo = gi;
-    cv = cv_fixed;
+  for (int i = 0; i < 4; ++i) r.d[i] = i < R ? (int32_t)(sizeof(cplx<T>) << (uint32_t)g.bits[i]) : 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) r.lm[j] = j < nz ? (1u << (uint32_t)g.sbits[j]) - 1u : 0xffffffffu;
+  r.flags = (ctrl_local ? 1u : 0u) | (has_ctrl ? 2u : 0u) | ((g.off_b & 128u) ? 4u : 0u) | ((g.off_b & 3u) << 3) |
+            ((g.off_a & 3u) << 5) | ((cb & 63u) << 8) | ((uint32_t)(m - nz) << 16) | ((uint32_t)m << 24) |
+            ((uint32_t)(R - 1) << 29);
+  r.xb = (uint32_t)(uint8_t)g.bits[R + 1] | ((uint32_t)(uint8_t)g.bits[R + 2] << 8);
+  r.mat = g.mat_off;
+  return r;
+}
+
+template <typename T, int R, int TYPE, bool MUXED>
+TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, const cplx<T> *M, int tid, int nthreads) {
+  constexpr int D = 1 << R;
+  constexpr int NZ = R + 1;
+  const uint32_t f = rd.flags;
+  const bool ctrl_local = (f & 1u) != 0u, has_ctrl = (f & 2u) != 0u, unit_p = (f & 4u) != 0u;
+  const uint32_t E = (f >> 3) & 3u;
+  const uint32_t cb = (f >> 8) & 63u;
+  const uint32_t free_bits = (f >> 16) & 31u;
+  const uint32_t ngroups = 1u << (((f >> 24) & 31u) - (uint32_t)R);
+  uint32_t cv_fixed = 0;
+  if (!ctrl_local && has_ctrl) cv_fixed = (uint32_t)((gbase >> cb) & 1ull);
+  uint32_t lm[NZ];
+#pragma unroll
+  for (int j = 0; j < NZ; ++j) lm[j] = rd.lm[j];
+  int32_t d[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) d[i] = rd.d[i] & ~(int32_t)(sizeof(cplx<T>) - 1);  // (a no-op that tells the compiler the accesses stay aligned)
+  // table: 2^(R+E) entries, index = register index + (extras << R); a gate with a control carries a second copy
+  // with register-index bit 0 flipped (control = 1: the fused cx renames the inputs of layer 0), so that the table
+  // is read at compile-time offsets from a per-thread base.  The layer coefficients follow the table(s).
+  const uint32_t tab = 1u << (R + E);
+  const cplx<T> *coef = M + (has_ctrl ? 2u * tab : tab);
+  const T a0 = coef[0].x, r0 = coef[0].y;
+  T kk[R];
+  bool inv[R];
+#pragma unroll
+  for (int i = 1; i < R; ++i) {
+    const cplx<T> c = coef[i];
+    kk[i] = c.x;
+    inv[i] = c.y != (T)0;
+  }
+  kk[0] = 0;
+  inv[0] = false;
+  char *const tbytes = reinterpret_cast<char *>(tile);
+  // (two groups per iteration was measured slower here as well: profiles/r01_tile_sweep.md)
+  for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
+    uint32_t base = gi, cv = cv_fixed;
     if (ctrl_local) {
       cv = gi >> free_bits;
-      lo = gi & ((1u << free_bits) - 1u);
+      base = gi & ((1u << free_bits) - 1u);
     }
-    base = lo;
 #pragma unroll
-    for (int j = 0; j < NZ; ++j)
-      if (j < nz) base = ((base >> sb[j]) << (sb[j] + 1u)) | (base & ((1u << sb[j]) - 1u));
+    for (int j = 0; j < NZ; ++j) base += base & ~lm[j];  // insert a zero bit at position p_j (no-op when lm is all ones)
     if (ctrl_local) base |= cv << cb;
-  };
-  // (two groups per iteration was measured slower here as well: profiles/r01_tile_sweep.md)
-  uint32_t gi = tid;
-  for (; gi < ngroups; gi += nthreads) {
-    uint32_t base, cv;
-    locate(gi, base, cv);
-    const uint32_t flip = cv << tb[0];
-    const int icv = (int)cv;  // register s holds input amplitude s ^ cv (cv toggles bit 0 = layer 0's bit)
-    cplx<T> v[1 << R];
+    // register s holds input amplitude s ^ cv (cv toggles bit 0 = layer 0's bit): start at the flipped element and
+    // step layer 0's stride backwards
+    char *q[D];
+    q[0] = tbytes + (size_t)base * sizeof(cplx<T>) + (cv ? d[0] : 0);
+    const int32_t d0 = (cv ? -d[0] : d[0]) & ~(int32_t)(sizeof(cplx<T>) - 1);
+#pragma unroll
+    for (int s = 1; s < D; ++s) q[s] = q[s & (s - 1)] + (TQB_LOW_BIT(s) == 0 ? d0 : d[TQB_LOW_BIT(s) < R ? TQB_LOW_BIT(s) : 0]);
+    cplx<T> v[D];
     if (unit_p) {
 #pragma unroll
-      for (int s = 0; s < (1 << R); ++s) v[s] = tile[offset(base, s) ^ flip];
+      for (int s = 0; s < D; ++s) v[s] = *reinterpret_cast<const cplx<T> *>(q[s]);
     } else {
       uint32_t x = 0;
 #pragma unroll
       for (int j = 0; j < 2; ++j)
-        if ((uint32_t)j < E)
-          x |= (xb[j] < 64u ? ((base >> xb[j]) & 1u) : (uint32_t)((gbase >> (xb[j] & 63u)) & 1ull)) << j;
-      const cplx<T> *P = M + ((size_t)x << R);
+        if ((uint32_t)j < E) {
+          const uint32_t xbj = (rd.xb >> (8 * j)) & 0xffu;
+          x |= (xbj < 64u ? ((base >> xbj) & 1u) : (uint32_t)((gbase >> (xbj & 63u)) & 1ull)) << j;
+        }
+      const cplx<T> *P = M + ((size_t)x << R) + (cv ? tab : 0u);
 #pragma unroll
-      for (int s = 0; s < (1 << R); ++s) v[s] = cmul(tile[offset(base, s) ^ flip], P[(s & 1) ? s - icv : s + icv]);
+      for (int s = 0; s < D; ++s) v[s] = cmul(*reinterpret_cast<const cplx<T> *>(q[s]), P[s]);
     }
-    rot_layer<T, R, 0, TYPE, false>(v, a[0], (TYPE == 1 && cv) ? -r[0] : r[0]);
-    rot_layer<T, R, 1, TYPE, MUXED>(v, a[1], r[1]);
-    if (R > 2) rot_layer<T, R, (R > 2 ? 2 : 1), TYPE, MUXED>(v, a[R > 2 ? 2 : 1], r[R > 2 ? 2 : 1]);
-    if (R > 3) rot_layer<T, R, (R > 3 ? 3 : 1), TYPE, MUXED>(v, a[R > 3 ? 3 : 1], r[R > 3 ? 3 : 1]);
+    rot_layer<T, R, 0, TYPE, false>(v, a0, (TYPE == 1 && cv) ? -r0 : r0);
+    rot_layer_scaled<T, R, 1, TYPE, MUXED>(v, kk[1], inv[1]);
+    if (R > 2) rot_layer_scaled<T, R, (R > 2 ? 2 : 1), TYPE, MUXED>(v, kk[R > 2 ? 2 : 1], inv[R > 2 ? 2 : 1]);
+    if (R > 3) rot_layer_scaled<T, R, (R > 3 ? 3 : 1), TYPE, MUXED>(v, kk[R > 3 ? 3 : 1], inv[R > 3 ? 3 : 1]);
+    // outputs are not renamed: register s goes to element s of the group
+    char *w[D];
+    w[0] = tbytes + (size_t)base * sizeof(cplx<T>);
 #pragma unroll
-    for (int s = 0; s < (1 << R); ++s) tile[offset(base, s)] = v[s];
+    for (int s = 1; s < D; ++s) w[s] = w[s & (s - 1)] + d[TQB_LOW_BIT(s) < R ? TQB_LOW_BIT(s) : 0];
+#pragma unroll
+    for (int s = 0; s < D; ++s) *reinterpret_cast<cplx<T> *>(w[s]) = v[s];
   }
+}
+
+// dispatch on (R, TYPE, MUXED) of a decoded rotation-form chain; M = base of the matrix buffer
+template <typename T>
+TQB_HD void chain_rot_dispatch(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, const cplx<T> *mats, int tid, int nthreads) {
+  const cplx<T> *M = mats + rd.mat;
+  switch ((rd.flags >> 5) & 3u | ((rd.flags >> 29) & 3u) << 2) {   // (off_a & 3) = 2 * TYPE + MUXED, R - 1
+#define TQB_ROT(R) \
+    case ((R - 1) << 2) | 0: chain_rot_sweep<T, R, 0, false>(tile, gbase, rd, M, tid, nthreads); break; \
+    case ((R - 1) << 2) | 1: chain_rot_sweep<T, R, 0, true>(tile, gbase, rd, M, tid, nthreads); break;  \
+    case ((R - 1) << 2) | 2: chain_rot_sweep<T, R, 1, false>(tile, gbase, rd, M, tid, nthreads); break; \
+    case ((R - 1) << 2) | 3: chain_rot_sweep<T, R, 1, true>(tile, gbase, rd, M, tid, nthreads); break;
+    TQB_ROT(2) TQB_ROT(3) TQB_ROT(4)
+#undef TQB_ROT
+    default: break;
+  }
+}
+
+template <typename T, int R, int TYPE, bool MUXED>
+TQB_HD void gate_chain_rot(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+  RotDesc rd = rot_decode<T>(g, m);
+  chain_rot_sweep<T, R, TYPE, MUXED>(tile, gbase, rd, M, tid, nthreads);
 }
 
 // R = 4 exists in rotation form only (16 amplitudes + 4 coefficient pairs fit the register budget; the general
@@ -593,6 +720,35 @@ TQB_HD void tile_apply_gate(cplx<T> *tile, const TileGeom &geo, const uint64_t *
       if (g.k == 2) gate_chain_any<T, 2>(tile, geo.m, gbase, g, mat, tid, nthreads);
       else if (g.k == 3) gate_chain_any<T, 3>(tile, geo.m, gbase, g, mat, tid, nthreads);
       else if (g.k == 4) gate_chain4<T>(tile, geo.m, gbase, g, mat, tid, nthreads);
+      break;
+    default: break;
+  }
+}
+
+// Lean dispatch: passes that hold only 1-qubit-layer gates (DENSE k = 1, DIAG, MUX, rotation-form CHAIN) -- every pass
+// of a hardware-efficient / QAOA / Trotter circuit after fusion.  The kernel built on it carries none of the dense
+// k >= 2 / PAIR / SWAP / general-CHAIN code, which is what keeps its loop state in registers.
+template <typename T, bool WITH_ROT = true>   // WITH_ROT = false: the caller handles rotation-form chains itself
+TQB_HD void tile_apply_gate_lean(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *mats, int tid,
+                                 int nthreads) {
+  const cplx<T> *mat = mats + g.mat_off;
+  switch (g.kind) {
+    case TQB_GATE_DENSE:
+      mux_sweep<T>(tile, 1u << (m - 1), (uint32_t)g.bits[0], 0, false, 0, 1u << g.bits[0], mat, tid, nthreads);
+      break;
+    case TQB_GATE_DIAG: gate_diag<T>(tile, m, gbase, g, mat, tid, nthreads); break;
+    case TQB_GATE_MUX: gate_mux<T>(tile, m, gbase, g, mat, tid, nthreads); break;
+    case TQB_GATE_CHAIN:
+      if (g.off_a >= 4u) {
+        if (WITH_ROT) {
+          const RotDesc rd = rot_decode<T>(g, m);
+          chain_rot_dispatch<T>(tile, gbase, rd, mats, tid, nthreads);
+        }
+      } else if (g.k == 2) {
+        gate_chain<T, 2>(tile, m, gbase, g, mat, tid, nthreads);
+      } else if (g.k == 3) {
+        gate_chain<T, 3>(tile, m, gbase, g, mat, tid, nthreads);
+      }
       break;
     default: break;
   }

@@ -245,6 +245,136 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
   }
 }
 
+// ---- lean variant ---------------------------------------------------------------------------------
+// Same producer / consumer structure as tile_pass_tma_kernel for passes that hold only 1-qubit-layer gates (DENSE
+// k = 1, DIAG, MUX, rotation-form CHAIN; matrices staged in shared memory): every pass of a hardware-efficient, QAOA
+// or Trotter circuit.  The general kernel inlines all gate kinds twice (staged / global matrices), needs its full
+// register budget for that and keeps the tile / gate loop state in LOCAL memory (ncu, profiles/r01_tile_sweep.md:
+// 27 % of the stall samples were long-scoreboard waits on those reloads); here the body is small enough for the
+// loop state to stay in registers, descriptors are read from a 16-byte aligned region and the tile base is
+// computed from a register-packed copy of hb[].
+// layout: NB tiles | 8 mbarrier slots | descriptors | staged matrices | run-offset table (producer only)
+template <typename T, int NB>
+__global__ void __launch_bounds__(160, 3)
+tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
+                      const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats,
+                      const int dbg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NB * tile_bytes);
+  uint64_t *done = full + 4;
+  tqb_gate *sg = reinterpret_cast<tqb_gate *>(full + 8);
+  RotDesc *srd = reinterpret_cast<RotDesc *>(sg + n_gates);  // decoded rotation-form chains (both 48 bytes per gate)
+  cplx<T> *smats = reinterpret_cast<cplx<T> *>(srd + n_gates);
+  uint64_t *roff = reinterpret_cast<uint64_t *>(smats + ((geo.mat_count + 1) & ~1));
+
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int ncons = nthreads - 32;
+  const int lane = tid & 31;
+  const bool producer = tid >= ncons;
+  for (uint32_t j = tid; j < (1u << geo.h); j += nthreads) roff[j] = run_offset(geo, j);
+  for (int i = tid; i < geo.mat_count; i += nthreads) smats[i] = mats[geo.mat_begin + i];
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(gates);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
+    const int nw = n_gates * (int)(sizeof(tqb_gate) / 4);
+    for (int i = tid; i < nw; i += nthreads) dst[i] = src[i];
+  }
+  for (int i = tid; i < n_gates; i += nthreads)
+    if (gates[i].kind == TQB_GATE_CHAIN && gates[i].off_a >= 4u) srd[i] = rot_decode<T>(gates[i], geo.m);
+  if (tid == 0) {
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&done[i], (uint32_t)ncons);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int tb = geo.n - geo.m;
+  const unsigned long long total = (unsigned long long)batch << tb;
+  const unsigned long long first = blockIdx.x, stride = gridDim.x;
+  const unsigned long long count = first < total ? (total - first + stride - 1) / stride : 0;
+  const uint32_t nruns = 1u << geo.h;
+  const uint32_t run_elems = 1u << geo.L;
+  const uint32_t run_bytes = (uint32_t)(sizeof(cplx<T>) << geo.L);
+  // hb[] packed into two registers (a run-time index into the by-value parameter would send it to local memory)
+  uint64_t hb_lo = 0, hb_hi = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hb_lo |= (uint64_t)(uint8_t)geo.hb[j] << (8 * j);
+    hb_hi |= (uint64_t)(uint8_t)geo.hb[8 + j] << (8 * j);
+  }
+  auto tile_index = [&](unsigned long long tt) -> uint64_t {  // element index of tile tt's first amplitude (batch included)
+    uint64_t x = (tt & ((1ull << tb) - 1ull)) << geo.L;
+    for (int j = 0; j < geo.h; ++j) {
+      const uint32_t p = (uint32_t)((j < 8 ? hb_lo >> (8 * j) : hb_hi >> (8 * (j - 8))) & 0xffu);
+      x = ((x >> p) << (p + 1u)) | (x & ((1ull << p) - 1ull));
+    }
+    return x;
+  };
+
+  if (producer) {
+    auto tile_ptr = [&](unsigned long long it) -> cplx<T> * {
+      const unsigned long long tt = first + it * stride;
+      return state + ((tt >> tb) << geo.n) + tile_index(tt);
+    };
+    auto issue_load = [&](unsigned long long it) {
+      const int b = (int)(it % NB);
+      cplx<T> *dst = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
+      const cplx<T> *src = tile_ptr(it);
+      if (dbg & 2) {
+        if (lane == 0) mbar_arrive(&full[b]);
+        return;
+      }
+      if (lane == 0) mbar_expect_tx(&full[b], (uint32_t)tile_bytes);
+      __syncwarp();
+      for (uint32_t j = lane; j < nruns; j += 32) bulk_load(dst + (size_t)j * run_elems, src + roff[j], run_bytes, &full[b]);
+    };
+    for (unsigned long long it = 0; it < (unsigned long long)(NB - 1) && it < count; ++it) issue_load(it);
+    for (unsigned long long it = 0; it < count; ++it) {
+      const int b = (int)(it % NB);
+      if (it + NB - 1 < count) {
+        bulk_wait_read<0>();
+        __syncwarp();
+        issue_load(it + NB - 1);
+      }
+      mbar_wait(&done[b], (uint32_t)((it / NB) & 1));
+      cplx<T> *dstg = tile_ptr(it);
+      const cplx<T> *srcs = reinterpret_cast<const cplx<T> *>(smem_raw + b * tile_bytes);
+      if (!(dbg & 4))
+        for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], srcs + (size_t)j * run_elems, run_bytes);
+      bulk_commit();
+    }
+    bulk_wait_all0();
+    return;
+  }
+
+  const cplx<T> *sm = smats - geo.mat_begin;
+  const int m = geo.m;
+#pragma unroll 1
+  for (unsigned long long it = 0; it < count; ++it) {
+    const int b = (int)(it % NB);
+    mbar_wait(&full[b], (uint32_t)((it / NB) & 1));
+    const uint64_t gbase = geo.global_base | tile_index(first + it * stride);
+    cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
+    if (!(dbg & 1)) {
+#pragma unroll 1
+      for (int gi = 0; gi < n_gates; ++gi) {
+        if (sg[gi].kind == TQB_GATE_CHAIN && sg[gi].off_a >= 4u) {
+          const RotDesc rd = srd[gi];
+          chain_rot_dispatch<T>(tile, gbase, rd, sm, tid, ncons);
+        } else {
+          tile_apply_gate_lean<T, false>(tile, m, gbase, sg[gi], sm, tid, ncons);
+        }
+        if (gi + 1 < n_gates) consumer_sync(ncons);
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(&done[b]);
+  }
+}
+
 // ---- ring variant: one CTA per SM, one producer warp, G consumer groups, NB-deep tile ring ----------
 // With one tile in flight per CTA (two buffers) the memory system sees at most 3 x 32 KiB per SM and only
 // while a CTA is not computing (ncu: DRAM 59 % busy, FP64 40 % busy, time = sum of both).  Here a single
@@ -435,6 +565,39 @@ static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, cons
   return 0;
 }
 
+static std::atomic<int> g_lean{1};  // tqb_set_tma(512 + v): 0 = never use the lean kernel
+
+template <typename T, int NB>
+static int launch_pass_lean(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
+                            const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st, bool *used) {
+  *used = false;
+  const int max_threads = 128;
+  if (threads > max_threads) threads = max_threads;
+  const size_t smem = NB * (sizeof(cplx<T>) << geo.m) + 64 + (size_t)n_gates * (sizeof(tqb_gate) + sizeof(RotDesc)) +
+                      (size_t)((geo.mat_count + 1) & ~1) * sizeof(cplx<T>) + (sizeof(uint64_t) << geo.h);
+  if (smem > (size_t)ws.max_smem_optin) return 0;
+  auto kern = tile_pass_lean_kernel<T, NB>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  const unsigned long long total = (unsigned long long)batch << (geo.n - geo.m);
+  int resident = 0;
+  const int block = threads + 32;
+  TQB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, block, smem));
+  if (resident < 1) return 0;
+  int per_sm = ctas_per_sm > 0 && ctas_per_sm < resident ? ctas_per_sm : resident;
+  unsigned long long grid = (unsigned long long)ws.sm_count * per_sm;
+  if (grid > total) grid = total;
+  kern<<<(unsigned)grid, block, smem, st>>>(reinterpret_cast<cplx<T> *>(state), geo, (long long)batch, gates, n_gates,
+                                             reinterpret_cast<const cplx<T> *>(mats), g_dbg.load());
+  TQB_CHECK_LAUNCH("tile_pass_lean_kernel");
+  *used = true;
+  return 0;
+}
+
 template <typename T, int MAXK>
 static int launch_pass_ring(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
                             const void *mats, int threads, const Workspace &ws, cudaStream_t st, bool *used) {
@@ -476,6 +639,9 @@ using namespace tqb;
 extern "C" {
 
 int tqb_set_tma(int mode) {
+  if (mode >= 512) {  // 512 + v: lean kernel variant on (1, default) / off (0)
+    return g_lean.exchange(mode - 512 ? 1 : 0);
+  }
   if (mode >= 256) {  // 256 + flags: profiling switches (results are WRONG with any flag set)
     g_dbg.store(mode - 256);
     return g_use_tma.load();
@@ -581,6 +747,13 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
     if (g_use_tma.load() && run_bytes >= 128 && n > ps.m) {
       bool used = false;
       rc = 0;
+      if (ps.max_dense_k < 0 && ps.mat_count > 0 && g_lean.load() && g_use_tma.load() != 4) {
+        rc = dtype == TQB_C128 ? launch_pass_lean<double, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
+                               : launch_pass_lean<float, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used);
+        if (rc) return rc;
+        if (used) continue;
+      }
+#ifndef TQB_LEAN_ONLY  // (defined only for quick SASS inspection builds of the lean kernel: tools/sass_lean.sh)
       if (g_use_tma.load() == 4) {  // ring: one CTA per SM, G consumer groups, NB-deep tile ring
         if (dtype == TQB_C128)
           rc = heavy ? launch_pass_ring<double, 4>(state, geo, batch, g, ps.n_gates, mats_dev, threads, *ws, st, &used)
@@ -614,6 +787,10 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
       rc = heavy ? TQB_LAUNCH(float, 1, 4) : TQB_LAUNCH(float, 1, 2);
 #undef TQB_LAUNCH
     if (rc) return rc;
+#else
+    }
+    return fail("lean-only build");
+#endif
   }
   return 0;
 }

@@ -266,7 +266,8 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
     ``control_bit`` (None: M_sel0 is used), layer i > 0 by the value of layer i-1's target bit.
     ``structure``: per layer MUX_GENERAL / MUX_XU / LAYER_PLAIN.  When every layer is plain or a gate followed by a
     fused cx, and all selector-0 matrices factor as rotation x diagonal of one type (``rot_decompose``), the gate is
-    emitted in rotation form: data = [P (2^R entries), (a_i + i r_i) per layer], pat_b = 4 + 2*type + muxed
+    emitted in rotation form: data = [P (2^R entries), S.(a_0 + i r_0), (t_i or c_i) + i mode_i for layers i > 0]
+    (tqb_core.cuh rot_layer_scaled: the larger of a_i, r_i is divided out and collected in S), pat_b = 4 + 2*type + muxed
     (R = 4 exists in rotation form only).  ``pre_diags``: diagonal gates that act right BEFORE the chain, on chain
     targets plus the ``extra_bits`` (<= 2): they are multiplied into the table, which then has 2^(R+E) entries
     (index = register index + extras << R); the extras are appended to ``bits`` and counted in pat_a >> 1."""
@@ -303,14 +304,35 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
                             di |= (((sv >> pos) if kind == "t" else (xv >> pos)) & 1) << j
                         tab[idx] *= complex(d.data[di])
             unit = all(t == 1.0 for t in tab)
-            tab += [complex(float(dec[i][0][0]), float(dec[i][1][0])) for i in range(R)]
+            if control_bit is not None:   # second copy for control = 1: register-index bit 0 flipped (gate_chain_rot)
+                tab = tab + [tab[i ^ 1] for i in range(len(tab))]
+            coef, scale = [], 1.0
+            for i in range(1, R):   # scaled layers: (t, 0) with t = r / a, or (c, 1) with c = a / r; the factor goes to layer 0
+                ai, ri = float(dec[i][0][0]), float(dec[i][1][0])
+                if abs(ai) >= abs(ri):
+                    coef.append(complex(ri / ai, 0.0))
+                    scale *= ai
+                else:
+                    coef.append(complex(ai / ri, 1.0))
+                    scale *= ri
+            tab += [complex(float(dec[0][0][0]) * scale, float(dec[0][1][0]) * scale)] + coef
             data = np.array(tab, dtype=C128).reshape(1, -1)
         else:
             P = np.ones((B, 1 << R), dtype=C128)
             for s in range(1 << R):
                 for i in range(R):
                     P[:, s] *= dec[i][3] if (s >> i) & 1 else dec[i][2]
-            coef = np.stack([np.broadcast_to(dec[i][0] + 1j * dec[i][1], (B,)) for i in range(R)], axis=1)
+            if control_bit is not None:
+                P = np.concatenate([P, P[:, np.arange(1 << R) ^ 1]], axis=1)
+            cols, scale = [], np.ones(B)
+            for i in range(1, R):   # scaled layers, per batch member (see the B == 1 branch)
+                ai, ri = np.broadcast_to(dec[i][0], (B,)), np.broadcast_to(dec[i][1], (B,))
+                big = np.abs(ai) >= np.abs(ri)
+                with np.errstate(all="ignore"):
+                    cols.append(np.where(big, ri / ai, ai / ri) + 1j * np.where(big, 0.0, 1.0))
+                scale = scale * np.where(big, ai, ri)
+            cols.insert(0, (np.broadcast_to(dec[0][0], (B,)) + 1j * np.broadcast_to(dec[0][1], (B,))) * scale)
+            coef = np.stack(cols, axis=1)
             data = np.ascontiguousarray(np.concatenate([P, coef], axis=1))
         kw["pat_b"] = (4 + 2 * typ + muxed) | (E << 4) | (128 if unit else 0)
     else:

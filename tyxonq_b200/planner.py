@@ -221,8 +221,11 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
             ps["hb"][j] = p
         maxk = 0
         any_batched = False
+        lean = True   # only 1-qubit-layer gates: DENSE k = 1, DIAG, MUX, CHAIN (the lean kernel variant)
         for idx in chosen:
             g = gates[idx]
+            if not (g.kind in (DIAG, MUX, CHAIN) or (g.kind == DENSE and g.k == 1)):
+                lean = False
             e = garr[gi]
             e["kind"] = g.kind
             e["k"] = g.k
@@ -279,9 +282,10 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
             mat_off += d.size
             order.append(idx)
             gi += 1
-        ps["max_dense_k"] = maxk
         cnt = mat_off - int(ps["mat_begin"])
         ps["mat_count"] = cnt if (not any_batched and cnt <= 4096) else 0   # staged in shared memory
+        # -1: lean-eligible pass with staged matrices (tqb_run_passes picks tile_pass_lean_kernel when the tile streams)
+        ps["max_dense_k"] = -1 if (lean and ps["mat_count"] > 0 and cnt <= 1024) else maxk
     flat = np.concatenate(mats) if mats else np.zeros(0, dtype=C128)
     return Program(n=n, passes=passes, gates=garr, mats=flat, n_gates_in=len(gates), tile=tile, order=order)
 
@@ -306,7 +310,7 @@ def fp_ops_per_amplitude(prog: Program) -> float:
             total += 8.0
         elif kind == _lib.GATE_CHAIN:
             if int(g["off_a"]) >= 4:
-                total += 4.0 * k + (0.0 if int(g["off_b"]) & 128 else 4.0)
+                total += 4.0 + 2.0 * (k - 1) + (0.0 if int(g["off_b"]) & 128 else 4.0)   # layer 0: 4, scaled layers: 2, table: 4
             else:
                 total += 8.0 * k
     return total
