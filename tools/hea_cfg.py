@@ -33,13 +33,14 @@ def main():
         f = [int(x) for x in cfg.split(":")]
         m, L, thr = f[:3]
         cps = f[3] if len(f) > 3 else 0
-        prog = compile_program(lg, n, TileConfig(m=m, L=L, threads=thr, ctas_per_sm=cps), itemsize=B)
+        rl = int(os.environ.get("TQB_RROT", "4"))
+        prog = compile_program(lg, n, TileConfig(m=m, L=L, threads=thr, ctas_per_sm=cps, rot_layers=rl), itemsize=B)
         dp = P.DeviceProgram(prog, dev, tdt)
         dp.run(st); torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); dp.run(st); e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        print(f"HEA n={n} {dt} m={m} L={L} thr={thr} cps={cps} passes={prog.n_passes} sweeps/pass={len(lg) / prog.n_passes:.1f} ms={ms:.1f} "
+        print(f"HEA n={n} {dt} m={m} L={L} thr={thr} cps={cps} passes={prog.n_passes} sweeps/pass={len(prog.gates) / prog.n_passes:.1f} ms={ms:.1f} "
               f"ms/pass={ms / prog.n_passes:.2f} gates/s={len(ops) / ms * 1e3:.0f} GBps={prog.n_passes * 2.0 * (1 << n) * B / ms / 1e6:.0f}", flush=True)
 
 

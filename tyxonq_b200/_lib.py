@@ -15,6 +15,8 @@ import numpy as np
 
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libtyxonq_b200.so"
+if os.environ.get("TQB_LIB"):   # profiling builds only (tools/build_prof.sh): an alternative build of the same sources
+    LIB_PATH = Path(os.environ["TQB_LIB"])
 
 TQB_C64, TQB_C128, TQB_F64 = 0, 1, 2
 GATE_DENSE, GATE_DIAG, GATE_PAIR, GATE_SWAP = 0, 1, 2, 3
@@ -128,6 +130,8 @@ def ensure_device(device_index: int) -> None:
     check(load().tqb_init(int(device_index)))
     if os.environ.get("TQB_TMA"):  # tuning knob: 0 = LDG/STG, 2 / 3 = TMA ring depth, 1 = auto
         load().tqb_set_tma(int(os.environ["TQB_TMA"]))
+    if os.environ.get("TQB_LEAN"):  # tuning knob: 0 = never use the lean kernel variant
+        load().tqb_set_tma(512 + int(os.environ["TQB_LEAN"]))
     if os.environ.get("TQB_DBG"):  # profiling only: 1 = no gate arithmetic, 2 = no bulk loads, 4 = no bulk stores
         load().tqb_set_tma(256 + int(os.environ["TQB_DBG"]))
     _inited_devices.add(device_index)

@@ -566,8 +566,16 @@ TQB_HD RotDesc rot_decode(const tqb_gate &g, int m) {
   return r;
 }
 
-template <typename T, int R, int TYPE, bool MUXED>
-TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, const cplx<T> *M, int tid, int nthreads) {
+// Sync: called by every thread exactly once per gate, right before its first access to the tile -- the lean kernel
+// passes its inter-gate barrier (or the wait for the tile to land) here, so that descriptor decoding, group location
+// and address arithmetic of gate g+1 overlap the other warps' tail of gate g.  NoSync: callers that synchronise outside.
+struct NoSync {
+  TQB_HD void operator()() const {}
+};
+
+template <typename T, int R, int TYPE, bool MUXED, class Sync = NoSync, int UNR = 1>   // UNR: groups in flight per thread
+TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, const cplx<T> *M, int tid, int nthreads,
+                            Sync sync = Sync()) {
   constexpr int D = 1 << R;
   constexpr int NZ = R + 1;
   const uint32_t f = rd.flags;
@@ -601,7 +609,9 @@ TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, co
   kk[0] = 0;
   inv[0] = false;
   char *const tbytes = reinterpret_cast<char *>(tile);
+  bool synced = false;
   // (two groups per iteration was measured slower here as well: profiles/r01_tile_sweep.md)
+#pragma unroll(UNR)
   for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
     uint32_t base = gi, cv = cv_fixed;
     if (ctrl_local) {
@@ -618,7 +628,17 @@ TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, co
     const int32_t d0 = (cv ? -d[0] : d[0]) & ~(int32_t)(sizeof(cplx<T>) - 1);
 #pragma unroll
     for (int s = 1; s < D; ++s) q[s] = q[s & (s - 1)] + (TQB_LOW_BIT(s) == 0 ? d0 : d[TQB_LOW_BIT(s) < R ? TQB_LOW_BIT(s) : 0]);
+    if (!synced) {
+      sync();
+      synced = true;
+    }
     cplx<T> v[D];
+#ifdef TQB_PROFILE_SWITCHES   // profiling only (results are wrong): flags bit 14 = no tile loads, bit 7 = no arithmetic, bit 15 = no stores
+    if (f & (1u << 14)) {
+#pragma unroll
+      for (int s = 0; s < D; ++s) v[s] = cplx<T>{(T)(gi + s), (T)s};
+    } else
+#endif
     if (unit_p) {
 #pragma unroll
       for (int s = 0; s < D; ++s) v[s] = *reinterpret_cast<const cplx<T> *>(q[s]);
@@ -634,33 +654,62 @@ TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, co
 #pragma unroll
       for (int s = 0; s < D; ++s) v[s] = cmul(*reinterpret_cast<const cplx<T> *>(q[s]), P[s]);
     }
-    rot_layer<T, R, 0, TYPE, false>(v, a0, (TYPE == 1 && cv) ? -r0 : r0);
-    rot_layer_scaled<T, R, 1, TYPE, MUXED>(v, kk[1], inv[1]);
-    if (R > 2) rot_layer_scaled<T, R, (R > 2 ? 2 : 1), TYPE, MUXED>(v, kk[R > 2 ? 2 : 1], inv[R > 2 ? 2 : 1]);
-    if (R > 3) rot_layer_scaled<T, R, (R > 3 ? 3 : 1), TYPE, MUXED>(v, kk[R > 3 ? 3 : 1], inv[R > 3 ? 3 : 1]);
+#ifdef TQB_PROFILE_SWITCHES
+    if (!(f & (1u << 7)))
+#endif
+    {
+      rot_layer<T, R, 0, TYPE, false>(v, a0, (TYPE == 1 && cv) ? -r0 : r0);
+      rot_layer_scaled<T, R, 1, TYPE, MUXED>(v, kk[1], inv[1]);
+      if (R > 2) rot_layer_scaled<T, R, (R > 2 ? 2 : 1), TYPE, MUXED>(v, kk[R > 2 ? 2 : 1], inv[R > 2 ? 2 : 1]);
+      if (R > 3) rot_layer_scaled<T, R, (R > 3 ? 3 : 1), TYPE, MUXED>(v, kk[R > 3 ? 3 : 1], inv[R > 3 ? 3 : 1]);
+    }
     // outputs are not renamed: register s goes to element s of the group
     char *w[D];
     w[0] = tbytes + (size_t)base * sizeof(cplx<T>);
 #pragma unroll
     for (int s = 1; s < D; ++s) w[s] = w[s & (s - 1)] + d[TQB_LOW_BIT(s) < R ? TQB_LOW_BIT(s) : 0];
+#ifdef TQB_PROFILE_SWITCHES
+    if (f & (1u << 15)) {   // keep the values alive with one store
+      cplx<T> acc = v[0];
+#pragma unroll
+      for (int s = 1; s < D; ++s) { acc.x += v[s].x; acc.y += v[s].y; }
+      if (acc.x == (T)1.2345e-300) *reinterpret_cast<cplx<T> *>(w[0]) = acc;
+      continue;
+    }
+#endif
 #pragma unroll
     for (int s = 0; s < D; ++s) *reinterpret_cast<cplx<T> *>(w[s]) = v[s];
+  }
+  if (!synced) sync();
+}
+
+template <typename T, class Sync, int UNR = 1>
+TQB_HD void chain_rot_dispatch4(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, const cplx<T> *M, int tid, int nthreads, Sync sync) {
+  switch ((rd.flags >> 5) & 3u) {
+    case 0: chain_rot_sweep<T, 4, 0, false, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync); break;
+    case 1: chain_rot_sweep<T, 4, 0, true, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync); break;
+    case 2: chain_rot_sweep<T, 4, 1, false, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync); break;
+    default: chain_rot_sweep<T, 4, 1, true, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync); break;
   }
 }
 
 // dispatch on (R, TYPE, MUXED) of a decoded rotation-form chain; M = base of the matrix buffer
-template <typename T>
-TQB_HD void chain_rot_dispatch(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, const cplx<T> *mats, int tid, int nthreads) {
+template <typename T, class Sync = NoSync, int MAXR = 4, int UNR = 1>   // MAXR = 3: the 4-layer bodies are compiled out (few-register variant)
+TQB_HD void chain_rot_dispatch(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, const cplx<T> *mats, int tid, int nthreads,
+                               Sync sync = Sync()) {
   const cplx<T> *M = mats + rd.mat;
   switch ((rd.flags >> 5) & 3u | ((rd.flags >> 29) & 3u) << 2) {   // (off_a & 3) = 2 * TYPE + MUXED, R - 1
 #define TQB_ROT(R) \
-    case ((R - 1) << 2) | 0: chain_rot_sweep<T, R, 0, false>(tile, gbase, rd, M, tid, nthreads); break; \
-    case ((R - 1) << 2) | 1: chain_rot_sweep<T, R, 0, true>(tile, gbase, rd, M, tid, nthreads); break;  \
-    case ((R - 1) << 2) | 2: chain_rot_sweep<T, R, 1, false>(tile, gbase, rd, M, tid, nthreads); break; \
-    case ((R - 1) << 2) | 3: chain_rot_sweep<T, R, 1, true>(tile, gbase, rd, M, tid, nthreads); break;
-    TQB_ROT(2) TQB_ROT(3) TQB_ROT(4)
+    case ((R - 1) << 2) | 0: chain_rot_sweep<T, R, 0, false, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync); break; \
+    case ((R - 1) << 2) | 1: chain_rot_sweep<T, R, 0, true, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync); break;  \
+    case ((R - 1) << 2) | 2: chain_rot_sweep<T, R, 1, false, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync); break; \
+    case ((R - 1) << 2) | 3: chain_rot_sweep<T, R, 1, true, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync); break;
+    TQB_ROT(2) TQB_ROT(3)
 #undef TQB_ROT
-    default: break;
+    default:
+      if (MAXR >= 4) chain_rot_dispatch4<T, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync);
+      else sync();
+      break;
   }
 }
 

@@ -254,8 +254,10 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
 // loop state to stay in registers, descriptors are read from a 16-byte aligned region and the tile base is
 // computed from a register-packed copy of hb[].
 // layout: NB tiles | 8 mbarrier slots | descriptors | staged matrices | run-offset table (producer only)
-template <typename T, int NB>
-__global__ void __launch_bounds__(160, 3)
+// CT = consumer threads per CTA: 128 (<= 136 registers: 4-layer complex128 chains) or 256 (<= 72 registers, twice
+// the resident warps: 4-layer complex64 chains, 3-layer complex128 chains)
+template <typename T, int NB, int CT>
+__global__ void __launch_bounds__(CT + 32, 3)
 tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                       const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats,
                       const int dbg) {
@@ -281,7 +283,13 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
     for (int i = tid; i < nw; i += nthreads) dst[i] = src[i];
   }
   for (int i = tid; i < n_gates; i += nthreads)
-    if (gates[i].kind == TQB_GATE_CHAIN && gates[i].off_a >= 4u) srd[i] = rot_decode<T>(gates[i], geo.m);
+    if (gates[i].kind == TQB_GATE_CHAIN && gates[i].off_a >= 4u) {
+      srd[i] = rot_decode<T>(gates[i], geo.m);
+      if (CT > 128 && sizeof(T) == 8 && gates[i].k > 3) __trap();  // the few-register variant carries no 4-layer bodies
+#ifdef TQB_PROFILE_SWITCHES   // dbg bits 8 / 16 / 32: chain sweeps without arithmetic / tile loads / tile stores
+      srd[i].flags |= ((dbg & 8) ? 1u << 7 : 0u) | ((dbg & 16) ? 1u << 14 : 0u) | ((dbg & 32) ? 1u << 15 : 0u);
+#endif
+    }
   if (tid == 0) {
     for (int i = 0; i < NB; ++i) {
       mbar_init(&full[i], 1);
@@ -352,22 +360,35 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
 
   const cplx<T> *sm = smats - geo.mat_begin;
   const int m = geo.m;
+  // every gate synchronises right before its first tile access: the first gate of a tile waits for the tile to
+  // land, the others for the previous gate's stores (named barrier) -- decoding and addressing run ahead of both
+  struct GateSync {
+    uint64_t *bar;    // != nullptr: first gate of the tile, wait on this mbarrier
+    uint32_t parity;
+    int ncons;
+    __device__ __forceinline__ void operator()() const {
+      if (bar) mbar_wait(bar, parity);
+      else consumer_sync(ncons);
+    }
+  };
 #pragma unroll 1
   for (unsigned long long it = 0; it < count; ++it) {
     const int b = (int)(it % NB);
-    mbar_wait(&full[b], (uint32_t)((it / NB) & 1));
     const uint64_t gbase = geo.global_base | tile_index(first + it * stride);
     cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
-    if (!(dbg & 1)) {
+    if (dbg & 1) {
+      mbar_wait(&full[b], (uint32_t)((it / NB) & 1));
+    } else {
 #pragma unroll 1
       for (int gi = 0; gi < n_gates; ++gi) {
+        const GateSync gs{gi == 0 ? &full[b] : nullptr, (uint32_t)((it / NB) & 1), ncons};
         if (sg[gi].kind == TQB_GATE_CHAIN && sg[gi].off_a >= 4u) {
           const RotDesc rd = srd[gi];
-          chain_rot_dispatch<T>(tile, gbase, rd, sm, tid, ncons);
+          chain_rot_dispatch<T, GateSync, (CT > 128 && sizeof(T) == 8) ? 3 : 4, (CT < 128 ? 2 : 1)>(tile, gbase, rd, sm, tid, ncons, gs);
         } else {
+          gs();
           tile_apply_gate_lean<T, false>(tile, m, gbase, sg[gi], sm, tid, ncons);
         }
-        if (gi + 1 < n_gates) consumer_sync(ncons);
       }
     }
     fence_proxy_async();
@@ -567,16 +588,15 @@ static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, cons
 
 static std::atomic<int> g_lean{1};  // tqb_set_tma(512 + v): 0 = never use the lean kernel
 
-template <typename T, int NB>
+template <typename T, int NB, int CT>
 static int launch_pass_lean(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
                             const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st, bool *used) {
   *used = false;
-  const int max_threads = 128;
-  if (threads > max_threads) threads = max_threads;
+  threads = CT;
   const size_t smem = NB * (sizeof(cplx<T>) << geo.m) + 64 + (size_t)n_gates * (sizeof(tqb_gate) + sizeof(RotDesc)) +
                       (size_t)((geo.mat_count + 1) & ~1) * sizeof(cplx<T>) + (sizeof(uint64_t) << geo.h);
   if (smem > (size_t)ws.max_smem_optin) return 0;
-  auto kern = tile_pass_lean_kernel<T, NB>;
+  auto kern = tile_pass_lean_kernel<T, NB, CT>;
   static thread_local bool configured = false;
   if (!configured) {
     TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
@@ -748,8 +768,10 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
       bool used = false;
       rc = 0;
       if (ps.max_dense_k < 0 && ps.mat_count > 0 && g_lean.load() && g_use_tma.load() != 4) {
-        rc = dtype == TQB_C128 ? launch_pass_lean<double, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
-                               : launch_pass_lean<float, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used);
+#define TQB_LEAN(T, CT) launch_pass_lean<T, 2, CT>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
+        if (threads >= 256) rc = dtype == TQB_C128 ? TQB_LEAN(double, 256) : TQB_LEAN(float, 256);
+        else rc = dtype == TQB_C128 ? TQB_LEAN(double, 128) : TQB_LEAN(float, 128);
+#undef TQB_LEAN
         if (rc) return rc;
         if (used) continue;
       }

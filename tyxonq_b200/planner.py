@@ -33,6 +33,7 @@ class TileConfig:
     threads: int = 256
     ctas_per_sm: int = 0
     max_gates: int = 384
+    rot_layers: int = 4   # longest rotation-form chain (4 needs the 128-thread kernel variant for complex128)
 
     @property
     def h(self) -> int:
@@ -178,7 +179,7 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
     symmetry; the descriptors do not depend on the state dtype.)"""
     m_eff = min(tile.m, n)
     tile = TileConfig(m=m_eff, L=min(tile.L, m_eff), threads=tile.threads, ctas_per_sm=tile.ctas_per_sm,
-                      max_gates=tile.max_gates)
+                      max_gates=tile.max_gates, rot_layers=tile.rot_layers)
     sched = schedule(gates, n, tile)
     if chain is None:
         chain = bool(getattr(gates, "chain_after_schedule", False))
@@ -190,7 +191,7 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
         grouped: List[LGate] = []
         sched2 = []
         for hb, chosen in sched:
-            sub = group_pass([gates[i] for i in chosen], set(range(tile.L)) | set(int(p) for p in hb))
+            sub = group_pass([gates[i] for i in chosen], set(range(tile.L)) | set(int(p) for p in hb), R_rot=tile.rot_layers)
             sched2.append((hb, list(range(len(grouped), len(grouped) + len(sub)))))
             grouped += sub
         gates, sched = grouped, sched2
