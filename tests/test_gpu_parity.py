@@ -269,6 +269,36 @@ def test_tfim_vqe_energy(cuda_device):
     assert np.abs(g3.reshape(-1) - fd3).max() < 1e-3
 
 
+def test_lean_and_general_kernels_agree_with_oracle(cuda_device):
+    """Every pass of HEA / hwe-ry / Trotter / QAOA circuits is lean-eligible (tile_pass_lean_kernel); the same plans must
+    give the oracle's state through the general kernel too (lean switched off) and through the 256-consumer-thread
+    lean variant (3-layer complex128 chains).  Angles in (-pi, pi): both scaled-rotation modes occur."""
+    import torch
+    from tyxonq_b200 import _lib
+    from tyxonq_b200.planner import TileConfig
+    lib = _lib.load()
+    rng = np.random.default_rng(77)
+    cases = [
+        (20, O.hea_ops(20, 8, rng.uniform(-np.pi, np.pi, 2 * 8 * 20))),
+        (20, O.hwe_ry_ops(20, 5, rng.uniform(-np.pi, np.pi, 6 * 20))),
+        (20, O.trotter_ops(*O.tfim_terms(20, 1.0, 0.7), 0.9, 4)),
+        (20, O.qaoa_ring_ops(20, 4, rng.uniform(-np.pi, np.pi, 8))),
+    ]
+    try:
+        for n, ops in cases:
+            ref, _ = O.evolve_ops(n, ops)
+            for td, tol, m, L in ((torch.complex128, TOL128, 11, 5), (torch.complex64, TOL64, 12, 6)):
+                for lean, tile in ((1, TileConfig(m=m, L=L, threads=128)), (0, TileConfig(m=m, L=L, threads=128)),
+                                   (1, TileConfig(m=m, L=L, threads=256, rot_layers=3 if td == torch.complex128 else 4))):
+                    lib.tqb_set_tma(512 + lean)
+                    eng = _engine(cuda_device, "b200", td, tile)
+                    psi, _, _ = eng._evolve(FakeCircuit(n, ops), "state")
+                    err = np.abs(psi.cpu().numpy() - ref).max()
+                    assert err < tol, (n, ops[0], td, lean, tile.threads, err)
+    finally:
+        lib.tqb_set_tma(512 + 1)
+
+
 def test_large_state_invariants(cuda_device):
     """n = 28 (4 GiB complex128): GHZ amplitudes, norm, reversibility -- size-independent properties."""
     import torch
