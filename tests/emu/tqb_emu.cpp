@@ -38,6 +38,29 @@ static void run_pass(cplx<T> *state, const TileGeom &geo, long long batch, const
   }
 }
 
+// Lean path (tile_pass_lean_kernel): padded tile layout, lean dispatch, chains decoded through RotDesc.
+template <typename T>
+static void run_pass_lean(cplx<T> *state, const TileGeom &geo, long long batch, const tqb_gate *gates, int n_gates,
+                          const cplx<T> *mats, int nthreads) {
+  const int padL = (geo.L >= 1 && geo.L <= 7 && geo.h > 0) ? geo.L : 0;
+  const uint32_t nel = 1u << geo.m;
+  std::vector<cplx<T>> tile((size_t)pidx<T>(nel - 1, padL) + 1);
+  std::vector<uint64_t> roff((size_t)1 << geo.h);
+  for (uint32_t j = 0; j < (1u << geo.h); ++j) roff[j] = run_offset(geo, j);
+  const int tb = geo.n - geo.m;
+  const unsigned long long total = (unsigned long long)batch << tb;
+  for (unsigned long long tt = 0; tt < total; ++tt) {
+    const unsigned long long b = tt >> tb;
+    const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
+    cplx<T> *sb = state + (b << geo.n);
+    for (uint32_t e = 0; e < nel; ++e) tile[pidx<T>(e, padL)] = sb[local_to_index(geo, roff.data(), base, e)];
+    for (int gi = 0; gi < n_gates; ++gi)
+      for (int tid = 0; tid < nthreads; ++tid)
+        tile_apply_gate_lean<T, true>(tile.data(), geo.m, geo.global_base | base, gates[gi], mats, tid, nthreads, padL);
+    for (uint32_t e = 0; e < nel; ++e) sb[local_to_index(geo, roff.data(), base, e)] = tile[pidx<T>(e, padL)];
+  }
+}
+
 extern "C" int tqb_emu_run_passes(void *state, int n, long long batch, int dtype, unsigned long long global_base,
                                   const tqb_pass *passes, int n_passes, const tqb_gate *gates, const void *mats,
                                   int threads) {
@@ -56,6 +79,11 @@ extern "C" int tqb_emu_run_passes(void *state, int n, long long batch, int dtype
       }
     }
     const tqb_gate *g = gates + ps.gate_begin;
+    if (ps.max_dense_k < 0 && batch == 1) {   // lean-eligible pass (the planner's flag), as tqb_run_passes would run it
+      if (dtype == TQB_C128) run_pass_lean<double>((cplx<double> *)state, geo, batch, g, ps.n_gates, (const cplx<double> *)mats, threads > 128 ? 128 : threads);
+      else run_pass_lean<float>((cplx<float> *)state, geo, batch, g, ps.n_gates, (const cplx<float> *)mats, threads > 128 ? 128 : threads);
+      continue;
+    }
     if (dtype == TQB_C128)
       run_pass<double, 1>((cplx<double> *)state, geo, batch, g, ps.n_gates, (const cplx<double> *)mats, threads, ps.max_dense_k);
     else if (ps.L >= 1)

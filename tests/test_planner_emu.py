@@ -147,3 +147,28 @@ def test_chains_grouped_after_scheduling_only_take_tile_local_targets(seed):
     assert np.abs(run_program_emulated(prog, psi0) - ref).max() < 1e-12
     kinds = {(int(g["kind"]), int(g["k"]), int(g["off_a"])) for g in prog.gates if int(g["kind"]) == 5}
     assert kinds  # the random circuits do produce chains
+
+
+@pytest.mark.parametrize("dtype,m,L", [(np.complex128, 7, 3), (np.complex64, 8, 4), (np.complex128, 6, 1)])
+def test_lean_passes_padded_layout(dtype, m, L):
+    """HEA / hwe-ry / QAOA / Trotter circuits compile to lean-eligible passes only (max_dense_k = -1): the emulator
+    runs them like tile_pass_lean_kernel does -- padded tile layout (pidx), chains decoded into RotDesc with padded
+    strides, low-bit targets included -- and must reproduce the oracle."""
+    from tyxonq_b200.fuse import fuse
+    rng = np.random.default_rng(5)
+    n = 12
+    cases = [
+        O.hea_ops(n, 5, rng.uniform(-np.pi, np.pi, 2 * 5 * n)),
+        O.hwe_ry_ops(n, 4, rng.uniform(-np.pi, np.pi, 5 * n)),
+        O.qaoa_ring_ops(n, 3, rng.uniform(-np.pi, np.pi, 6)),
+        O.trotter_ops(*O.tfim_terms(n, 1.0, 0.8), 0.7, 3),
+    ]
+    for ops in cases:
+        ref, _ = O.evolve_ops(n, ops)
+        prog = P.compile_program(fuse(_lower([o for o in ops if o[0] != "measure_z"], n, mode="state")), n,
+                                 P.TileConfig(m=m, L=L), itemsize=np.dtype(dtype).itemsize)
+        assert (prog.passes["max_dense_k"] < 0).all(), "these circuits must be lean-eligible"
+        psi0 = np.zeros(1 << n, dtype=dtype)
+        psi0[0] = 1
+        out = run_program_emulated(prog, psi0)
+        assert np.abs(out - ref).max() < (1e-12 if dtype == np.complex128 else 3e-5)

@@ -80,6 +80,16 @@ TQB_HD uint64_t insert_zeros64(uint64_t g, const int8_t *sb, int k) {
   return g;
 }
 
+// Padded tile layout (lean kernel): every contiguous run of 2^L amplitudes is followed by 16 bytes of padding, so
+// that threads whose groups differ in a HIGH tile bit hit different shared-memory banks when the register-resident
+// targets are LOW bits (a chain on bits 0-3 keeps 256 contiguous bytes per thread: 8-way conflicts in the plain
+// layout, 2-way here).  padL = L when the tile is padded, 0 when it is not; PADSH = log2(16 / sizeof(amplitude)).
+template <typename T>
+TQB_HD uint32_t pidx(uint32_t e, int padL) {
+  constexpr int PADSH = sizeof(cplx<T>) == 16 ? 0 : 1;
+  return padL ? e + ((e >> padL) << PADSH) : e;
+}
+
 // Index (within one batch member) of element 0 of tile t: t's bits deposited into the
 // index bits that are NOT tile bits.
 TQB_HD uint64_t tile_base(const TileGeom &g, uint64_t t) {
@@ -232,7 +242,7 @@ TQB_HD void gate_pair(cplx<T> *tile, const TileGeom &geo, const uint64_t *roff, 
 // index bit (bits[j] - 64) outside the tile, constant for the whole tile (read from gbase).
 template <typename T, int K>
 TQB_HD void gate_diag_k(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *tab,
-                        int tid, int nthreads) {
+                        int tid, int nthreads, int padL = 0) {
   uint32_t pos[K];
   uint32_t cpart = 0, lmask = 0;
 #pragma unroll
@@ -252,19 +262,21 @@ TQB_HD void gate_diag_k(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g,
 #pragma unroll
     for (int j = 0; j < K; ++j)
       if ((lmask >> j) & 1u) t |= ((e >> pos[j]) & 1u) << j;
-    tile[e] = cmul(tile[e], tab[t]);
+    const uint32_t pe = pidx<T>(e, padL);
+    tile[pe] = cmul(tile[pe], tab[t]);
   }
 }
 
 template <typename T>
-TQB_HD void gate_diag(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *tab, int tid, int nthreads) {
+TQB_HD void gate_diag(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *tab, int tid, int nthreads,
+                      int padL = 0) {
   switch (g.k) {
-    case 1: gate_diag_k<T, 1>(tile, m, gbase, g, tab, tid, nthreads); break;
-    case 2: gate_diag_k<T, 2>(tile, m, gbase, g, tab, tid, nthreads); break;
-    case 3: gate_diag_k<T, 3>(tile, m, gbase, g, tab, tid, nthreads); break;
-    case 4: gate_diag_k<T, 4>(tile, m, gbase, g, tab, tid, nthreads); break;
-    case 5: gate_diag_k<T, 5>(tile, m, gbase, g, tab, tid, nthreads); break;
-    case 6: gate_diag_k<T, 6>(tile, m, gbase, g, tab, tid, nthreads); break;
+    case 1: gate_diag_k<T, 1>(tile, m, gbase, g, tab, tid, nthreads, padL); break;
+    case 2: gate_diag_k<T, 2>(tile, m, gbase, g, tab, tid, nthreads, padL); break;
+    case 3: gate_diag_k<T, 3>(tile, m, gbase, g, tab, tid, nthreads, padL); break;
+    case 4: gate_diag_k<T, 4>(tile, m, gbase, g, tab, tid, nthreads, padL); break;
+    case 5: gate_diag_k<T, 5>(tile, m, gbase, g, tab, tid, nthreads, padL); break;
+    case 6: gate_diag_k<T, 6>(tile, m, gbase, g, tab, tid, nthreads, padL); break;
     default: break;
   }
 }
@@ -276,33 +288,35 @@ TQB_HD void gate_diag(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, c
 // bits[1] >= 64: it is index bit bits[1] - 64 outside the tile (constant for the whole tile).
 template <typename T>
 TQB_HD void mux_sweep(cplx<T> *tile, uint32_t ngroups, uint32_t p0, uint32_t p1, bool two, uint32_t fixed,
-                      uint32_t tstride, const cplx<T> *M, int tid, int nthreads) {
+                      uint32_t tstride, const cplx<T> *M, int tid, int nthreads, int padL = 0) {
   const cplx<T> m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
 #pragma unroll 4
   for (uint32_t gi = tid; gi < ngroups; gi += nthreads) {
     uint32_t base = ((gi >> p0) << (p0 + 1u)) | (gi & ((1u << p0) - 1u));
     if (two) base = ((base >> p1) << (p1 + 1u)) | (base & ((1u << p1) - 1u));
     base |= fixed;
-    const cplx<T> a = tile[base], b = tile[base + tstride];
+    const uint32_t ia = pidx<T>(base, padL), ib = pidx<T>(base + tstride, padL);
+    const cplx<T> a = tile[ia], b = tile[ib];
     cplx<T> x{0, 0}, y{0, 0};
     cmac(x, m00, a); cmac(x, m01, b);
     cmac(y, m10, a); cmac(y, m11, b);
-    tile[base] = x;
-    tile[base + tstride] = y;
+    tile[ia] = x;
+    tile[ib] = y;
   }
 }
 
 template <typename T>
-TQB_HD void gate_mux(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+TQB_HD void gate_mux(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads,
+                     int padL = 0) {
   const uint32_t tb = (uint32_t)g.bits[0];
   const uint32_t cb = (uint32_t)(uint8_t)g.bits[1];
   if (cb & 64u) {  // control outside the tile: one matrix for the whole tile
     const uint32_t cv = (uint32_t)((gbase >> (cb & 63u)) & 1ull);
-    mux_sweep<T>(tile, 1u << (m - 1), tb, 0, false, 0, 1u << tb, M + 4 * cv, tid, nthreads);
+    mux_sweep<T>(tile, 1u << (m - 1), tb, 0, false, 0, 1u << tb, M + 4 * cv, tid, nthreads, padL);
   } else {
     const uint32_t p0 = tb < cb ? tb : cb, p1 = tb < cb ? cb : tb;
-    mux_sweep<T>(tile, 1u << (m - 2), p0, p1, true, 0, 1u << tb, M, tid, nthreads);
-    mux_sweep<T>(tile, 1u << (m - 2), p0, p1, true, 1u << cb, 1u << tb, M + 4, tid, nthreads);
+    mux_sweep<T>(tile, 1u << (m - 2), p0, p1, true, 0, 1u << tb, M, tid, nthreads, padL);
+    mux_sweep<T>(tile, 1u << (m - 2), p0, p1, true, 1u << cb, 1u << tb, M + 4, tid, nthreads, padL);
   }
 }
 
@@ -349,7 +363,8 @@ TQB_HD void chain_layer_sel(cplx<T> (&v)[1 << R], const cplx<T> *M) {
 }
 
 template <typename T, int R>
-TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads) {
+TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *M, int tid, int nthreads,
+                       int padL = 0) {
   uint32_t tb[R];
 #pragma unroll
   for (int i = 0; i < R; ++i) tb[i] = (uint32_t)g.bits[i];
@@ -382,7 +397,7 @@ TQB_HD void gate_chain(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, 
 #pragma unroll
     for (int i = 0; i < R; ++i)
       if (s & (1 << i)) o |= 1u << tb[i];
-    return o;
+    return pidx<T>(o, padL);
   };
   uint32_t gi = tid;
   // two groups per iteration: two independent dependency chains keep the FP pipe fed (the sweep is latency bound
@@ -536,7 +551,7 @@ TQB_HD void rot_layer_scaled(cplx<T> (&v)[1 << R], const T k, const bool inv) {
 // every gate of the pass ONCE per CTA into shared memory (tile_pass_lean_kernel), the general kernel decodes in place.
 //   flags: bit 0 control is tile-local, bit 1 has a control, bit 2 table is all ones, bits 3-4 E, bit 5 MUXED,
 //          bit 6 TYPE, bits 8-13 control position (tile-local bit, or index bit outside the tile), bits 16-20 number
-//          of free bits (m - targets - local control), bits 24-28 m, bits 29-30 R - 1
+//          of free bits (m - targets - local control), bits 21-23 padL (pidx), bits 24-28 m, bits 29-30 R - 1
 //   d[i]:  byte stride of target i;  lm[j]: (1 << p_j) - 1 for the ascending positions p_j where a zero bit is
 //          inserted into the group counter (targets + local control), all ones beyond the last one
 struct alignas(16) RotDesc {
@@ -548,18 +563,21 @@ struct alignas(16) RotDesc {
 };
 
 template <typename T>
-TQB_HD RotDesc rot_decode(const tqb_gate &g, int m) {
+TQB_HD RotDesc rot_decode(const tqb_gate &g, int m, int padL = 0) {   // padL: see pidx (0 < padL <= 7, or 0 = plain layout)
   RotDesc r;
   const int R = g.k;
   const uint32_t cb = (uint32_t)(uint8_t)g.bits[R];
   const bool ctrl_local = cb < 64u, has_ctrl = cb != 127u;
   const int nz = ctrl_local ? R + 1 : R;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) r.d[i] = i < R ? (int32_t)(sizeof(cplx<T>) << (uint32_t)g.bits[i]) : 0;
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t b = (uint32_t)g.bits[i];
+    r.d[i] = i < R ? (int32_t)((sizeof(cplx<T>) << b) + ((padL && b >= (uint32_t)padL) ? (16u << (b - (uint32_t)padL)) : 0u)) : 0;
+  }
 #pragma unroll
   for (int j = 0; j < 5; ++j) r.lm[j] = j < nz ? (1u << (uint32_t)g.sbits[j]) - 1u : 0xffffffffu;
   r.flags = (ctrl_local ? 1u : 0u) | (has_ctrl ? 2u : 0u) | ((g.off_b & 128u) ? 4u : 0u) | ((g.off_b & 3u) << 3) |
-            ((g.off_a & 3u) << 5) | ((cb & 63u) << 8) | ((uint32_t)(m - nz) << 16) | ((uint32_t)m << 24) |
+            ((g.off_a & 3u) << 5) | ((cb & 63u) << 8) | ((uint32_t)(m - nz) << 16) | ((uint32_t)padL << 21) | ((uint32_t)m << 24) |
             ((uint32_t)(R - 1) << 29);
   r.xb = (uint32_t)(uint8_t)g.bits[R + 1] | ((uint32_t)(uint8_t)g.bits[R + 2] << 8);
   r.mat = g.mat_off;
@@ -584,6 +602,7 @@ TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, co
   const uint32_t cb = (f >> 8) & 63u;
   const uint32_t free_bits = (f >> 16) & 31u;
   const uint32_t ngroups = 1u << (((f >> 24) & 31u) - (uint32_t)R);
+  const uint32_t padL = (f >> 21) & 7u;
   uint32_t cv_fixed = 0;
   if (!ctrl_local && has_ctrl) cv_fixed = (uint32_t)((gbase >> cb) & 1ull);
   uint32_t lm[NZ];
@@ -624,7 +643,8 @@ TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, co
     // register s holds input amplitude s ^ cv (cv toggles bit 0 = layer 0's bit): start at the flipped element and
     // step layer 0's stride backwards
     char *q[D];
-    q[0] = tbytes + (size_t)base * sizeof(cplx<T>) + (cv ? d[0] : 0);
+    const uint32_t boff = base * (uint32_t)sizeof(cplx<T>) + (padL ? ((base >> padL) << 4) : 0u);  // byte offset of the group's element 0
+    q[0] = tbytes + boff + (cv ? d[0] : 0);
     const int32_t d0 = (cv ? -d[0] : d[0]) & ~(int32_t)(sizeof(cplx<T>) - 1);
 #pragma unroll
     for (int s = 1; s < D; ++s) q[s] = q[s & (s - 1)] + (TQB_LOW_BIT(s) == 0 ? d0 : d[TQB_LOW_BIT(s) < R ? TQB_LOW_BIT(s) : 0]);
@@ -665,7 +685,7 @@ TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, co
     }
     // outputs are not renamed: register s goes to element s of the group
     char *w[D];
-    w[0] = tbytes + (size_t)base * sizeof(cplx<T>);
+    w[0] = tbytes + boff;
 #pragma unroll
     for (int s = 1; s < D; ++s) w[s] = w[s & (s - 1)] + d[TQB_LOW_BIT(s) < R ? TQB_LOW_BIT(s) : 0];
 #ifdef TQB_PROFILE_SWITCHES
@@ -779,24 +799,24 @@ TQB_HD void tile_apply_gate(cplx<T> *tile, const TileGeom &geo, const uint64_t *
 // k >= 2 / PAIR / SWAP / general-CHAIN code, which is what keeps its loop state in registers.
 template <typename T, bool WITH_ROT = true>   // WITH_ROT = false: the caller handles rotation-form chains itself
 TQB_HD void tile_apply_gate_lean(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *mats, int tid,
-                                 int nthreads) {
+                                 int nthreads, int padL = 0) {
   const cplx<T> *mat = mats + g.mat_off;
   switch (g.kind) {
     case TQB_GATE_DENSE:
-      mux_sweep<T>(tile, 1u << (m - 1), (uint32_t)g.bits[0], 0, false, 0, 1u << g.bits[0], mat, tid, nthreads);
+      mux_sweep<T>(tile, 1u << (m - 1), (uint32_t)g.bits[0], 0, false, 0, 1u << g.bits[0], mat, tid, nthreads, padL);
       break;
-    case TQB_GATE_DIAG: gate_diag<T>(tile, m, gbase, g, mat, tid, nthreads); break;
-    case TQB_GATE_MUX: gate_mux<T>(tile, m, gbase, g, mat, tid, nthreads); break;
+    case TQB_GATE_DIAG: gate_diag<T>(tile, m, gbase, g, mat, tid, nthreads, padL); break;
+    case TQB_GATE_MUX: gate_mux<T>(tile, m, gbase, g, mat, tid, nthreads, padL); break;
     case TQB_GATE_CHAIN:
       if (g.off_a >= 4u) {
         if (WITH_ROT) {
-          const RotDesc rd = rot_decode<T>(g, m);
+          const RotDesc rd = rot_decode<T>(g, m, padL);
           chain_rot_dispatch<T>(tile, gbase, rd, mats, tid, nthreads);
         }
       } else if (g.k == 2) {
-        gate_chain<T, 2>(tile, m, gbase, g, mat, tid, nthreads);
+        gate_chain<T, 2>(tile, m, gbase, g, mat, tid, nthreads, padL);
       } else if (g.k == 3) {
-        gate_chain<T, 3>(tile, m, gbase, g, mat, tid, nthreads);
+        gate_chain<T, 3>(tile, m, gbase, g, mat, tid, nthreads, padL);
       }
       break;
     default: break;

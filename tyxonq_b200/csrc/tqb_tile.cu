@@ -253,7 +253,7 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
 // 27 % of the stall samples were long-scoreboard waits on those reloads); here the body is small enough for the
 // loop state to stay in registers, descriptors are read from a 16-byte aligned region and the tile base is
 // computed from a register-packed copy of hb[].
-// layout: NB tiles | 8 mbarrier slots | descriptors | staged matrices | run-offset table (producer only)
+// layout: NB (padded) tiles | 8 mbarrier slots | descriptors | decoded chains | staged matrices | run-offset table
 // CT = consumer threads per CTA: 128 (<= 136 registers: 4-layer complex128 chains) or 256 (<= 72 registers, twice
 // the resident warps: 4-layer complex64 chains, 3-layer complex128 chains)
 template <typename T, int NB, int CT>
@@ -263,7 +263,11 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
                       const int dbg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NB * tile_bytes);
+  // padded tile layout (tqb_core.cuh pidx): 16 bytes after every run
+  const int padL = (geo.L >= 1 && geo.L <= 7 && geo.h > 0) ? geo.L : 0;
+  const uint32_t pad_elems = padL ? (uint32_t)(16 / sizeof(cplx<T>)) : 0u;
+  const size_t tile_stride = tile_bytes + (padL ? ((size_t)16 << geo.h) : 0);  // bytes between the NB tile buffers
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NB * tile_stride);
   uint64_t *done = full + 4;
   tqb_gate *sg = reinterpret_cast<tqb_gate *>(full + 8);
   RotDesc *srd = reinterpret_cast<RotDesc *>(sg + n_gates);  // decoded rotation-form chains (both 48 bytes per gate)
@@ -284,7 +288,7 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
   }
   for (int i = tid; i < n_gates; i += nthreads)
     if (gates[i].kind == TQB_GATE_CHAIN && gates[i].off_a >= 4u) {
-      srd[i] = rot_decode<T>(gates[i], geo.m);
+      srd[i] = rot_decode<T>(gates[i], geo.m, padL);
       if (CT > 128 && sizeof(T) == 8 && gates[i].k > 3) __trap();  // the few-register variant carries no 4-layer bodies
 #ifdef TQB_PROFILE_SWITCHES   // dbg bits 8 / 16 / 32: chain sweeps without arithmetic / tile loads / tile stores
       srd[i].flags |= ((dbg & 8) ? 1u << 7 : 0u) | ((dbg & 16) ? 1u << 14 : 0u) | ((dbg & 32) ? 1u << 15 : 0u);
@@ -329,7 +333,7 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
     };
     auto issue_load = [&](unsigned long long it) {
       const int b = (int)(it % NB);
-      cplx<T> *dst = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
+      cplx<T> *dst = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_stride);
       const cplx<T> *src = tile_ptr(it);
       if (dbg & 2) {
         if (lane == 0) mbar_arrive(&full[b]);
@@ -337,7 +341,7 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
       }
       if (lane == 0) mbar_expect_tx(&full[b], (uint32_t)tile_bytes);
       __syncwarp();
-      for (uint32_t j = lane; j < nruns; j += 32) bulk_load(dst + (size_t)j * run_elems, src + roff[j], run_bytes, &full[b]);
+      for (uint32_t j = lane; j < nruns; j += 32) bulk_load(dst + (size_t)j * (run_elems + pad_elems), src + roff[j], run_bytes, &full[b]);
     };
     for (unsigned long long it = 0; it < (unsigned long long)(NB - 1) && it < count; ++it) issue_load(it);
     for (unsigned long long it = 0; it < count; ++it) {
@@ -349,9 +353,9 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
       }
       mbar_wait(&done[b], (uint32_t)((it / NB) & 1));
       cplx<T> *dstg = tile_ptr(it);
-      const cplx<T> *srcs = reinterpret_cast<const cplx<T> *>(smem_raw + b * tile_bytes);
+      const cplx<T> *srcs = reinterpret_cast<const cplx<T> *>(smem_raw + b * tile_stride);
       if (!(dbg & 4))
-        for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], srcs + (size_t)j * run_elems, run_bytes);
+        for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], srcs + (size_t)j * (run_elems + pad_elems), run_bytes);
       bulk_commit();
     }
     bulk_wait_all0();
@@ -375,7 +379,7 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
   for (unsigned long long it = 0; it < count; ++it) {
     const int b = (int)(it % NB);
     const uint64_t gbase = geo.global_base | tile_index(first + it * stride);
-    cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_bytes);
+    cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_stride);
     if (dbg & 1) {
       mbar_wait(&full[b], (uint32_t)((it / NB) & 1));
     } else {
@@ -387,7 +391,7 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
           chain_rot_dispatch<T, GateSync, (CT > 128 && sizeof(T) == 8) ? 3 : 4, (CT < 128 ? 2 : 1)>(tile, gbase, rd, sm, tid, ncons, gs);
         } else {
           gs();
-          tile_apply_gate_lean<T, false>(tile, m, gbase, sg[gi], sm, tid, ncons);
+          tile_apply_gate_lean<T, false>(tile, m, gbase, sg[gi], sm, tid, ncons, padL);
         }
       }
     }
@@ -593,7 +597,9 @@ static int launch_pass_lean(void *state, const TileGeom &geo, int64_t batch, con
                             const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st, bool *used) {
   *used = false;
   threads = CT;
-  const size_t smem = NB * (sizeof(cplx<T>) << geo.m) + 64 + (size_t)n_gates * (sizeof(tqb_gate) + sizeof(RotDesc)) +
+  const bool padded = geo.L >= 1 && geo.L <= 7 && geo.h > 0;   // must match the kernel's padL
+  const size_t smem = NB * ((sizeof(cplx<T>) << geo.m) + (padded ? ((size_t)16 << geo.h) : 0)) + 64 +
+                      (size_t)n_gates * (sizeof(tqb_gate) + sizeof(RotDesc)) +
                       (size_t)((geo.mat_count + 1) & ~1) * sizeof(cplx<T>) + (sizeof(uint64_t) << geo.h);
   if (smem > (size_t)ws.max_smem_optin) return 0;
   auto kern = tile_pass_lean_kernel<T, NB, CT>;

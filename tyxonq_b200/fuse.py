@@ -233,7 +233,10 @@ def _merge(gates: Sequence[LGate], max_diag_k: int = 6, merge_diag: bool = True)
                 if p.kind == DENSE and len(p.bits) == 2 and not p.batched and not g.batched:
                     out[j] = LGate(DENSE, p.bits, _embed_1q(_m1(g), p.bits.index(t)) @ p.data, name="fused")
                     continue
-                if p.kind == MUX and p.bits[0] == t:      # 1q gate after a MUX on the same target
+                # 1q gate after a MUX on the same target -- unless the MUX is "gate, then cx" (MUX_XU): that structure is
+                # what lets it ride in a rotation-form chain, and the 1q gate will pair up with the NEXT cx the same way
+                # (last qubit of a cx ladder: otherwise one lone general MUX sweep per layer)
+                if p.kind == MUX and p.bits[0] == t and p.pat_b != MUX_XU:
                     v = _m1(g)
                     u0, u1 = _mux_blocks(p)
                     out[j] = mux_gate(v @ u0, v @ u1, t, p.bits[1], name="fused")
