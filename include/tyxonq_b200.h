@@ -86,8 +86,9 @@ typedef struct tqb_pass {
   int32_t gate_begin;
   int32_t n_gates;
   int32_t max_dense_k; /* largest k of a DENSE gate in the pass (selects the kernel variant); */
-                       /* -1 = the pass holds only DENSE k = 1, DIAG, MUX and CHAIN gates and   */
-                       /* mat_count > 0: eligible for the lean kernel variant                   */
+                       /* -1 = the pass holds only DENSE k = 1, DIAG, MUX and CHAIN gates:      */
+                       /* eligible for the lean kernel variant (matrices staged when            */
+                       /* mat_count > 0, else read per batch member from global memory)         */
   int32_t mat_begin;   /* the pass's matrices are mats[mat_begin .. mat_begin+mat_count): they  */
   int32_t mat_count;   /* are staged in shared memory once per CTA; 0 = read from global memory */
   int8_t hb[TQB_MAX_TILE_HIGH];

@@ -56,7 +56,7 @@ static void run_pass_lean(cplx<T> *state, const TileGeom &geo, long long batch, 
     for (uint32_t e = 0; e < nel; ++e) tile[pidx<T>(e, padL)] = sb[local_to_index(geo, roff.data(), base, e)];
     for (int gi = 0; gi < n_gates; ++gi)
       for (int tid = 0; tid < nthreads; ++tid)
-        tile_apply_gate_lean<T, true>(tile.data(), geo.m, geo.global_base | base, gates[gi], mats, tid, nthreads, padL);
+        tile_apply_gate_lean<T, true>(tile.data(), geo.m, geo.global_base | base, gates[gi], mats, tid, nthreads, padL, (size_t)b);
     for (uint32_t e = 0; e < nel; ++e) sb[local_to_index(geo, roff.data(), base, e)] = tile[pidx<T>(e, padL)];
   }
 }
@@ -79,7 +79,7 @@ extern "C" int tqb_emu_run_passes(void *state, int n, long long batch, int dtype
       }
     }
     const tqb_gate *g = gates + ps.gate_begin;
-    if (ps.max_dense_k < 0 && batch == 1) {   // lean-eligible pass (the planner's flag), as tqb_run_passes would run it
+    if (ps.max_dense_k < 0) {   // lean-eligible pass (the planner's flag), as tqb_run_passes would run it
       if (dtype == TQB_C128) run_pass_lean<double>((cplx<double> *)state, geo, batch, g, ps.n_gates, (const cplx<double> *)mats, threads > 128 ? 128 : threads);
       else run_pass_lean<float>((cplx<float> *)state, geo, batch, g, ps.n_gates, (const cplx<float> *)mats, threads > 128 ? 128 : threads);
       continue;

@@ -558,7 +558,7 @@ struct alignas(16) RotDesc {
   int32_t d[4];
   uint32_t lm[5];
   uint32_t flags;
-  uint32_t xb;   // extra table bits: xb0 | xb1 << 8 (encoding of tqb_gate.bits: < 64 tile-local, 64 + p outside)
+  uint32_t xb;   // extra table bits: xb0 | xb1 << 8 (encoding of tqb_gate.bits: < 64 tile-local, 64 + p outside) | mat_bstride << 16
   uint32_t mat;  // tqb_gate.mat_off
 };
 
@@ -579,7 +579,7 @@ TQB_HD RotDesc rot_decode(const tqb_gate &g, int m, int padL = 0) {   // padL: s
   r.flags = (ctrl_local ? 1u : 0u) | (has_ctrl ? 2u : 0u) | ((g.off_b & 128u) ? 4u : 0u) | ((g.off_b & 3u) << 3) |
             ((g.off_a & 3u) << 5) | ((cb & 63u) << 8) | ((uint32_t)(m - nz) << 16) | ((uint32_t)padL << 21) | ((uint32_t)m << 24) |
             ((uint32_t)(R - 1) << 29);
-  r.xb = (uint32_t)(uint8_t)g.bits[R + 1] | ((uint32_t)(uint8_t)g.bits[R + 2] << 8);
+  r.xb = (uint32_t)(uint8_t)g.bits[R + 1] | ((uint32_t)(uint8_t)g.bits[R + 2] << 8) | (g.mat_bstride << 16);  // (stride <= 2^7 + 4)
   r.mat = g.mat_off;
   return r;
 }
@@ -716,8 +716,8 @@ TQB_HD void chain_rot_dispatch4(cplx<T> *tile, uint64_t gbase, const RotDesc &rd
 // dispatch on (R, TYPE, MUXED) of a decoded rotation-form chain; M = base of the matrix buffer
 template <typename T, class Sync = NoSync, int MAXR = 4, int UNR = 1>   // MAXR = 3: the 4-layer bodies are compiled out (few-register variant)
 TQB_HD void chain_rot_dispatch(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, const cplx<T> *mats, int tid, int nthreads,
-                               Sync sync = Sync()) {
-  const cplx<T> *M = mats + rd.mat;
+                               Sync sync = Sync(), size_t bm = 0) {   // bm: batch member of the tile (per-member matrices)
+  const cplx<T> *M = mats + rd.mat + bm * (size_t)(rd.xb >> 16);
   switch ((rd.flags >> 5) & 3u | ((rd.flags >> 29) & 3u) << 2) {   // (off_a & 3) = 2 * TYPE + MUXED, R - 1
 #define TQB_ROT(R) \
     case ((R - 1) << 2) | 0: chain_rot_sweep<T, R, 0, false, Sync, UNR>(tile, gbase, rd, M, tid, nthreads, sync); break; \
@@ -799,8 +799,8 @@ TQB_HD void tile_apply_gate(cplx<T> *tile, const TileGeom &geo, const uint64_t *
 // k >= 2 / PAIR / SWAP / general-CHAIN code, which is what keeps its loop state in registers.
 template <typename T, bool WITH_ROT = true>   // WITH_ROT = false: the caller handles rotation-form chains itself
 TQB_HD void tile_apply_gate_lean(cplx<T> *tile, int m, uint64_t gbase, const tqb_gate &g, const cplx<T> *mats, int tid,
-                                 int nthreads, int padL = 0) {
-  const cplx<T> *mat = mats + g.mat_off;
+                                 int nthreads, int padL = 0, size_t bm = 0) {
+  const cplx<T> *mat = mats + g.mat_off + bm * g.mat_bstride;
   switch (g.kind) {
     case TQB_GATE_DENSE:
       mux_sweep<T>(tile, 1u << (m - 1), (uint32_t)g.bits[0], 0, false, 0, 1u << g.bits[0], mat, tid, nthreads, padL);
@@ -811,7 +811,7 @@ TQB_HD void tile_apply_gate_lean(cplx<T> *tile, int m, uint64_t gbase, const tqb
       if (g.off_a >= 4u) {
         if (WITH_ROT) {
           const RotDesc rd = rot_decode<T>(g, m, padL);
-          chain_rot_dispatch<T>(tile, gbase, rd, mats, tid, nthreads);
+          chain_rot_dispatch<T>(tile, gbase, rd, mats, tid, nthreads, NoSync(), bm);
         }
       } else if (g.k == 2) {
         gate_chain<T, 2>(tile, m, gbase, g, mat, tid, nthreads, padL);

@@ -256,7 +256,9 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
 // layout: NB (padded) tiles | 8 mbarrier slots | descriptors | decoded chains | staged matrices | run-offset table
 // CT = consumer threads per CTA: 128 (<= 136 registers: 4-layer complex128 chains) or 256 (<= 72 registers, twice
 // the resident warps: 4-layer complex64 chains, 3-layer complex128 chains)
-template <typename T, int NB, int CT>
+// GM = true: matrices are read from global memory (per-batch-member matrices, tqb_gate.mat_bstride) instead of the
+// staged copy -- a separate instantiation so that the staged variant keeps shared-address-space loads
+template <typename T, int NB, int CT, bool GM>
 __global__ void __launch_bounds__(CT + 32, 3)
 tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                       const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats,
@@ -362,7 +364,7 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
     return;
   }
 
-  const cplx<T> *sm = smats - geo.mat_begin;
+  const cplx<T> *sm = GM ? mats : smats - geo.mat_begin;
   const int m = geo.m;
   // every gate synchronises right before its first tile access: the first gate of a tile waits for the tile to
   // land, the others for the previous gate's stores (named barrier) -- decoding and addressing run ahead of both
@@ -379,6 +381,7 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
   for (unsigned long long it = 0; it < count; ++it) {
     const int b = (int)(it % NB);
     const uint64_t gbase = geo.global_base | tile_index(first + it * stride);
+    const size_t bm = GM ? (size_t)((first + it * stride) >> tb) : 0;
     cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_stride);
     if (dbg & 1) {
       mbar_wait(&full[b], (uint32_t)((it / NB) & 1));
@@ -388,10 +391,10 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
         const GateSync gs{gi == 0 ? &full[b] : nullptr, (uint32_t)((it / NB) & 1), ncons};
         if (sg[gi].kind == TQB_GATE_CHAIN && sg[gi].off_a >= 4u) {
           const RotDesc rd = srd[gi];
-          chain_rot_dispatch<T, GateSync, (CT > 128 && sizeof(T) == 8) ? 3 : 4, (CT < 128 ? 2 : 1)>(tile, gbase, rd, sm, tid, ncons, gs);
+          chain_rot_dispatch<T, GateSync, (CT > 128 && sizeof(T) == 8) ? 3 : 4, (CT < 128 ? 2 : 1)>(tile, gbase, rd, sm, tid, ncons, gs, bm);
         } else {
           gs();
-          tile_apply_gate_lean<T, false>(tile, m, gbase, sg[gi], sm, tid, ncons, padL);
+          tile_apply_gate_lean<T, false>(tile, m, gbase, sg[gi], sm, tid, ncons, padL, bm);
         }
       }
     }
@@ -592,7 +595,7 @@ static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, cons
 
 static std::atomic<int> g_lean{1};  // tqb_set_tma(512 + v): 0 = never use the lean kernel
 
-template <typename T, int NB, int CT>
+template <typename T, int NB, int CT, bool GM>
 static int launch_pass_lean(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
                             const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st, bool *used) {
   *used = false;
@@ -602,7 +605,7 @@ static int launch_pass_lean(void *state, const TileGeom &geo, int64_t batch, con
                       (size_t)n_gates * (sizeof(tqb_gate) + sizeof(RotDesc)) +
                       (size_t)((geo.mat_count + 1) & ~1) * sizeof(cplx<T>) + (sizeof(uint64_t) << geo.h);
   if (smem > (size_t)ws.max_smem_optin) return 0;
-  auto kern = tile_pass_lean_kernel<T, NB, CT>;
+  auto kern = tile_pass_lean_kernel<T, NB, CT, GM>;
   static thread_local bool configured = false;
   if (!configured) {
     TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
@@ -773,10 +776,11 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
     if (g_use_tma.load() && run_bytes >= 128 && n > ps.m) {
       bool used = false;
       rc = 0;
-      if (ps.max_dense_k < 0 && ps.mat_count > 0 && g_lean.load() && g_use_tma.load() != 4) {
-#define TQB_LEAN(T, CT) launch_pass_lean<T, 2, CT>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
-        if (threads >= 256) rc = dtype == TQB_C128 ? TQB_LEAN(double, 256) : TQB_LEAN(float, 256);
-        else rc = dtype == TQB_C128 ? TQB_LEAN(double, 128) : TQB_LEAN(float, 128);
+      if (ps.max_dense_k < 0 && g_lean.load() && g_use_tma.load() != 4) {
+#define TQB_LEAN(T, CT, GM) launch_pass_lean<T, 2, CT, GM>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
+        if (ps.mat_count == 0) rc = dtype == TQB_C128 ? TQB_LEAN(double, 128, true) : TQB_LEAN(float, 128, true);
+        else if (threads >= 256) rc = dtype == TQB_C128 ? TQB_LEAN(double, 256, false) : TQB_LEAN(float, 256, false);
+        else rc = dtype == TQB_C128 ? TQB_LEAN(double, 128, false) : TQB_LEAN(float, 128, false);
 #undef TQB_LEAN
         if (rc) return rc;
         if (used) continue;

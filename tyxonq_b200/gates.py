@@ -303,7 +303,7 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
                         for j, (kind, pos) in enumerate(src):
                             di |= (((sv >> pos) if kind == "t" else (xv >> pos)) & 1) << j
                         tab[idx] *= complex(d.data[di])
-            unit = all(t == 1.0 for t in tab)
+            unit = all(abs(t - 1.0) < 1e-15 for t in tab)   # (phases of exactly 1 up to the rounding of their normalisation)
             if control_bit is not None:   # second copy for control = 1: register-index bit 0 flipped (gate_chain_rot)
                 tab = tab + [tab[i ^ 1] for i in range(len(tab))]
             coef, scale = [], 1.0
@@ -322,6 +322,7 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
             for s in range(1 << R):
                 for i in range(R):
                     P[:, s] *= dec[i][3] if (s >> i) & 1 else dec[i][2]
+            unit = bool(np.abs(P - 1.0).max() < 1e-15)   # plain rotations (ry, rx layers): the kernel skips the table multiply
             if control_bit is not None:
                 P = np.concatenate([P, P[:, np.arange(1 << R) ^ 1]], axis=1)
             cols, scale = [], np.ones(B)

@@ -285,8 +285,8 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
             gi += 1
         cnt = mat_off - int(ps["mat_begin"])
         ps["mat_count"] = cnt if (not any_batched and cnt <= 4096) else 0   # staged in shared memory
-        # -1: lean-eligible pass with staged matrices (tqb_run_passes picks tile_pass_lean_kernel when the tile streams)
-        ps["max_dense_k"] = -1 if (lean and ps["mat_count"] > 0 and cnt <= 1024) else maxk
+        # -1: lean-eligible pass, matrices staged or per batch member (tqb_run_passes picks tile_pass_lean_kernel when the tile streams)
+        ps["max_dense_k"] = -1 if (lean and (any_batched or (ps["mat_count"] > 0 and cnt <= 1024))) else maxk
     flat = np.concatenate(mats) if mats else np.zeros(0, dtype=C128)
     return Program(n=n, passes=passes, gates=garr, mats=flat, n_gates_in=len(gates), tile=tile, order=order)
 
