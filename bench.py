@@ -247,7 +247,7 @@ def own_arm(args) -> None:
         pass_ms = per_launch_ms * info["passes"]
     alg_bytes = 2.0 * (1 << n_local) * B
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "tile_pass_lean_kernel<double,2,128>" if args.dtype == "complex128" else "tile_pass_lean_kernel<float,2,128>", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "tile_pass_lean_kernel<double,2,128,GM=false,PAD=false|true>" if args.dtype == "complex128" else "tile_pass_lean_kernel<float,2,128,GM=false,PAD=false|true>", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"], "traffic": None,
             "alg_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms, "pass_share_of_step": pass_ms / ms_per_step}
     if "fp_ops_per_amplitude" in info:

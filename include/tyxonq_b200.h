@@ -88,7 +88,10 @@ typedef struct tqb_pass {
   int32_t max_dense_k; /* largest k of a DENSE gate in the pass (selects the kernel variant); */
                        /* -1 = the pass holds only DENSE k = 1, DIAG, MUX and CHAIN gates:      */
                        /* eligible for the lean kernel variant (matrices staged when            */
-                       /* mat_count > 0, else read per batch member from global memory)         */
+                       /* mat_count > 0, else read per batch member from global memory);        */
+                       /* -2 = the same, staged in the PADDED tile layout (16 bytes after every  */
+                       /* run: for passes whose gates keep index bits below 128 bytes in          */
+                       /* registers, which would bank-conflict 8-way in the plain layout)        */
   int32_t mat_begin;   /* the pass's matrices are mats[mat_begin .. mat_begin+mat_count): they  */
   int32_t mat_count;   /* are staged in shared memory once per CTA; 0 = read from global memory */
   int8_t hb[TQB_MAX_TILE_HIGH];

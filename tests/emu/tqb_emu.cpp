@@ -41,8 +41,8 @@ static void run_pass(cplx<T> *state, const TileGeom &geo, long long batch, const
 // Lean path (tile_pass_lean_kernel): padded tile layout, lean dispatch, chains decoded through RotDesc.
 template <typename T>
 static void run_pass_lean(cplx<T> *state, const TileGeom &geo, long long batch, const tqb_gate *gates, int n_gates,
-                          const cplx<T> *mats, int nthreads) {
-  const int padL = (geo.L >= 1 && geo.L <= 7 && geo.h > 0) ? geo.L : 0;
+                          const cplx<T> *mats, int nthreads, bool pad) {
+  const int padL = (pad && geo.L >= 1 && geo.L <= 7 && geo.h > 0) ? geo.L : 0;
   const uint32_t nel = 1u << geo.m;
   std::vector<cplx<T>> tile((size_t)pidx<T>(nel - 1, padL) + 1);
   std::vector<uint64_t> roff((size_t)1 << geo.h);
@@ -80,8 +80,8 @@ extern "C" int tqb_emu_run_passes(void *state, int n, long long batch, int dtype
     }
     const tqb_gate *g = gates + ps.gate_begin;
     if (ps.max_dense_k < 0) {   // lean-eligible pass (the planner's flag), as tqb_run_passes would run it
-      if (dtype == TQB_C128) run_pass_lean<double>((cplx<double> *)state, geo, batch, g, ps.n_gates, (const cplx<double> *)mats, threads > 128 ? 128 : threads);
-      else run_pass_lean<float>((cplx<float> *)state, geo, batch, g, ps.n_gates, (const cplx<float> *)mats, threads > 128 ? 128 : threads);
+      if (dtype == TQB_C128) run_pass_lean<double>((cplx<double> *)state, geo, batch, g, ps.n_gates, (const cplx<double> *)mats, threads > 128 ? 128 : threads, ps.max_dense_k == -2);
+      else run_pass_lean<float>((cplx<float> *)state, geo, batch, g, ps.n_gates, (const cplx<float> *)mats, threads > 128 ? 128 : threads, ps.max_dense_k == -2);
       continue;
     }
     if (dtype == TQB_C128)

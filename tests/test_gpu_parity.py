@@ -271,8 +271,7 @@ def test_tfim_vqe_energy(cuda_device):
 
 def test_lean_and_general_kernels_agree_with_oracle(cuda_device):
     """Every pass of HEA / hwe-ry / Trotter / QAOA circuits is lean-eligible (tile_pass_lean_kernel); the same plans must
-    give the oracle's state through the general kernel too (lean switched off) and through the 256-consumer-thread
-    lean variant (3-layer complex128 chains).  Angles in (-pi, pi): both scaled-rotation modes occur."""
+    give the oracle's state through the general kernel too (lean switched off) and with chains limited to 3 layers.  Angles in (-pi, pi): both scaled-rotation modes occur."""
     import torch
     from tyxonq_b200 import _lib
     from tyxonq_b200.planner import TileConfig
@@ -289,7 +288,7 @@ def test_lean_and_general_kernels_agree_with_oracle(cuda_device):
             ref, _ = O.evolve_ops(n, ops)
             for td, tol, m, L in ((torch.complex128, TOL128, 11, 5), (torch.complex64, TOL64, 12, 6)):
                 for lean, tile in ((1, TileConfig(m=m, L=L, threads=128)), (0, TileConfig(m=m, L=L, threads=128)),
-                                   (1, TileConfig(m=m, L=L, threads=256, rot_layers=3 if td == torch.complex128 else 4))):
+                                   (1, TileConfig(m=m, L=L, threads=128, rot_layers=3))):
                     lib.tqb_set_tma(512 + lean)
                     eng = _engine(cuda_device, "b200", td, tile)
                     psi, _, _ = eng._evolve(FakeCircuit(n, ops), "state")

@@ -254,11 +254,12 @@ tile_pass_tma_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long
 // loop state to stay in registers, descriptors are read from a 16-byte aligned region and the tile base is
 // computed from a register-packed copy of hb[].
 // layout: NB (padded) tiles | 8 mbarrier slots | descriptors | decoded chains | staged matrices | run-offset table
-// CT = consumer threads per CTA: 128 (<= 136 registers: 4-layer complex128 chains) or 256 (<= 72 registers, twice
-// the resident warps: 4-layer complex64 chains, 3-layer complex128 chains)
+// CT = consumer threads per CTA (128: <= 136 registers, 4-layer complex128 chains; a 256-thread / 72-register variant
+// with twice the resident warps was measured slower and is not instantiated: profiles/r01_tile_sweep.md)
 // GM = true: matrices are read from global memory (per-batch-member matrices, tqb_gate.mat_bstride) instead of the
 // staged copy -- a separate instantiation so that the staged variant keeps shared-address-space loads
-template <typename T, int NB, int CT, bool GM>
+// PAD = true: padded tile layout (the planner asks for it when a gate of the pass keeps LOW index bits in registers)
+template <typename T, int NB, int CT, bool GM, bool PAD>
 __global__ void __launch_bounds__(CT + 32, 3)
 tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
                       const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats,
@@ -266,7 +267,7 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
   // padded tile layout (tqb_core.cuh pidx): 16 bytes after every run
-  const int padL = (geo.L >= 1 && geo.L <= 7 && geo.h > 0) ? geo.L : 0;
+  const int padL = (PAD && geo.L >= 1 && geo.L <= 7 && geo.h > 0) ? geo.L : 0;
   const uint32_t pad_elems = padL ? (uint32_t)(16 / sizeof(cplx<T>)) : 0u;
   const size_t tile_stride = tile_bytes + (padL ? ((size_t)16 << geo.h) : 0);  // bytes between the NB tile buffers
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + NB * tile_stride);
@@ -291,7 +292,6 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
   for (int i = tid; i < n_gates; i += nthreads)
     if (gates[i].kind == TQB_GATE_CHAIN && gates[i].off_a >= 4u) {
       srd[i] = rot_decode<T>(gates[i], geo.m, padL);
-      if (CT > 128 && sizeof(T) == 8 && gates[i].k > 3) __trap();  // the few-register variant carries no 4-layer bodies
 #ifdef TQB_PROFILE_SWITCHES   // dbg bits 8 / 16 / 32: chain sweeps without arithmetic / tile loads / tile stores
       srd[i].flags |= ((dbg & 8) ? 1u << 7 : 0u) | ((dbg & 16) ? 1u << 14 : 0u) | ((dbg & 32) ? 1u << 15 : 0u);
 #endif
@@ -595,17 +595,17 @@ static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, cons
 
 static std::atomic<int> g_lean{1};  // tqb_set_tma(512 + v): 0 = never use the lean kernel
 
-template <typename T, int NB, int CT, bool GM>
+template <typename T, int NB, int CT, bool GM, bool PAD>
 static int launch_pass_lean(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
                             const void *mats, int threads, int ctas_per_sm, const Workspace &ws, cudaStream_t st, bool *used) {
   *used = false;
   threads = CT;
-  const bool padded = geo.L >= 1 && geo.L <= 7 && geo.h > 0;   // must match the kernel's padL
+  const bool padded = PAD && geo.L >= 1 && geo.L <= 7 && geo.h > 0;   // must match the kernel's padL
   const size_t smem = NB * ((sizeof(cplx<T>) << geo.m) + (padded ? ((size_t)16 << geo.h) : 0)) + 64 +
                       (size_t)n_gates * (sizeof(tqb_gate) + sizeof(RotDesc)) +
                       (size_t)((geo.mat_count + 1) & ~1) * sizeof(cplx<T>) + (sizeof(uint64_t) << geo.h);
   if (smem > (size_t)ws.max_smem_optin) return 0;
-  auto kern = tile_pass_lean_kernel<T, NB, CT, GM>;
+  auto kern = tile_pass_lean_kernel<T, NB, CT, GM, PAD>;
   static thread_local bool configured = false;
   if (!configured) {
     TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
@@ -777,10 +777,15 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
       bool used = false;
       rc = 0;
       if (ps.max_dense_k < 0 && g_lean.load() && g_use_tma.load() != 4) {
-#define TQB_LEAN(T, CT, GM) launch_pass_lean<T, 2, CT, GM>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
-        if (ps.mat_count == 0) rc = dtype == TQB_C128 ? TQB_LEAN(double, 128, true) : TQB_LEAN(float, 128, true);
-        else if (threads >= 256) rc = dtype == TQB_C128 ? TQB_LEAN(double, 256, false) : TQB_LEAN(float, 256, false);
-        else rc = dtype == TQB_C128 ? TQB_LEAN(double, 128, false) : TQB_LEAN(float, 128, false);
+#define TQB_LEAN(T, GM, PAD) launch_pass_lean<T, 2, 128, GM, PAD>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
+        const bool pad = ps.max_dense_k == -2;   // the planner's request for the padded tile layout
+        if (dtype == TQB_C128) {
+          if (ps.mat_count == 0) rc = pad ? TQB_LEAN(double, true, true) : TQB_LEAN(double, true, false);
+          else rc = pad ? TQB_LEAN(double, false, true) : TQB_LEAN(double, false, false);
+        } else {
+          if (ps.mat_count == 0) rc = pad ? TQB_LEAN(float, true, true) : TQB_LEAN(float, true, false);
+          else rc = pad ? TQB_LEAN(float, false, true) : TQB_LEAN(float, false, false);
+        }
 #undef TQB_LEAN
         if (rc) return rc;
         if (used) continue;

@@ -223,6 +223,8 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
         maxk = 0
         any_batched = False
         lean = True   # only 1-qubit-layer gates: DENSE k = 1, DIAG, MUX, CHAIN (the lean kernel variant)
+        low_regs = False   # a gate keeps index bits below 128 bytes in registers: bank conflicts unless the tile is padded
+        low_bits = 3 if itemsize == 16 else 4
         for idx in chosen:
             g = gates[idx]
             if not (g.kind in (DIAG, MUX, CHAIN) or (g.kind == DENSE and g.k == 1)):
@@ -230,6 +232,8 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
             e = garr[gi]
             e["kind"] = g.kind
             e["k"] = g.k
+            if g.kind != DIAG and any(local_of.get(b, 99) < low_bits for b in g.bits):
+                low_regs = True
             if g.kind == DIAG:
                 assert g.k <= 6, "diagonal tables are limited to 6 bits"
                 for j, b in enumerate(g.bits):
@@ -286,7 +290,8 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
         cnt = mat_off - int(ps["mat_begin"])
         ps["mat_count"] = cnt if (not any_batched and cnt <= 4096) else 0   # staged in shared memory
         # -1: lean-eligible pass, matrices staged or per batch member (tqb_run_passes picks tile_pass_lean_kernel when the tile streams)
-        ps["max_dense_k"] = -1 if (lean and (any_batched or (ps["mat_count"] > 0 and cnt <= 1024))) else maxk
+        # -2: the same with the padded tile layout (tqb_core.cuh pidx)
+        ps["max_dense_k"] = (-2 if low_regs else -1) if (lean and (any_batched or (ps["mat_count"] > 0 and cnt <= 1024))) else maxk
     flat = np.concatenate(mats) if mats else np.zeros(0, dtype=C128)
     return Program(n=n, passes=passes, gates=garr, mats=flat, n_gates_in=len(gates), tile=tile, order=order)
 
