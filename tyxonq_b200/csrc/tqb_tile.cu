@@ -345,20 +345,45 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
       __syncwarp();
       for (uint32_t j = lane; j < nruns; j += 32) bulk_load(dst + (size_t)j * (run_elems + pad_elems), src + roff[j], run_bytes, &full[b]);
     };
-    for (unsigned long long it = 0; it < (unsigned long long)(NB - 1) && it < count; ++it) issue_load(it);
+    // Every buffer cycles compute -> store drain -> refill.  The refill of a buffer is issued right behind its own
+    // stores, run by run: a lane waits only until ITS earlier store has been read out of shared memory
+    // (cp.async.bulk.wait_group.read counts per thread) and then loads the same run of the tile NB steps ahead, so the
+    // drain of one half of the tile overlaps the refill of the other (per-tile period (Tc + S + Ld) / NB with the drain
+    // S and the load latency Ld in sequence before; measured with 3-gate passes: 8.2 ms against 5.5 ms of transfer).
+    for (unsigned long long it = 0; it < (unsigned long long)NB && it < count; ++it) issue_load(it);
     for (unsigned long long it = 0; it < count; ++it) {
       const int b = (int)(it % NB);
-      if (it + NB - 1 < count) {
-        bulk_wait_read<0>();
-        __syncwarp();
-        issue_load(it + NB - 1);
-      }
-      mbar_wait(&done[b], (uint32_t)((it / NB) & 1));
+      mbar_wait(&done[b], (uint32_t)((it / NB) & 1));  // consumers finished tile it (their fence.proxy.async precedes the arrive)
+      const unsigned long long nxt = it + NB;
+      const bool refill = nxt < count;
       cplx<T> *dstg = tile_ptr(it);
-      const cplx<T> *srcs = reinterpret_cast<const cplx<T> *>(smem_raw + b * tile_stride);
-      if (!(dbg & 4))
-        for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], srcs + (size_t)j * (run_elems + pad_elems), run_bytes);
-      bulk_commit();
+      cplx<T> *buf = reinterpret_cast<cplx<T> *>(smem_raw + b * tile_stride);
+      if (nruns <= 64 && !(dbg & 6)) {
+        const cplx<T> *srcn = refill ? tile_ptr(nxt) : nullptr;
+        if (refill && lane == 0) mbar_expect_tx(&full[b], (uint32_t)tile_bytes);
+        __syncwarp();
+        const uint32_t j0 = (uint32_t)lane, j1 = (uint32_t)lane + 32u;
+        cplx<T> *s0 = buf + (size_t)j0 * (run_elems + pad_elems), *s1 = buf + (size_t)j1 * (run_elems + pad_elems);
+        if (j0 < nruns) bulk_store(dstg + roff[j0], s0, run_bytes);
+        bulk_commit();
+        if (j1 < nruns) bulk_store(dstg + roff[j1], s1, run_bytes);
+        bulk_commit();
+        if (refill) {
+          bulk_wait_read<1>();
+          if (j0 < nruns) bulk_load(s0, srcn + roff[j0], run_bytes, &full[b]);
+          bulk_wait_read<0>();
+          if (j1 < nruns) bulk_load(s1, srcn + roff[j1], run_bytes, &full[b]);
+        }
+      } else {
+        if (!(dbg & 4))
+          for (uint32_t j = lane; j < nruns; j += 32) bulk_store(dstg + roff[j], buf + (size_t)j * (run_elems + pad_elems), run_bytes);
+        bulk_commit();
+        if (refill) {
+          bulk_wait_read<0>();
+          __syncwarp();
+          issue_load(nxt);
+        }
+      }
     }
     bulk_wait_all0();
     return;
