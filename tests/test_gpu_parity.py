@@ -344,3 +344,42 @@ def test_batched_ansatz_expval_and_sampling(cuda_device):
             assert np.abs(st[b] - ref).max() < tol
             assert abs(ev[b] - O.expect_pauli_sum(ref, terms, w)) < tol * 50
             assert np.array_equal(idx[b], O.sample_indices(O.probabilities(st[b]), u[b]))
+
+
+def test_pauli_sum_on_shards_of_one_state(cuda_device):
+    """The per-rank call of ShardedState.expect_pauli_sum, on one GPU: the 2^g slices of a state are evaluated one
+    after the other with global_base = rank << n_local (xmasks local, Z factors anywhere) and summed; then the
+    world-size-1 ShardedState path itself (layout logic on CPU: tests/test_sharded_cpu.py)."""
+    import torch
+    from tyxonq_b200 import PauliSum
+    from tyxonq_b200.sharded import ShardedState, lower_and_fuse, plan_sharded
+    rng = np.random.default_rng(17)
+    n, g = 12, 2
+    n_local = n - g
+    terms = [[int(c) for c in rng.integers(0, 4, n)] for _ in range(30)]
+    for t in terms:                       # X / Y only on local qubits (qubit q = bit n-1-q: qubits >= g), Z / I on the rank bits
+        for q in range(g):
+            t[q] = 3 if t[q] in (2, 3) else 0
+    w = rng.normal(size=30).tolist()
+    st = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    st /= np.linalg.norm(st)
+    full = PauliSum.from_codes(terms, w)
+    sub = PauliSum(n_local, [(int(x), int(z), complex(c)) for gi, x in enumerate(full.group_x)
+                             for z, c in zip(full.term_z[full.group_ptr[gi]:full.group_ptr[gi + 1]],
+                                             full.term_coef[full.group_ptr[gi]:full.group_ptr[gi + 1]])])
+    for dt, tol in ((torch.complex128, TOL128), (torch.complex64, 1e-5)):
+        d = torch.from_numpy(st).to(cuda_device).to(dt)
+        tot = 0j
+        for r in range(1 << g):
+            shard = d[r << n_local:(r + 1) << n_local].contiguous()
+            tot += complex(sub.expectation(shard, global_base=r << n_local).cpu().numpy()[0])
+        assert abs(tot.real - O.expect_pauli_sum(st, terms, w)) < tol and abs(tot.imag) < tol
+    ops = O.hea_ops(n, 2, rng.uniform(-3, 3, 4 * n))
+    ss = ShardedState(n, torch.complex128, cuda_device)
+    ss.init_zero()
+    ss.run(plan_sharded(lower_and_fuse(ops, n), n, ss.g))
+    terms2 = [[int(c) for c in rng.integers(0, 4, n)] for _ in range(20)] + [[1] * n, [2] * n]
+    w2 = rng.normal(size=22).tolist()
+    ref, _ = O.evolve_ops(n, ops, mode="run")
+    e = complex(ss.expect_pauli_sum(PauliSum.from_codes(terms2, w2)))
+    assert abs(e.real - O.expect_pauli_sum(ref, terms2, w2)) < TOL128 and abs(e.imag) < TOL128

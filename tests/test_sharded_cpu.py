@@ -42,6 +42,20 @@ class _EmuLocal:
         z = np.array([np.sum(p * (1 - 2 * ((idx >> b) & 1))) for b in range(n_local)])
         return torch.from_numpy(z), torch.tensor(p.sum())
 
+    def pauli_local(self, state, sub, global_base):
+        """numpy statement of tqb_expect_pauli_sum on one shard: sum_j conj(psi_{j^x}) c (-1)^popc((base|j)&z) psi_j."""
+        psi = state.numpy().astype(np.complex128)
+        j = np.arange(psi.size, dtype=np.int64)
+        tot = 0j
+        for gi in range(sub.n_groups):
+            x = int(sub.group_x[gi])
+            assert x < psi.size, "xmask of a group handed to the local kernel must be local"
+            for t in range(int(sub.group_ptr[gi]), int(sub.group_ptr[gi + 1])):
+                zm = int(sub.term_z[t])
+                par = np.array([bin((int(global_base) | int(i)) & zm).count("1") & 1 for i in j])
+                tot += complex(sub.term_coef[t]) * np.sum(np.conj(psi[j ^ x]) * (1 - 2 * par) * psi)
+        return torch.tensor([tot.real, tot.imag], dtype=torch.float64)
+
 
 def _worker(rank, world, port, n, ops, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -225,3 +239,73 @@ def test_plan_restore_reaches_identity_from_any_layout():
                     m.update({v: k for k, v in m.items()})
                     cur = [m.get(p, p) for p in cur]
             assert cur == list(range(n))
+
+
+# ---- sharded Pauli sums: X / Y factors on rank bits need a layout change (or a basis rotation) first ----
+def _pauli_worker(rank, world, port, n, ops, terms, weights, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tyxonq_b200.pauli import PauliSum
+        from tyxonq_b200.sharded import ShardedState, lower_and_fuse, plan_sharded
+        st = ShardedState(n, torch.complex128, torch.device("cpu"), backend=_EmuLocal())
+        st.init_zero()
+        st.run(plan_sharded(lower_and_fuse(ops, n), n, st.g))
+        before = st.expect_z_all().numpy()
+        vals, nex = [], []
+        for tl, wl in zip(terms, weights):
+            vals.append(complex(st.expect_pauli_sum(PauliSum.from_codes(tl, wl))))
+            nex.append(st.pauli_exchanges)
+        after = st.expect_z_all().numpy()
+        assert np.abs(before - after).max() < 1e-12     # the state is the same state afterwards
+        # and gates can still be applied in whatever layout it is left in
+        st.apply(lower_and_fuse([("h", 0), ("cx", 0, n - 1)], n))
+        z2 = st.expect_z_all().numpy()
+        if rank == 0:
+            np.save(os.path.join(out_dir, "vals.npy"), np.array(vals))
+            np.save(os.path.join(out_dir, "nex.npy"), np.array(nex))
+            np.save(os.path.join(out_dir, "z2.npy"), z2)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 7), (4, 8)])
+def test_sharded_pauli_sum_matches_oracle(tmp_path, world, n):
+    rng = np.random.default_rng(100 * world + n)
+    ops = O.hea_ops(n, 2, rng.uniform(-3, 3, 4 * n))
+    heis_t, heis_w = O.heisenberg_terms(n, [(i, (i + 1) % n) for i in range(n)])
+    rand_t = [list(rng.integers(0, 4, n)) for _ in range(12)]
+    rand_w = list(rng.uniform(-1, 1, 12))
+    wide_t = [[1] * n, [2] * n, [1, 2] * (n // 2) + [1] * (n % 2), [2] + [1] * (n - 1), [3] * n, [0] * n]
+    wide_w = [0.7, -0.4, 0.3, 0.2, 0.5, 1.5]
+    diag_t, diag_w = [[3 if q in (0, 1) else 0 for q in range(n)], [3] + [0] * (n - 1)], [0.9, -0.2]
+    sets = [(heis_t, list(heis_w)), (rand_t, rand_w), (wide_t, wide_w), (diag_t, diag_w)]
+    mp.spawn(_pauli_worker, args=(world, _free_port(), n, ops, [s[0] for s in sets], [s[1] for s in sets], str(tmp_path)),
+             nprocs=world, join=True)
+    ref, _ = O.evolve_ops(n, ops, mode="run")
+    vals = np.load(tmp_path / "vals.npy")
+    for (tl, wl), v in zip(sets, vals):
+        assert abs(v.imag) < 1e-12
+        assert abs(v.real - O.expect_pauli_sum(ref, tl, wl)) < 1e-12
+    nex = np.load(tmp_path / "nex.npy")
+    assert nex[3] == 0                                   # diagonal Hamiltonian: no exchange whatever the layout
+    ref2, _ = O.evolve_ops(n, list(ops) + [("h", 0), ("cx", 0, n - 1)], mode="run")
+    z2 = np.load(tmp_path / "z2.npy")
+    for q in range(n):
+        assert abs(z2[n - 1 - q] - O.expect_z(ref2, q, n)) < 1e-12
+
+
+def test_plan_localize_one_exchange_and_victim_choice():
+    from tyxonq_b200.sharded import plan_localize
+    n, g = 8, 2
+    phys = list(range(n))
+    assert plan_localize(phys, 0b00111111, n, g).segments == []          # already local
+    cost = [5, 0, 5, 5, 0, 5, 9, 9]
+    plan = plan_localize(phys, 0b11000000, n, g, cost)
+    assert plan.n_exchanges == 1 and len(plan.segments) == 1
+    n_local = n - g
+    assert all(plan.final_phys[b] < n_local for b in (6, 7))
+    assert sorted(l for l in range(n) if plan.final_phys[l] >= n_local) == [1, 4]   # the cheapest bits went away
+    with pytest.raises(RuntimeError):
+        plan_localize(phys, 0b11111110, n, g)

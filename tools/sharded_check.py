@@ -16,6 +16,7 @@ from tyxonq_b200 import _lib  # noqa: E402
 from tyxonq_b200 import program as P  # noqa: E402
 from tyxonq_b200.circuits import Circuit, hea_ops, trotter_ops, tfim_terms  # noqa: E402
 from tyxonq_b200.engine import StatevectorEngine  # noqa: E402
+from tyxonq_b200.pauli import PauliSum  # noqa: E402
 from tyxonq_b200.sharded import ShardedState, lower_and_fuse, plan_sharded  # noqa: E402
 
 
@@ -48,6 +49,11 @@ def main():
             sample_ms = t0.elapsed_time(t1)
             parts = [torch.empty_like(st.state) for _ in range(world)] if rank == 0 else None
             dist.gather(torch.view_as_real(st.state), [torch.view_as_real(x) for x in parts] if rank == 0 else None, dst=0)
+            # sharded Pauli sum with X / Y factors on every qubit (rank bits included): ring Heisenberg + fields
+            ham = PauliSum.from_pauli_list(n, [(c, [(p_, q), (p_, (q + 1) % n)]) for q in range(n) for p_, c in (("X", 0.5), ("Y", -0.3), ("Z", 0.8))]
+                                           + [(0.2, [("X", q)]) for q in range(n)] + [(0.1, [("Y", 0), ("Z", n // 2), ("X", n - 1)])])
+            e_sh = complex(st.expect_pauli_sum(ham))
+            n_pex = st.pauli_exchanges
             if rank == 0:
                 full = torch.cat(parts)
                 del parts
@@ -57,11 +63,13 @@ def main():
                 zr = P.expect_z_bits(ref)[0].cpu().numpy()
                 err = float(np.abs(z - zr).max())
                 amp_err = float((full - ref).abs().max())
-                good = err < tol and abs(float(nrm[0]) - 1.0) < tol and same and amp_err < tol
+                e_ref = complex(ham.expectation(ref).cpu().numpy()[0])
+                e_err = abs(e_sh - e_ref)
+                good = err < tol and abs(float(nrm[0]) - 1.0) < tol and same and amp_err < tol and e_err < tol * n
                 ok &= good
                 print(f"{name} n={n} world={world} {dt}: exchanges={plan.n_exchanges} segments={len(plan.segments)} max|dZ|={err:.2e} "
                       f"norm-1={float(nrm[0]) - 1.0:.2e} restored-state max|d|={amp_err:.2e} sharded sampler == single-GPU sampler: {same} "
-                      f"(restore + 4096 shots {sample_ms:.1f} ms) {'OK' if good else 'FAIL'}", flush=True)
+                      f"(restore + 4096 shots {sample_ms:.1f} ms) sharded <H> err={e_err:.2e} ({n_pex} exchanges) {'OK' if good else 'FAIL'}", flush=True)
                 del ref, full
             del st
             torch.cuda.empty_cache()

@@ -75,10 +75,11 @@ class ShardPlan:
     n_exchanges: int = 0
 
 
-def plan_sharded(gates: Sequence[LGate], n: int, g: int) -> ShardPlan:
-    """Split a gate list (logical index bits) into local segments separated by global<->local exchanges."""
+def plan_sharded(gates: Sequence[LGate], n: int, g: int, phys0: Optional[Sequence[int]] = None) -> ShardPlan:
+    """Split a gate list (logical index bits) into local segments separated by global<->local exchanges.
+    ``phys0``: the logical->physical map the state is in when the plan starts (default: identity)."""
     n_local = n - g
-    phys = list(range(n))                     # logical -> physical
+    phys = list(range(n)) if phys0 is None else list(phys0)      # logical -> physical
     remaining = list(range(len(gates)))
     segments: List[Segment] = []
     n_ex = 0
@@ -150,6 +151,41 @@ def plan_sharded(gates: Sequence[LGate], n: int, g: int) -> ShardPlan:
                 inv[a], inv[b] = lb, la
         segments.append(seg)
     return ShardPlan(n, g, segments, phys, n_ex)
+
+
+def plan_localize(phys_in: Sequence[int], need_mask: int, n: int, g: int, cost: Optional[Sequence[int]] = None) -> ShardPlan:
+    """One exchange that makes every logical bit of ``need_mask`` local: the all-to-all brings all g rank bits home and
+    sends g local victims away.  Victims are local logical bits outside ``need_mask`` with the smallest ``cost``
+    (e.g. how many pending Pauli groups flip that bit).  No segment if the mask is already local."""
+    n_local = n - g
+    phys = list(phys_in)
+    if g == 0 or all(phys[b] < n_local for b in _bits(need_mask)):
+        return ShardPlan(n, g, [], phys, 0)
+    inv = {p: l for l, p in enumerate(phys)}
+    cands = [l for l in range(n) if phys[l] < n_local and not (need_mask >> l) & 1]
+    if len(cands) < g:
+        raise RuntimeError("mask touches more than n - g qubits: it cannot be made local")
+    cands.sort(key=lambda l: (cost[l] if cost is not None else 0, -phys[l]))
+    victims = cands[:g]
+    seg = Segment([])
+    vict_set = set(victims)
+    free_top = [p for p in range(n_local - g, n_local) if inv[p] not in vict_set]
+    for v in victims:
+        pv = phys[v]
+        if pv >= n_local - g:
+            continue
+        pt = free_top.pop()
+        other = inv[pt]
+        seg.gates.append(LGate(SWAP, (pv, pt), X_MAT.reshape(4).copy(), pat_a=0b01, pat_b=0b10, name="bitswap"))
+        phys[v], phys[other] = pt, pv
+        inv[pt], inv[pv] = v, other
+    seg.exchange_after = True
+    for i in range(g):
+        a, b = n_local - g + i, n_local + i
+        la, lb = inv[a], inv[b]
+        phys[la], phys[lb] = b, a
+        inv[a], inv[b] = lb, la
+    return ShardPlan(n, g, [seg], phys, 1)
 
 
 def plan_restore(phys_in: Sequence[int], n: int, g: int) -> ShardPlan:
@@ -262,6 +298,7 @@ class ShardedState:
         self.programs: List[Any] = []
         self.backend = backend or _CudaLocal(self)
         self.exchange_s = 0.0
+        self.pauli_exchanges = 0           # exchanges the last expect_pauli_sum needed
 
     def init_zero(self) -> None:
         self.backend.init_local(self.state, self.n_local, self.global_base)
@@ -278,6 +315,12 @@ class ShardedState:
                 self.state, self.scratch = self.scratch, self.state
                 self.exchange_s += time.perf_counter() - t0
         self.phys = list(plan.final_phys)
+
+    def apply(self, gates: Sequence[LGate]) -> int:
+        """Apply more gates (logical bits) to the state in WHATEVER layout it is in now; returns the exchanges used."""
+        plan = plan_sharded(list(gates), self.n, self.g, phys0=self.phys)
+        self.run(plan, cache=False)
+        return plan.n_exchanges
 
     # -- sampling -------------------------------------------------------------------------
     def restore_layout(self) -> int:
@@ -343,9 +386,84 @@ class ShardedState:
             dist.all_reduce(out, group=self.group)
         return out
 
+    def expect_pauli_sum(self, ps: Any) -> torch.Tensor:
+        """<psi|H|psi> for a ``pauli.PauliSum`` over LOGICAL qubits (complex128 scalar tensor, same on every rank) -- the
+        sharded form of ``PauliSum.expectation`` (reference: kernels/pauli.py:74-87 + dynamics.py:117-126 on one device).
+        A term flips the bits of its xmask, so its partner amplitude lives on this rank iff the xmask is local in the
+        current layout; Z factors on rank bits only need ``global_base``.  Groups are evaluated layout by layout: all
+        groups whose xmask is local now go through one local kernel call, then ONE exchange (``plan_localize``) brings
+        the rank bits home and sends away the g local bits that the fewest pending groups flip, until none is pending.
+        An xmask on more than n - g qubits can never be local: its terms are measured after rotating g of its X/Y
+        factors into Z (H, or Sdg then H), and the rotation is undone afterwards.  One all-reduce at the end.
+        The layout (``self.phys``) may differ afterwards; the state itself is unchanged."""
+        from .pauli import PauliSum
+        if int(ps.n) != self.n:
+            raise ValueError(f"PauliSum on {ps.n} qubits, state on {self.n}")
+        n, n_local, g = self.n, self.n_local, self.g
+        gx = [int(x) for x in ps.group_x]
+        pending = list(range(len(gx)))
+        acc = torch.zeros(2, dtype=torch.float64, device=self.device)
+        self.pauli_exchanges = 0
+
+        def terms_of(gi: int) -> List[Tuple[int, int, complex]]:
+            a, b = int(ps.group_ptr[gi]), int(ps.group_ptr[gi + 1])
+            return [(gx[gi], int(ps.term_z[t]), complex(ps.term_coef[t])) for t in range(a, b)]
+
+        def eval_local(terms: List[Tuple[int, int, complex]]) -> None:
+            nonlocal acc
+            sub = PauliSum(n_local, [(_remap_mask(x, self.phys), _remap_mask(z, self.phys), c) for x, z, c in terms])
+            acc = acc + self.backend.pauli_local(self.state, sub, self.global_base)
+
+        def localize(mask: int, groups: Sequence[int]) -> None:
+            cost = [sum((gx[gi] >> l) & 1 for gi in groups) for l in range(n)]
+            plan = plan_localize(self.phys, mask, n, g, cost)
+            if plan.segments:
+                self.run(plan, cache=False)
+                self.pauli_exchanges += plan.n_exchanges
+
+        wide = [gi for gi in pending if bin(gx[gi]).count("1") > n_local]
+        pending = [gi for gi in pending if gi not in set(wide)]
+        while pending:
+            now = [gi for gi in pending if _remap_mask(gx[gi], self.phys) < (1 << n_local)]
+            if now:
+                eval_local([t for gi in now for t in terms_of(gi)])
+                done = set(now)
+                pending = [gi for gi in pending if gi not in done]
+                continue
+            localize(gx[pending[0]], pending)
+        for gi in wide:
+            by_basis: dict = {}
+            rot = _bits(gx[gi])[-g:]                     # g of the flipped bits: these factors are rotated to Z
+            rmask = sum(1 << b for b in rot)
+            for x, z, c in terms_of(gi):
+                by_basis.setdefault(z & rmask, []).append((x, z, c))
+            for ymask, terms in by_basis.items():
+                fwd, bwd = [], []
+                for b in rot:
+                    q = n - 1 - b
+                    if (ymask >> b) & 1:
+                        fwd += [("sdg", q), ("h", q)]
+                        bwd += [("h", q), ("s", q)]
+                    else:
+                        fwd += [("h", q)]
+                        bwd += [("h", q)]
+                ny = bin(ymask).count("1")
+                self.pauli_exchanges += self.apply(lower_and_fuse(fwd, n))
+                rterms = [(x & ~rmask, (z & ~rmask) | rmask, c / (1j ** ny)) for x, z, c in terms]
+                localize(gx[gi] & ~rmask, [])
+                eval_local(rterms)
+                self.pauli_exchanges += self.apply(lower_and_fuse(bwd, n))
+        if self.world > 1:
+            dist.all_reduce(acc, group=self.group)
+        return torch.view_as_complex(acc.reshape(1, 2))[0]
+
 
 class _CudaLocal:
     """Local work of one rank on its GPU: the fused passes and reductions of libtyxonq_b200.so."""
+
+    def pauli_local(self, state: torch.Tensor, sub: Any, global_base: int) -> torch.Tensor:
+        """(re, im) float64 [2] of sum_j conj(psi_{j^x}) phase(global_base | j) psi_j over this shard (tqb_expect_pauli_sum)."""
+        return torch.view_as_real(sub.expectation(state, global_base=global_base)).reshape(-1)[:2]
 
     def zmasks_local(self, state: torch.Tensor, masks: Sequence[int], global_base: int) -> torch.Tensor:
         from . import program as P
