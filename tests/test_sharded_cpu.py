@@ -309,3 +309,17 @@ def test_plan_localize_one_exchange_and_victim_choice():
     assert sorted(l for l in range(n) if plan.final_phys[l] >= n_local) == [1, 4]   # the cheapest bits went away
     with pytest.raises(RuntimeError):
         plan_localize(phys, 0b11111110, n, g)
+    # six flipped bits, one of them on a rank bit, and only ONE spare local bit: the other spare bit is itself on a
+    # rank bit, so it must come home first (two exchanges)
+    mask = 0b10111110
+    plan = plan_localize(phys, mask, n, g)
+    assert plan.n_exchanges == 2
+    assert all(plan.final_phys[b] < n_local for b in range(n) if (mask >> b) & 1)
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        n2, g2 = int(rng.integers(8, 13)), int(rng.integers(1, 4))
+        ph = [int(v) for v in rng.permutation(n2)]
+        bits = rng.choice(n2, size=int(rng.integers(0, n2 - g2 + 1)), replace=False)
+        mk = sum(1 << int(b) for b in bits)
+        pl = plan_localize(ph, mk, n2, g2)
+        assert sorted(pl.final_phys) == list(range(n2)) and all(pl.final_phys[int(b)] < n2 - g2 for b in bits)

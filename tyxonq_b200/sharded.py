@@ -153,20 +153,11 @@ def plan_sharded(gates: Sequence[LGate], n: int, g: int, phys0: Optional[Sequenc
     return ShardPlan(n, g, segments, phys, n_ex)
 
 
-def plan_localize(phys_in: Sequence[int], need_mask: int, n: int, g: int, cost: Optional[Sequence[int]] = None) -> ShardPlan:
-    """One exchange that makes every logical bit of ``need_mask`` local: the all-to-all brings all g rank bits home and
-    sends g local victims away.  Victims are local logical bits outside ``need_mask`` with the smallest ``cost``
-    (e.g. how many pending Pauli groups flip that bit).  No segment if the mask is already local."""
+def _exchange_segment(phys: List[int], victims: Sequence[int], n: int, g: int) -> Segment:
+    """Segment that moves the logical bits ``victims`` (local, len g) to the top g local positions with in-tile bit
+    swaps and then exchanges them with the g rank bits; ``phys`` is updated in place."""
     n_local = n - g
-    phys = list(phys_in)
-    if g == 0 or all(phys[b] < n_local for b in _bits(need_mask)):
-        return ShardPlan(n, g, [], phys, 0)
     inv = {p: l for l, p in enumerate(phys)}
-    cands = [l for l in range(n) if phys[l] < n_local and not (need_mask >> l) & 1]
-    if len(cands) < g:
-        raise RuntimeError("mask touches more than n - g qubits: it cannot be made local")
-    cands.sort(key=lambda l: (cost[l] if cost is not None else 0, -phys[l]))
-    victims = cands[:g]
     seg = Segment([])
     vict_set = set(victims)
     free_top = [p for p in range(n_local - g, n_local) if inv[p] not in vict_set]
@@ -185,7 +176,32 @@ def plan_localize(phys_in: Sequence[int], need_mask: int, n: int, g: int, cost: 
         la, lb = inv[a], inv[b]
         phys[la], phys[lb] = b, a
         inv[a], inv[b] = lb, la
-    return ShardPlan(n, g, [seg], phys, 1)
+    return seg
+
+
+def plan_localize(phys_in: Sequence[int], need_mask: int, n: int, g: int, cost: Optional[Sequence[int]] = None) -> ShardPlan:
+    """Exchanges that make every logical bit of ``need_mask`` local: the all-to-all brings all g rank bits home and
+    sends g local victims away.  Victims are local logical bits outside ``need_mask`` with the smallest ``cost``
+    (e.g. how many pending Pauli groups flip that bit).  No segment if the mask is already local; one exchange when
+    g bits outside the mask are local now; two when some of them sit on rank bits themselves (the first exchange sends
+    g mask bits away to bring every rank bit home)."""
+    n_local = n - g
+    phys = list(phys_in)
+    if g == 0 or all(phys[b] < n_local for b in _bits(need_mask)):
+        return ShardPlan(n, g, [], phys, 0)
+    if n - bin(need_mask).count("1") < g:
+        raise RuntimeError("mask touches more than n - g qubits: it cannot be made local")
+    segments: List[Segment] = []
+    cands = [l for l in range(n) if phys[l] < n_local and not (need_mask >> l) & 1]
+    if len(cands) < g:
+        inside = [l for l in range(n) if phys[l] < n_local and (need_mask >> l) & 1]
+        if len(inside) < g:
+            raise RuntimeError("not enough local qubits to exchange")
+        segments.append(_exchange_segment(phys, inside[:g], n, g))
+        cands = [l for l in range(n) if phys[l] < n_local and not (need_mask >> l) & 1]
+    cands.sort(key=lambda l: (cost[l] if cost is not None else 0, -phys[l]))
+    segments.append(_exchange_segment(phys, cands[:g], n, g))
+    return ShardPlan(n, g, segments, phys, len(segments))
 
 
 def plan_restore(phys_in: Sequence[int], n: int, g: int) -> ShardPlan:
