@@ -323,3 +323,60 @@ def test_plan_localize_one_exchange_and_victim_choice():
         mk = sum(1 << int(b) for b in bits)
         pl = plan_localize(ph, mk, n2, g2)
         assert sorted(pl.final_phys) == list(range(n2)) and all(pl.final_phys[int(b)] < n2 - g2 for b in bits)
+
+
+# ---- seam B1 over ranks: ShardedStatevectorEngine.run / expval, called collectively ----
+def _engine_worker(rank, world, port, n, ops, uniforms, ham, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import json
+        from tests.conftest import FakeCircuit
+        from tyxonq_b200 import ShardedStatevectorEngine
+        eng = ShardedStatevectorEngine(device="cpu", local_backend=_EmuSampler())
+        c = FakeCircuit(n, ops)
+        r_counts = eng.run(c, shots=len(uniforms), uniforms=uniforms)
+        r_exp = eng.run(c, shots=0)
+        r_seed = eng.run(c, shots=64, seed=11)          # rank 0 draws, everyone gets the same uniforms
+        e = eng.expval(c, ham)
+        with pytest.raises(NotImplementedError):
+            eng.run(FakeCircuit(n, list(ops) + [("reset", 0)]), shots=0)
+        with open(os.path.join(out_dir, f"res{rank}.json"), "w") as f:
+            json.dump({"counts": r_counts, "exp": r_exp, "seed": r_seed, "e": e, "nex": eng.last_exchanges}, f)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 8), (4, 9)])
+def test_sharded_engine_run_contract(tmp_path, world, n):
+    import json
+    rng = np.random.default_rng(7 * world + n)
+    ops = O.hea_ops(n, 2, rng.uniform(-3, 3, 4 * n)) + [("cry", 0, n - 1, 0.7), ("measure_z", 0), ("rxx", 1, n - 2, 0.4)]
+    ops += [("measure_z", q) for q in range(1, n)]
+    u = rng.random(200)
+    ham = [(0.5, [("X", 0), ("X", 1)]), (-0.3, [("Y", 0), ("Z", n - 1)]), (0.8, [("Z", 1)]), (0.25, []), (0.4, [("Y", n - 1), ("Y", n - 2)])]
+    mp.spawn(_engine_worker, args=(world, _free_port(), n, ops, u, ham, str(tmp_path)), nprocs=world, join=True)
+    res = [json.load(open(tmp_path / f"res{r}.json")) for r in range(world)]
+    assert all(r == res[0] for r in res[1:])            # every rank holds the same result
+    ref, measures = O.evolve_ops(n, ops, mode="run")
+    want = O.sample_indices(ref.real ** 2 + ref.imag ** 2, u, block=_BLK)
+    assert res[0]["counts"]["result"] == O.counts_from_indices(want, n)
+    assert res[0]["counts"]["metadata"] == {"shots": 200, "backend": "b200-sharded", "three_level": False}
+    exp = O.run_expectations(n, ops)
+    assert set(res[0]["exp"]["expectations"]) == set(exp)
+    for k, v in exp.items():
+        assert abs(res[0]["exp"]["expectations"][k] - v) < 1e-12
+    want64 = O.sample_indices(ref.real ** 2 + ref.imag ** 2, np.random.default_rng(11).random(64), block=_BLK)
+    assert res[0]["seed"]["result"] == O.counts_from_indices(want64, n)
+    codes = {"X": 1, "Y": 2, "Z": 3}
+    terms, w = [], []
+    for c, lst in ham:
+        t = [0] * n
+        for p_, q in lst:
+            t[q] = codes[p_]
+        terms.append(t); w.append(c)
+    # expval follows engine.state(): the op set of "state" mode (no cry, engine.py:918-1038)
+    psi_state, _ = O.evolve_ops(n, ops, mode="state")
+    assert abs(res[0]["e"] - O.expect_pauli_sum(psi_state, terms, w)) < 1e-12
+    assert res[0]["nex"] >= 1

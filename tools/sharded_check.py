@@ -74,6 +74,29 @@ def main():
             del st
             torch.cuda.empty_cache()
             dist.barrier()
+    # seam B1 over ranks: ShardedStatevectorEngine.run / expval against the single-GPU engine on the same circuit
+    from tyxonq_b200 import ShardedStatevectorEngine
+    ops = hea_ops(n, layers, np.random.default_rng(2).uniform(-3, 3, 2 * layers * n)) + [("measure_z", q) for q in range(n)]
+    circ = Circuit(n, ops)
+    u = np.random.default_rng(5).random(2048)
+    ham = [(0.5, [("X", q), ("X", (q + 1) % n)]) for q in range(n)] + [(-0.3, [("Y", 0), ("Z", n - 1)]), (0.25, [])] \
+        + [(0.4, [("Z", q)]) for q in range(n)]
+    seng = ShardedStatevectorEngine(device=dev)
+    r_counts = seng.run(circ, shots=2048, uniforms=u)
+    r_exp = seng.run(circ, shots=0)
+    e_sh = seng.expval(circ, ham)
+    if rank == 0:
+        eng = StatevectorEngine("b200", device=dev)
+        w_counts = eng.run(circ, shots=2048, uniforms=u)
+        w_exp = eng.run(circ, shots=0)
+        e_one = eng.expval(circ, ham)
+        same_counts = r_counts["result"] == w_counts["result"]
+        dz = max(abs(r_exp["expectations"][k] - v) for k, v in w_exp["expectations"].items())
+        good = same_counts and dz < 1e-10 and abs(e_sh - e_one) < 1e-10 and set(r_exp["expectations"]) == set(w_exp["expectations"])
+        ok &= good
+        print(f"ShardedStatevectorEngine n={n} world={world}: counts == single-GPU counts: {same_counts} ({len(r_counts['result'])} bitstrings), "
+              f"max|dZ|={dz:.2e}, expval err={abs(e_sh - e_one):.2e}, exchanges={seng.last_exchanges} {'OK' if good else 'FAIL'}", flush=True)
+    dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
         sys.exit(1)

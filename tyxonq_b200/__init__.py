@@ -26,6 +26,7 @@ _LAZY = {
     "PauliSum": ("pauli", "PauliSum"),
     "B200Backend": ("backend", "B200Backend"),
     "DensityMatrixEngine": ("density", "DensityMatrixEngine"),
+    "ShardedStatevectorEngine": ("sharded_engine", "ShardedStatevectorEngine"),
     "install": ("install", "install"),
     "uninstall": ("install", "uninstall"),
 }
@@ -36,7 +37,7 @@ def __getattr__(name: str):
         import importlib
         mod, attr = _LAZY[name]
         return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
-    if name in ("kernels", "engine", "pauli", "program", "planner", "gates", "autograd", "ucc", "vqe", "sharded", "circuits", "backend", "batched", "measure", "noise", "density"):
+    if name in ("kernels", "engine", "pauli", "program", "planner", "gates", "autograd", "ucc", "vqe", "sharded", "sharded_engine", "circuits", "backend", "batched", "measure", "noise", "density"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

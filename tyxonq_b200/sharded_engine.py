@@ -1,0 +1,120 @@
+"""Seam B1 over several GPUs: the ``run(circuit, shots)`` contract of the reference's statevector engine
+(devices/simulators/statevector/engine.py:43-473) for states that do not fit one B200.
+
+Launched under ``torchrun`` (one rank per GPU, ``torch.distributed`` initialised): EVERY rank constructs the engine and
+calls ``run`` / ``expval`` with the same circuit -- the calls are collective -- and every rank gets the same result
+dict.  The state is sharded by its g = log2(world) highest index bits (``sharded.ShardedState``); gates on global
+qubits cost amplitude exchanges planned by ``sharded.plan_sharded``; counts come from the blocked-CDF sampler across
+ranks and equal the single-GPU (and the reference-order) counts bit for bit given the same uniforms; <Z_q> and Pauli
+sums are local reductions plus one all-reduce.  Ops outside the sharded path (kraus, project_z / reset, pulses,
+noise models) raise: there is no fallback.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .gates import lower_op
+from .sharded import ShardedState, plan_sharded
+
+_NOT_SHARDED = ("kraus", "project_z", "reset", "pulse", "pulse_inline")
+
+
+class ShardedStatevectorEngine:
+    name = "statevector"
+    capabilities = {"supports_shots": True, "sharded": True}
+
+    def __init__(self, backend_name: str | None = None, *, device: str | torch.device | None = None,
+                 dtype: torch.dtype = torch.complex128, group: Any = None, local_backend: Optional[Any] = None) -> None:
+        """``local_backend``: the per-rank executor handed to ShardedState (default: this package's CUDA kernels)."""
+        self.backend_name = backend_name or "b200"
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("ShardedStatevectorEngine needs a CUDA device (no CPU fallback)")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.group = group
+        self.local_backend = local_backend
+        self.last_state: Optional[ShardedState] = None
+        self.last_exchanges = 0
+
+    @property
+    def backend_label(self) -> str:
+        return f"{self.backend_name}-sharded"
+
+    # ------------------------------------------------------------------------------------
+    def _evolve(self, circuit: Any, mode: str = "run"):
+        n = int(getattr(circuit, "num_qubits", 0))
+        if getattr(circuit, "_initial_state", None) is not None:
+            raise NotImplementedError("a host-side initial state cannot seed a sharded run (it would not fit one device)")
+        ucache = getattr(circuit, "_unitary_cache", {}) or {}
+        measures: List[int] = []
+        gates = []
+        for op in getattr(circuit, "ops", []):
+            if not isinstance(op, (list, tuple)) or not op:
+                continue
+            nm = op[0]
+            if nm in _NOT_SHARDED:
+                raise NotImplementedError(f"op {nm!r} is outside the sharded path; run it on one GPU (StatevectorEngine)")
+            if nm == "measure_z":
+                measures.append(int(op[1]))
+                continue
+            fixed = tuple(float(a.detach().cpu()) if isinstance(a, torch.Tensor) else a for a in op)
+            g = lower_op(fixed, n, mode=mode, unitary_cache=ucache)   # unknown ops: silently skipped (engine.py:372-374)
+            if g is not None:
+                gates.append(g)
+        from .fuse import fuse
+        st = ShardedState(n, self.dtype, self.device, self.group, backend=self.local_backend)
+        plan = plan_sharded(fuse(gates), n, st.g)
+        st.init_zero()
+        st.run(plan, cache=False)
+        self.last_state = st
+        self.last_exchanges = plan.n_exchanges
+        return st, measures
+
+    def _uniforms(self, shots: int, kwargs: Dict[str, Any]) -> torch.Tensor:
+        """The same uniforms on every rank: host-supplied ones as they are; else rank 0 draws them (fresh generator like
+        nb.rng(None), engine.py:381, or ``seed``) and broadcasts."""
+        u = kwargs.get("uniforms")
+        if u is not None:
+            return torch.from_numpy(np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(-1)))
+        t = torch.from_numpy(np.random.default_rng(kwargs.get("seed")).random(shots)).to(self.device)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        return t
+
+    def run(self, circuit: Any, shots: int | None = None, **kwargs: Any) -> Dict[str, Any]:
+        shots = int(shots or 0)
+        if kwargs.get("three_level"):
+            raise NotImplementedError("three_level mode is outside the B200 hot path")
+        if kwargs.get("use_noise"):
+            raise NotImplementedError("noise models are not part of the sharded path; run them on one GPU")
+        n = int(getattr(circuit, "num_qubits", 0))
+        st, measures = self._evolve(circuit)
+        if shots > 0 and measures:
+            counts = st.counts(self._uniforms(shots, kwargs))
+            return {"result": counts, "metadata": {"shots": shots, "backend": self.backend_label, "three_level": False}}
+        expectations: Dict[str, float] = {}
+        if measures:
+            z = st.expect_z_all().cpu().numpy()
+            for q in measures:
+                expectations[f"Z{q}"] = float(z[n - 1 - q])
+        return {"expectations": expectations, "metadata": {"shots": shots, "backend": self.backend_label}}
+
+    def expval(self, circuit: Any, obs: Any, **kwargs: Any) -> float:
+        """<psi|H|psi> for a PauliSum, a [(coeff, [(P, q), ...]), ...] list or an OpenFermion-style operator
+        (engine.py:475-484 without the sparse matrix)."""
+        from .pauli import PauliSum
+        n = int(getattr(circuit, "num_qubits", 0))
+        if isinstance(obs, PauliSum):
+            ham = obs
+        elif hasattr(obs, "terms"):
+            ham = PauliSum.from_qubit_operator(n, obs)
+        else:
+            ham = PauliSum.from_pauli_list(n, obs)
+        st, _ = self._evolve(circuit, "state")
+        return float(st.expect_pauli_sum(ham).real)
