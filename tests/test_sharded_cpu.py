@@ -340,10 +340,12 @@ def _engine_worker(rank, world, port, n, ops, uniforms, ham, out_dir):
         r_exp = eng.run(c, shots=0)
         r_seed = eng.run(c, shots=64, seed=11)          # rank 0 draws, everyone gets the same uniforms
         e = eng.expval(c, ham)
+        amps = [eng.amplitude(c, format(i, f"0{n}b")) for i in (0, 1, (1 << n) - 1, 0b1011 << (n - 4), 37)]
         with pytest.raises(NotImplementedError):
             eng.run(FakeCircuit(n, list(ops) + [("reset", 0)]), shots=0)
         with open(os.path.join(out_dir, f"res{rank}.json"), "w") as f:
-            json.dump({"counts": r_counts, "exp": r_exp, "seed": r_seed, "e": e, "nex": eng.last_exchanges}, f)
+            json.dump({"counts": r_counts, "exp": r_exp, "seed": r_seed, "e": e, "nex": eng.last_exchanges,
+                       "amps": [[a.real, a.imag] for a in amps]}, f)
     finally:
         dist.destroy_process_group()
 
@@ -380,3 +382,5 @@ def test_sharded_engine_run_contract(tmp_path, world, n):
     psi_state, _ = O.evolve_ops(n, ops, mode="state")
     assert abs(res[0]["e"] - O.expect_pauli_sum(psi_state, terms, w)) < 1e-12
     assert res[0]["nex"] >= 1
+    for i, (re, im) in zip((0, 1, (1 << n) - 1, 0b1011 << (n - 4), 37), res[0]["amps"]):
+        assert abs(complex(re, im) - psi_state[i]) < 1e-12

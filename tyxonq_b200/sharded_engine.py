@@ -105,6 +105,25 @@ class ShardedStatevectorEngine:
                 expectations[f"Z{q}"] = float(z[n - 1 - q])
         return {"expectations": expectations, "metadata": {"shots": shots, "backend": self.backend_label}}
 
+    def amplitude(self, circuit: Any, bitstring: str) -> complex:
+        """psi[int(bitstring, 2)] (engine.py:1052-1060): the owner rank reads one amplitude, everyone gets it."""
+        n = int(getattr(circuit, "num_qubits", 0))
+        if len(bitstring) != n:
+            raise ValueError(f"bitstring of length {len(bitstring)} for {n} qubits")
+        st, _ = self._evolve(circuit, "state")
+        idx = int(bitstring, 2) if n else 0
+        pidx = 0
+        for l in range(n):
+            pidx |= ((idx >> l) & 1) << st.phys[l]
+        out = torch.zeros(2, dtype=torch.float64, device=self.device)
+        if (pidx >> st.n_local) == st.rank:
+            a = st.state[pidx & ((1 << st.n_local) - 1)]
+            out[0], out[1] = a.real.to(torch.float64), a.imag.to(torch.float64)
+        if st.world > 1:
+            dist.all_reduce(out, group=self.group)
+        v = out.cpu().numpy()
+        return complex(float(v[0]), float(v[1]))
+
     def expval(self, circuit: Any, obs: Any, **kwargs: Any) -> float:
         """<psi|H|psi> for a PauliSum, a [(coeff, [(P, q), ...]), ...] list or an OpenFermion-style operator
         (engine.py:475-484 without the sparse matrix)."""
