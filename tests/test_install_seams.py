@@ -37,6 +37,22 @@ def test_install_rebinds_and_restores():
                 assert callable(getattr(eng_cls, meth))
         finally:
             tyxonq_b200.uninstall()
+        # sharded=True: the sharded engine only when a process group with more than one rank is live
+        inst = sys.modules["tyxonq_b200.install"]
+        tyxonq_b200.install(sharded=True)
+        try:
+            assert driver._select_engine("statevector") is tyxonq_b200.StatevectorEngine
+            real = inst._multi_rank
+            inst._multi_rank = lambda: True
+            try:
+                cls = driver._select_engine("statevector")
+                assert cls is tyxonq_b200.ShardedStatevectorEngine and cls.name == "statevector"
+                for meth in ("run", "state", "amplitude", "expval", "state_shard"):
+                    assert callable(getattr(cls, meth))
+            finally:
+                inst._multi_rank = real
+        finally:
+            tyxonq_b200.uninstall()
         assert ref_engine.StatevectorEngine is ref_cls
         assert ref_kernels.apply_1q_statevector is ref_fn
         assert driver._select_engine("statevector") is ref_cls

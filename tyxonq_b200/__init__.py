@@ -36,7 +36,13 @@ def __getattr__(name: str):
     if name in _LAZY:
         import importlib
         mod, attr = _LAZY[name]
-        return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
+        obj = getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
+        # importing the submodule ``install`` binds the MODULE to this package's attribute ``install``: rebind the
+        # function, or a second ``tyxonq_b200.install()`` would find the module
+        globals()[name] = obj
+        if mod == "install":
+            globals()["install"] = getattr(importlib.import_module(f"{__name__}.install"), "install")
+        return obj
     if name in ("kernels", "engine", "pauli", "program", "planner", "gates", "autograd", "ucc", "vqe", "sharded", "sharded_engine", "circuits", "backend", "batched", "measure", "noise", "density"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")

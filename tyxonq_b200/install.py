@@ -17,11 +17,18 @@ from typing import Any, Dict
 _saved: Dict[str, Any] = {}
 
 
-def install(set_backend: bool = False, density: bool = False) -> None:
+def _multi_rank() -> bool:
+    import torch.distributed as dist
+    return bool(dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+
+
+def install(set_backend: bool = False, density: bool = False, sharded: bool = False) -> None:
     """``set_backend=True`` additionally makes ``B200Backend`` the process-global numerics backend (seam B3,
     numerics/__init__.py:20-36), so that ``Circuit.state()`` returns device tensors and ``K.value_and_grad`` runs the
     adjoint sweep.  ``density=True`` also routes ``device="density_matrix"`` (driver.py:20-30) to the
-    density-matrix engine that rides on the same kernels (density.py; at most 17 qubits)."""
+    density-matrix engine that rides on the same kernels (density.py; at most 17 qubits).  ``sharded=True``: when the process
+    runs under ``torchrun`` with an initialised process group of more than one rank, "statevector" resolves to
+    ``ShardedStatevectorEngine`` (sharded_engine.py): every rank runs the same script, ``run`` is collective."""
     import importlib
     drv = importlib.import_module("tyxonq.devices.simulators.driver")
     eng_mod = importlib.import_module("tyxonq.devices.simulators.statevector.engine")
@@ -40,6 +47,9 @@ def install(set_backend: bool = False, density: bool = False) -> None:
     def _select_engine(device: str):
         name = device.split("::")[-1] if "::" in device else device
         if name in ("simulator:statevector", "statevector"):
+            if sharded and _multi_rank():
+                from .sharded_engine import ShardedStatevectorEngine
+                return ShardedStatevectorEngine
             return StatevectorEngine
         if density and name in ("simulator:density_matrix", "density_matrix"):
             from .density import DensityMatrixEngine

@@ -105,6 +105,22 @@ class ShardedStatevectorEngine:
                 expectations[f"Z{q}"] = float(z[n - 1 - q])
         return {"expectations": expectations, "metadata": {"shots": shots, "backend": self.backend_label}}
 
+    def state_shard(self, circuit: Any):
+        """(this rank's slice of psi in LOGICAL index order, global_base): amplitudes global_base .. global_base + 2^n_local
+        of the final state (engine.py:897-1039 for the part of the state this rank owns; the layout is restored first)."""
+        st, _ = self._evolve(circuit, "state")
+        st.restore_layout()
+        return st.state, st.global_base
+
+    def state(self, circuit: Any) -> Any:
+        """The reference's driver asks for the full state after a shots == 0 run (driver.py:115-126).  A sharded state is
+        never gathered: with one rank this is the device tensor; otherwise it raises (the driver then reports no
+        ``probabilities`` / ``statevector``) -- use ``state_shard``."""
+        st, _ = self._evolve(circuit, "state")
+        if st.world == 1:
+            return st.state
+        raise NotImplementedError("the state is sharded over ranks and is not gathered; use state_shard(circuit)")
+
     def amplitude(self, circuit: Any, bitstring: str) -> complex:
         """psi[int(bitstring, 2)] (engine.py:1052-1060): the owner rank reads one amplitude, everyone gets it."""
         n = int(getattr(circuit, "num_qubits", 0))
