@@ -343,6 +343,11 @@ def _engine_worker(rank, world, port, n, ops, uniforms, ham, out_dir):
         amps = [eng.amplitude(c, format(i, f"0{n}b")) for i in (0, 1, (1 << n) - 1, 0b1011 << (n - 4), 37)]
         with pytest.raises(NotImplementedError):
             eng.run(FakeCircuit(n, list(ops) + [("reset", 0)]), shots=0)
+        with pytest.raises(NotImplementedError):
+            eng.state(c)                                 # never gathered; the driver's shots == 0 epilogue gets no statevector
+        shard, base = eng.state_shard(c)
+        assert base == rank << (n - eng.last_state.g)
+        np.save(os.path.join(out_dir, f"eshard{rank}.npy"), shard.numpy())
         with open(os.path.join(out_dir, f"res{rank}.json"), "w") as f:
             json.dump({"counts": r_counts, "exp": r_exp, "seed": r_seed, "e": e, "nex": eng.last_exchanges,
                        "amps": [[a.real, a.imag] for a in amps]}, f)
@@ -382,5 +387,7 @@ def test_sharded_engine_run_contract(tmp_path, world, n):
     psi_state, _ = O.evolve_ops(n, ops, mode="state")
     assert abs(res[0]["e"] - O.expect_pauli_sum(psi_state, terms, w)) < 1e-12
     assert res[0]["nex"] >= 1
+    full = np.concatenate([np.load(tmp_path / f"eshard{r}.npy") for r in range(world)])
+    assert np.abs(full - psi_state).max() < 1e-12
     for i, (re, im) in zip((0, 1, (1 << n) - 1, 0b1011 << (n - 4), 37), res[0]["amps"]):
         assert abs(complex(re, im) - psi_state[i]) < 1e-12
