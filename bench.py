@@ -285,7 +285,8 @@ def own_arm(args) -> None:
         assert len(res["expectations"]) == n
         e2e = {"value": n_gates * norm / float(np.mean(ts)), "unit": "gates/s", "h2d_bytes_per_step": int(eng.last_h2d_bytes),
                "d2h_bytes_per_step": int(eng.last_d2h_bytes), "ms_per_step": 1e3 * float(np.mean(ts)),
-               "api": "StatevectorEngine.run(Circuit(n, ops), shots=0): plan + upload + passes + <Z_q> + D2H"}
+               "api": "StatevectorEngine.run(Circuit(n, ops), shots=0): plan + upload + passes + <Z_q> + D2H",
+               "expz_checksum": float(sum(res["expectations"].values()))}
     else:
         e2e = sb.e2e(args)
 

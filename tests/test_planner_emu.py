@@ -172,3 +172,33 @@ def test_lean_passes_padded_layout(dtype, m, L):
         psi0[0] = 1
         out = run_program_emulated(prog, psi0)
         assert np.abs(out - ref).max() < (1e-12 if dtype == np.complex128 else 3e-5)
+
+
+def test_streamed_chunks_are_the_same_program():
+    """compile_program_stream (what StatevectorEngine launches chunk by chunk) yields, chunk after chunk, exactly the
+    passes, gate descriptors and matrices of compile_program -- only the offsets restart at 0 in every chunk."""
+    from tests.conftest import random_ops
+    from tyxonq_b200.fuse import fuse
+    from tyxonq_b200.gates import lower_op
+    from tyxonq_b200.planner import TileConfig, compile_program, compile_program_stream, default_tile
+    rng = np.random.default_rng(21)
+    cases = [(14, O.hea_ops(14, 6, rng.uniform(-3, 3, 12 * 14))), (12, O.qaoa_ring_ops(12, 5, rng.uniform(-3, 3, 10))),
+             (10, random_ops(rng, 10, 250))]
+    for n, ops in cases:
+        lowered = [g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None]
+        for itemsize in (16, 8):
+            for chain in (None, False):
+                for tile in (default_tile(n, itemsize, 1), TileConfig(m=min(n, 6), L=2)):
+                    full = compile_program(fuse(list(lowered)), n, tile, itemsize=itemsize, chain=chain)
+                    for first, chunk in ((8, 32), (1, 1), (2, 3)):
+                        ps_all, g_all, m_all, go, mo = [], [], [], 0, 0
+                        for pr in compile_program_stream(fuse(list(lowered)), n, tile, itemsize=itemsize, chain=chain, first=first, chunk=chunk):
+                            ps, ga = pr.passes.copy(), pr.gates.copy()
+                            assert int(ps["gate_begin"][0]) == 0 and int(ps["mat_begin"][0]) == 0
+                            ps["gate_begin"] += go; ps["mat_begin"] += mo; ga["mat_off"] += mo
+                            ps_all.append(ps); g_all.append(ga); m_all.append(pr.mats)
+                            go += pr.gates.size; mo += pr.mats.size
+                            assert pr.tile == full.tile
+                        assert np.concatenate(ps_all).tobytes() == full.passes.tobytes()
+                        assert np.concatenate(g_all).tobytes() == full.gates.tobytes()
+                        assert np.concatenate(m_all).tobytes() == full.mats.tobytes()

@@ -72,14 +72,16 @@ class StatevectorEngine:
     def _flush(self, state: torch.Tensor, pending: List[LGate]) -> None:
         if pending:
             ptr, n, batch, dt, _ = P._prep(state)
-            from .planner import compile_program, default_tile
+            from .planner import compile_program_stream, default_tile
             from .fuse import fuse
             tile = self.tile or default_tile(n, state.element_size(), batch)
-            prog = compile_program(fuse(pending), n, tile, itemsize=state.element_size())
-            dp = P.DeviceProgram(prog, state.device, state.dtype)
-            dp.run(state)
-            self.last_h2d_bytes += dp.h2d_bytes
-            self.last_passes += prog.n_passes
+            # the passes are launched chunk by chunk (asynchronously, pinned uploads on the same stream): the host groups
+            # and packs chunk i + 1 while the GPU runs chunk i, so that only lowering, fusion and scheduling stay serial
+            for prog in compile_program_stream(fuse(pending), n, tile, itemsize=state.element_size()):
+                dp = P.DeviceProgram(prog, state.device, state.dtype)
+                dp.run(state)
+                self.last_h2d_bytes += dp.h2d_bytes
+                self.last_passes += prog.n_passes
             self.last_gates += len(pending)
             pending.clear()
 

@@ -172,11 +172,8 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
     return out
 
 
-def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_mats: int = 1, itemsize: int = 16,
-                    chain: Optional[bool] = None) -> Program:
-    """Pack scheduled gates into the ABI arrays.  ``batch_mats`` > 1: every gate's ``data`` has a
-    leading batch axis (one matrix per batch member) when ``gate.batched`` is set.  (``itemsize`` is accepted for call-site
-    symmetry; the descriptors do not depend on the state dtype.)"""
+def _prepare(gates: Sequence[LGate], n: int, tile: TileConfig, chain: Optional[bool]):
+    """Effective tile, the pass schedule (diagonals sunk to their consumers when chains are grouped) and the chain switch."""
     m_eff = min(tile.m, n)
     tile = TileConfig(m=m_eff, L=min(tile.L, m_eff), threads=tile.threads, ctas_per_sm=tile.ctas_per_sm,
                       max_gates=tile.max_gates, rot_layers=tile.rot_layers)
@@ -184,17 +181,60 @@ def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_m
     if chain is None:
         chain = bool(getattr(gates, "chain_after_schedule", False))
     if chain:
-        # group the 1-qubit / MUX gates of every pass into CHAIN gates now that their targets are known to be
-        # tile-local together (``order`` then no longer maps compiled gates to input gates)
-        from .fuse import group_pass, sink_diagonals
+        from .fuse import sink_diagonals
         sched = sink_diagonals(gates, sched)
-        grouped: List[LGate] = []
-        sched2 = []
-        for hb, chosen in sched:
-            sub = group_pass([gates[i] for i in chosen], set(range(tile.L)) | set(int(p) for p in hb), R_rot=tile.rot_layers)
-            sched2.append((hb, list(range(len(grouped), len(grouped) + len(sub)))))
-            grouped += sub
-        gates, sched = grouped, sched2
+    return tile, sched, chain
+
+
+def _group(gates: Sequence[LGate], sched, tile: TileConfig):
+    """Group the 1-qubit / MUX gates of every pass into CHAIN gates now that their targets are known to be
+    tile-local together (``order`` then no longer maps compiled gates to input gates)."""
+    from .fuse import group_pass
+    grouped: List[LGate] = []
+    sched2 = []
+    for hb, chosen in sched:
+        sub = group_pass([gates[i] for i in chosen], set(range(tile.L)) | set(int(p) for p in hb), R_rot=tile.rot_layers)
+        sched2.append((hb, list(range(len(grouped), len(grouped) + len(sub)))))
+        grouped += sub
+    return grouped, sched2
+
+
+def compile_program(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_mats: int = 1, itemsize: int = 16,
+                    chain: Optional[bool] = None) -> Program:
+    """Pack scheduled gates into the ABI arrays.  ``batch_mats`` > 1: every gate's ``data`` has a
+    leading batch axis (one matrix per batch member) when ``gate.batched`` is set.  ``itemsize`` (bytes per amplitude)
+    only decides which passes ask for the padded tile layout."""
+    tile, sched, chain = _prepare(gates, n, tile, chain)
+    if chain:
+        gates, sched = _group(gates, sched, tile)
+    return _pack(gates, sched, n, tile, batch_mats, itemsize)
+
+
+def compile_program_stream(gates: Sequence[LGate], n: int, tile: TileConfig, *, batch_mats: int = 1, itemsize: int = 16,
+                           chain: Optional[bool] = None, first: int = 8, chunk: int = 32):
+    """The same passes as ``compile_program`` as a sequence of Programs (``first`` passes, then ``chunk`` at a time), so
+    that a caller can launch a chunk while the host groups and packs the next one: scheduling is global and happens
+    before the first chunk, chain grouping and packing are per pass.  Concatenating the chunks' passes gives exactly
+    compile_program's passes."""
+    tile, sched, chain = _prepare(gates, n, tile, chain)
+    lo = 0
+    size = max(1, int(first))
+    while lo < len(sched):
+        part = sched[lo:lo + size]
+        if chain:
+            g2, part = _group(gates, part, tile)
+        else:
+            # re-index the chunk's gates from 0 so that the chunk is a self-contained Program
+            idx = [i for _, c in part for i in c]
+            pos = {i: j for j, i in enumerate(idx)}
+            g2, part = [gates[i] for i in idx], [(hb, [pos[i] for i in c]) for hb, c in part]
+        yield _pack(g2, part, n, tile, batch_mats, itemsize)
+        lo += size
+        size = max(1, int(chunk))
+
+
+def _pack(gates: Sequence[LGate], sched, n: int, tile: TileConfig, batch_mats: int, itemsize: int) -> Program:
+    m_eff = tile.m
     ng = sum(len(c) for _, c in sched)
     passes = np.zeros(len(sched), dtype=_lib.PASS_DTYPE)
     garr = np.zeros(ng, dtype=_lib.GATE_DTYPE)
