@@ -97,6 +97,8 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
     needs = [g.local_mask & ~low for g in gates]   # bits that must become high tile bits
     is_diag = [g.kind == DIAG for g in gates]
 
+    max_gates = tile.max_gates
+
     def select(start: int, window: int) -> Tuple[List[int], int, int, int]:
         """window < 0: budget mode (i); else only gates whose needs lie inside ``window`` run.  Returns
         (chosen, H, number of high bits used, number of non-diagonal gates chosen)."""
@@ -105,40 +107,42 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
         blocked = 0      # bits of skipped gates
         blocked_nd = 0   # ... of skipped non-diagonal gates only
         chosen: List[int] = []
+        push = chosen.append
         nd = 0
-        i = start
         seen = 0
-        while i < N and seen < 4096:
-            if not done[i]:
-                seen += 1
-                mk = masks[i]
-                if is_diag[i]:
-                    if mk & blocked_nd:
-                        blocked |= mk
-                    else:
-                        chosen.append(i)
-                elif mk & blocked:
+        budget = window < 0
+        outside = ~window
+        for i in range(start, N):
+            if done[i]:
+                continue
+            seen += 1
+            mk = masks[i]
+            if is_diag[i]:
+                if mk & blocked_nd:
+                    blocked |= mk
+                else:
+                    push(i)
+            elif mk & blocked:
+                blocked |= mk
+                blocked_nd |= mk
+            else:
+                need = needs[i] & ~H
+                if budget:
+                    cnt = need.bit_count()
+                    ok = nH + cnt <= h
+                else:
+                    ok = not (need & outside)
+                    cnt = need.bit_count() if ok else 0
+                if ok:
+                    H |= need
+                    nH += cnt
+                    push(i)
+                    nd += 1
+                else:
                     blocked |= mk
                     blocked_nd |= mk
-                else:
-                    need = needs[i] & ~H
-                    if window >= 0:
-                        ok = not (need & ~window)
-                        cnt = bin(need).count("1") if ok else 0
-                    else:
-                        cnt = bin(need).count("1")
-                        ok = nH + cnt <= h
-                    if ok:
-                        H |= need
-                        nH += cnt
-                        chosen.append(i)
-                        nd += 1
-                    else:
-                        blocked |= mk
-                        blocked_nd |= mk
-                if blocked_nd == all_bits or len(chosen) >= tile.max_gates:
-                    break
-            i += 1
+            if blocked_nd == all_bits or len(chosen) >= max_gates or seen >= 4096:
+                break
         return chosen, H, nH, nd
 
     while remaining:
