@@ -391,3 +391,43 @@ def test_sharded_engine_run_contract(tmp_path, world, n):
     assert np.abs(full - psi_state).max() < 1e-12
     for i, (re, im) in zip((0, 1, (1 << n) - 1, 0b1011 << (n - 4), 37), res[0]["amps"]):
         assert abs(complex(re, im) - psi_state[i]) < 1e-12
+
+
+def _grad_worker(rank, world, port, n, template, ham, params, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tyxonq_b200 import ShardedStatevectorEngine
+        eng = ShardedStatevectorEngine(device="cpu", local_backend=_EmuLocal())
+        e, g = eng.energy_and_grad(n, template, ham, params)
+        np.save(os.path.join(out_dir, f"eg{rank}.npy"), np.concatenate([[e], g]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_parameter_shift_gradient(tmp_path):
+    from tyxonq_b200.vqe import Param
+    n, world = 6, 2
+    template = [("h", q) for q in range(n)] + [("ry", 0, Param(0)), ("rx", 1, Param(1)), ("cx", 0, 1), ("rz", 2, Param(2)),
+                ("rzz", 0, 5, Param(3)), ("cx", 2, 3), ("ry", 3, Param(1, 2.0)), ("rxx", 0, 4, Param(0, -1.0)), ("cx", 4, 5), ("rx", 5, Param(2))]
+    ham = [(0.5, [("X", 0), ("X", 1)]), (-0.3, [("Y", 0), ("Z", 5)]), (0.8, [("Z", 1)]), (0.25, []), (0.4, [("Y", 4), ("Y", 3)]), (0.6, [("Z", 0), ("Z", 2)])]
+    params = np.random.default_rng(9).uniform(-1, 1, 4)
+    mp.spawn(_grad_worker, args=(world, _free_port(), n, template, ham, params, str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(tmp_path / f"eg{r}.npy") for r in range(world)]
+    assert np.array_equal(got[0], got[1])
+    codes = {"X": 1, "Y": 2, "Z": 3}
+    terms, w = [], []
+    for c, lst in ham:
+        t = [0] * n
+        for p_, q in lst:
+            t[q] = codes[p_]
+        terms.append(t); w.append(c)
+
+    def energy(th):
+        ops = [tuple(a.scale * float(th[a.index]) if isinstance(a, Param) else a for a in op) for op in template]
+        psi, _ = O.evolve_ops(n, ops, mode="state")
+        return O.expect_pauli_sum(psi, terms, w)
+
+    assert abs(got[0][0] - energy(params)) < 1e-12
+    assert np.abs(got[0][1:] - O.central_fd_gradient(energy, params, eps=1e-5)).max() < 1e-8

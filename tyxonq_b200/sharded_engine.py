@@ -11,7 +11,7 @@ noise models) raise: there is no fallback.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -153,3 +153,35 @@ class ShardedStatevectorEngine:
             ham = PauliSum.from_pauli_list(n, obs)
         st, _ = self._evolve(circuit, "state")
         return float(st.expect_pauli_sum(ham).real)
+
+    # ------------------------------------------------------------------------------------
+    _SHIFT_OPS = ("rx", "ry", "rz", "rxx", "ryy", "rzz")     # exp(-i theta/2 P), P^2 = 1: the two-term shift rule is exact
+
+    def energy_and_grad(self, n: int, template: Sequence[Sequence[Any]], obs: Any, params: Sequence[float]) -> Tuple[float, np.ndarray]:
+        """E(theta) and dE/dtheta by the parameter-shift rule (kernels/common.py:11-23, compiler/gradients/
+        parameter_shift.py:9-36) on the sharded state; ``template`` holds ``vqe.Param(index, scale)`` placeholders.  The
+        shift is applied per gate OCCURRENCE (angle +- pi/2, weighted by the placeholder's scale), so parameters that
+        are shared between gates or scaled differentiate exactly; 1 + 2 * occurrences collective evaluations."""
+        from .circuits import Circuit
+        from .vqe import Param
+        theta = np.asarray(params, dtype=np.float64).reshape(-1)
+        occ = []
+        for k, op in enumerate(template):
+            refs = [a for a in op if isinstance(a, Param)]
+            if refs:
+                if op[0] not in self._SHIFT_OPS or len(refs) != 1:
+                    raise NotImplementedError(f"no two-term shift rule for parametrised op {op[0]!r}")
+                occ.append((k, refs[0]))
+
+        def energy(shift_at: int = -1, delta: float = 0.0) -> float:
+            ops = []
+            for k, op in enumerate(template):
+                ops.append(tuple((a.scale * float(theta[a.index]) + (delta if k == shift_at else 0.0)) if isinstance(a, Param) else a
+                                 for a in op))
+            return self.expval(Circuit(n, ops), obs)
+
+        e0 = energy()
+        grad = np.zeros_like(theta)
+        for k, ref in occ:
+            grad[ref.index] += ref.scale * 0.5 * (energy(k, 0.5 * np.pi) - energy(k, -0.5 * np.pi))
+        return e0, grad
