@@ -202,3 +202,24 @@ def test_streamed_chunks_are_the_same_program():
                         assert np.concatenate(ps_all).tobytes() == full.passes.tobytes()
                         assert np.concatenate(g_all).tobytes() == full.gates.tobytes()
                         assert np.concatenate(m_all).tobytes() == full.mats.tobytes()
+
+
+@pytest.mark.parametrize("kind,n", [("hea", 11), ("random", 9)])
+def test_streamed_chunks_run_one_after_the_other_equal_the_oracle(kind, n):
+    """Every chunk of compile_program_stream is a self-contained Program: the emulated kernel runs them in sequence on
+    the same state (what StatevectorEngine._flush does on the device) and must land on the oracle's state."""
+    from tyxonq_b200.fuse import fuse
+    from tyxonq_b200.gates import lower_op
+    from tyxonq_b200.planner import TileConfig, compile_program_stream
+    rng = np.random.default_rng(33)
+    ops = O.hea_ops(n, 5, rng.uniform(-3, 3, 10 * n)) if kind == "hea" else random_ops(rng, n, 200)
+    lowered = [g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None]
+    state = np.zeros(1 << n, dtype=np.complex128)
+    state[0] = 1
+    chunks = 0
+    for prog in compile_program_stream(fuse(lowered), n, TileConfig(m=6, L=2), first=2, chunk=3):
+        state = run_program_emulated(prog, state)
+        chunks += 1
+    assert chunks >= 3
+    ref, _ = O.evolve_ops(n, ops, mode="run")
+    assert np.abs(state - ref).max() < 1e-12
