@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TQB_ABI_VERSION 1
+#define TQB_ABI_VERSION 2
 
 #define TQB_C64 0
 #define TQB_C128 1
@@ -124,6 +124,36 @@ int tqb_init_basis(void *state, int n, int64_t batch, int dtype, uint64_t global
 int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global_base,
                    const tqb_pass *passes, int n_passes, const tqb_gate *gates_dev,
                    const void *mats_dev, int threads, int ctas_per_sm, void *stream);
+
+/* The same with a HOST copy of the gate descriptors (gates_host[i] == gates_dev[i]; NULL = none).  With the host
+ * copy the library may run a lean-eligible pass (tqb_pass.max_dense_k < 0, matrices staged) through a kernel
+ * SPECIALISED for that pass shape: the gate list, every bit position and the thread mapping become compile-time
+ * constants of one hand-written kernel template (csrc/tqb_spec.cuh) compiled by NVRTC for sm_100a and cached in
+ * memory and on disk; outside-the-tile bit positions, hb[] and matrix values stay run-time parameters.  Results are
+ * the same as the generic kernels' to rounding.  Passes that are not eligible, or whose kernel is not ready yet
+ * (asynchronous mode), run the generic kernels.                                                          */
+int tqb_run_passes2(void *state, int n, int64_t batch, int dtype, uint64_t global_base,
+                    const tqb_pass *passes, int n_passes, const tqb_gate *gates_dev,
+                    const tqb_gate *gates_host, const void *mats_dev, int threads, int ctas_per_sm,
+                    void *stream);
+/* Specialisation mode: 0 = off, 1 = asynchronous (default: new shapes compile on background threads while the
+ * generic kernel runs them), 2 = synchronous (compile on first use; compile errors are returned).  256 + flags:
+ * profiling switches of the specialised kernels (1 = skip gates, 2 = skip bulk loads, 4 = skip bulk stores; results
+ * are WRONG with any flag set).  Returns the old mode.                                                    */
+int tqb_set_jit(int mode);
+/* Directory of the on-disk cubin cache (NULL or "" = none).                                              */
+int tqb_set_jit_cache(const char *dir);
+/* Block until every queued specialisation has been compiled (asynchronous mode).                          */
+int tqb_jit_wait(void);
+/* out4 = { specialised launches, NVRTC compilations, disk-cache hits, shapes known }.                    */
+int tqb_jit_stats(int64_t *out4);
+/* Source of one pass's specialised kernel: the generated constants (+ the kernel template when with_template != 0)
+ * copied into buf (cap bytes, 0-terminated); returns the size needed, negative when the pass is not eligible.
+ * tqb_spec_compile: NVRTC-compile it for sm_100a without launching (needs no GPU; fills the disk cache); returns
+ * the cubin size.  Both are used by the CPU test tier and by the build step that pre-warms the cache.     */
+int64_t tqb_spec_source(const tqb_pass *pass, const tqb_gate *gates_host, int dtype, int with_template,
+                        char *buf, int64_t cap);
+int tqb_spec_compile(const tqb_pass *pass, const tqb_gate *gates_host, int dtype);
 
 /* Tile staging mode of tqb_run_passes.  0 = vectorised LDG/STG, single buffer.  Otherwise TMA bulk
  * copies (cp.async.bulk) with mbarrier completion into a ring of tile buffers, used whenever the

@@ -298,6 +298,49 @@ def test_lean_and_general_kernels_agree_with_oracle(cuda_device):
         lib.tqb_set_tma(512 + 1)
 
 
+def test_specialised_kernels_match_oracle(cuda_device):
+    """The NVRTC-specialised pass kernels (csrc/tqb_spec.cuh through tqb_run_passes2, synchronous mode so that every
+    eligible pass really runs its own kernel) against the oracle, complex128 and complex64, plain and padded layouts,
+    outside-the-tile controls, batched states."""
+    import torch
+    from tyxonq_b200 import _lib
+    from tyxonq_b200 import program as P
+    from tyxonq_b200.fuse import fuse
+    from tyxonq_b200.gates import lower_op
+    from tyxonq_b200.planner import TileConfig, compile_program
+    lib = _lib.load()
+    rng = np.random.default_rng(78)
+    cases = [
+        (20, O.hea_ops(20, 8, rng.uniform(-np.pi, np.pi, 2 * 8 * 20))),
+        (19, O.hwe_ry_ops(19, 5, rng.uniform(-np.pi, np.pi, 6 * 19))),
+        (18, O.trotter_ops(*O.tfim_terms(18, 1.0, 0.7), 0.9, 4)),
+        (20, O.qaoa_ring_ops(20, 4, rng.uniform(-np.pi, np.pi, 8))),
+    ]
+    old = lib.tqb_set_jit(2)
+    try:
+        for n, ops in cases:
+            ref, _ = O.evolve_ops(n, ops)
+            for td, tol, m, L in ((torch.complex128, TOL128, 11, 5), (torch.complex64, TOL64, 12, 6), (torch.complex64, TOL64, 11, 6)):
+                before = _lib.jit_stats()["spec_launches"]
+                eng = _engine(cuda_device, "b200", td, TileConfig(m=m, L=L, threads=128))
+                psi, _, _ = eng._evolve(FakeCircuit(n, ops), "state")
+                err = np.abs(psi.cpu().numpy() - ref).max()
+                assert err < tol, (n, ops[0], td, m, err)
+                assert _lib.jit_stats()["spec_launches"] > before, "no specialised kernel ran"
+        # batched states: the batch index is more tile-index bits
+        n, ops = 14, O.qaoa_ring_ops(14, 3, rng.uniform(-np.pi, np.pi, 6))
+        ref, _ = O.evolve_ops(n, ops)
+        lg = fuse([g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None])
+        prog = compile_program(lg, n, TileConfig(m=11, L=5, threads=128), itemsize=16)
+        st = P.new_state(n, batch=5, dtype=torch.complex128, device=cuda_device)
+        before = _lib.jit_stats()["spec_launches"]
+        P.DeviceProgram(prog, cuda_device, torch.complex128).run(st)
+        assert _lib.jit_stats()["spec_launches"] - before == prog.n_passes
+        assert np.abs(st.cpu().numpy() - ref[None, :]).max() < TOL128
+    finally:
+        lib.tqb_set_jit(old)
+
+
 def test_large_state_invariants(cuda_device):
     """n = 28 (4 GiB complex128): GHZ amplitudes, norm, reversibility -- size-independent properties."""
     import torch

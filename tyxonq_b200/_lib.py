@@ -15,6 +15,7 @@ import numpy as np
 
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libtyxonq_b200.so"
+JIT_CACHE = PKG / "jit_cache"
 if os.environ.get("TQB_LIB"):   # profiling builds only (tools/build_prof.sh): an alternative build of the same sources
     LIB_PATH = Path(os.environ["TQB_LIB"])
 
@@ -61,6 +62,13 @@ SIGNATURES = {
     "tqb_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i)]),
     "tqb_init_basis": (_i, [_vp, _i, _i64, _i, _u64, _u64, _vp]),
     "tqb_run_passes": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "tqb_run_passes2": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "tqb_set_jit": (_i, [_i]),
+    "tqb_set_jit_cache": (_i, [C.c_char_p]),
+    "tqb_jit_wait": (_i, []),
+    "tqb_jit_stats": (_i, [C.POINTER(_i64)]),
+    "tqb_spec_source": (_i64, [_vp, _vp, _i, _i, _vp, _i64]),
+    "tqb_spec_compile": (_i, [_vp, _vp, _i]),
     "tqb_set_tma": (_i, [_i]),
     "tqb_norm2": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_expect_z_bits": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
@@ -103,15 +111,44 @@ def load() -> C.CDLL:
         raise TqbError(
             f"{LIB_PATH} is missing: build it with `python -m tyxonq_b200.build` "
             "(tyxonq_b200 has no CPU fallback)")
+    _find_nvrtc()
     lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the ABI and the header drift apart
         fn.restype = res
         fn.argtypes = args
-    if lib.tqb_abi_version() != 1:
+    if lib.tqb_abi_version() != 2:
         raise TqbError("libtyxonq_b200.so ABI version mismatch")
+    # specialised pass kernels (csrc/tqb_jit.cu): cubin cache next to the library; TQB_JIT = 0 off / 1 async / 2 sync
+    lib.tqb_set_jit_cache(os.environ.get("TQB_JIT_CACHE", str(JIT_CACHE)).encode())
+    if os.environ.get("TQB_JIT"):
+        lib.tqb_set_jit(int(os.environ["TQB_JIT"]))
     _lib = lib
     return lib
+
+
+def _find_nvrtc() -> None:
+    """Point the library's dlopen at an NVRTC (the CUDA toolkit's, else the wheel torch depends on)."""
+    if os.environ.get("TQB_NVRTC"):
+        return
+    cands = ["/usr/local/cuda/lib64/libnvrtc.so.12"]
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.cuda_nvrtc")
+        if spec and spec.submodule_search_locations:
+            cands.append(str(Path(list(spec.submodule_search_locations)[0]) / "lib" / "libnvrtc.so.12"))
+    except Exception:
+        pass
+    for c in cands:
+        if os.path.exists(c):
+            os.environ["TQB_NVRTC"] = c
+            return
+
+
+def jit_stats() -> dict:
+    out = (_i64 * 4)()
+    load().tqb_jit_stats(out)
+    return {"spec_launches": int(out[0]), "compiles": int(out[1]), "disk_hits": int(out[2]), "shapes": int(out[3])}
 
 
 def check(rc: int) -> None:
@@ -134,6 +171,7 @@ def ensure_device(device_index: int) -> None:
         load().tqb_set_tma(512 + int(os.environ["TQB_LEAN"]))
     if os.environ.get("TQB_DBG"):  # profiling only: 1 = no gate arithmetic, 2 = no bulk loads, 4 = no bulk stores
         load().tqb_set_tma(256 + int(os.environ["TQB_DBG"]))
+        load().tqb_set_jit(256 + int(os.environ["TQB_DBG"]))
     _inited_devices.add(device_index)
 
 

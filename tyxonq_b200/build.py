@@ -14,8 +14,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libtyxonq_b200.so"
-SOURCES = ["tqb_tile.cu", "tqb_reduce.cu"]
-HEADERS = ["tqb_core.cuh", "tqb_host.h", "../../include/tyxonq_b200.h"]
+SOURCES = ["tqb_tile.cu", "tqb_reduce.cu", "tqb_jit.cu"]
+HEADERS = ["tqb_core.cuh", "tqb_host.h", "tqb_spec.cuh", "../../include/tyxonq_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -32,6 +32,19 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libtyxonq_b200.so")
 
 
+def embed_spec_template() -> Path:
+    """csrc/tqb_spec.cuh -> csrc/tqb_spec_src.inc (a C++ raw string literal): the kernel text tqb_jit.cu hands to NVRTC."""
+    src = (CSRC / "tqb_spec.cuh").read_text()
+    assert ')TQBSPEC"' not in src
+    out = CSRC / "tqb_spec_src.inc"
+    # (string literals are limited to 64 KiB by some front ends: split into adjacent literals)
+    parts = [src[i:i + 12000] for i in range(0, len(src), 12000)]
+    text = "\n".join('R"TQBSPEC(' + p + ')TQBSPEC"' for p in parts) + "\n"
+    if not out.exists() or out.read_text() != text:
+        out.write_text(text)
+    return out
+
+
 def is_stale() -> bool:
     if not LIB.exists():
         return True
@@ -44,6 +57,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
     nvcc = _nvcc()
+    embed_spec_template()
     objs = []
     build_dir = PKG / "build"
     build_dir.mkdir(exist_ok=True)
@@ -60,7 +74,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
         (build_dir / (src + ".ptxas.log")).write_text(out)
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-lcudart", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout)

@@ -25,6 +25,10 @@ Workspace *workspace();  // workspace of the current device, nullptr (with error
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// tqb_jit.cu: run one lean-eligible pass with its NVRTC-specialised kernel (*used = false: caller falls back)
+int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t global_base, const tqb_pass &ps,
+                    const tqb_gate *gates_host, const void *mats_dev, const Workspace &ws, cudaStream_t st, bool *used);
+
 #define TQB_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \
     cudaError_t _e = (expr);                                                              \

@@ -1,0 +1,801 @@
+// tqb_jit.cu -- per-pass-shape specialisation of the fused gate pass.
+//
+// tqb_run_passes2() hands every lean-eligible pass (only 1-qubit-layer gates, matrices staged) to spec_try_launch():
+//   1. spec_plan()   turns the pass + its gate descriptors into a compile-time description: for every gate the
+//                    register bits (targets + fillers), the thread-bit map, the kind of synchronisation in front of
+//                    it, the tile layout (plain / padded) -- chosen by exhaustive search over the few candidates with
+//                    an exact shared-memory bank-conflict count;
+//   2. spec_header() prints that description as C++ constants (the cache key);
+//   3. the constants + the hand-written kernel text (tqb_spec.cuh, embedded at build time) are compiled by NVRTC for
+//      sm_100a, the cubin is loaded with cudaLibraryLoadData and cached in memory and on disk;
+//   4. the kernel is launched like tile_pass_lean_kernel (persistent grid of resident CTAs).
+// Outside-the-tile bit positions, the high tile bits hb[] and all matrix VALUES are run-time parameters, so e.g. the
+// four middle passes of every layer period of a hardware-efficient ansatz share one kernel.
+//
+// Modes (tqb_set_jit): 0 = off (generic kernels only), 1 = asynchronous (default: shapes compile on background
+// threads while the generic lean kernel runs them; tqb_jit_wait() drains the queue), 2 = synchronous (compile on first
+// use, errors are returned to the caller).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <chrono>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "tqb_host.h"
+
+namespace tqb {
+
+static const char *const kSpecTemplate =
+#include "tqb_spec_src.inc"
+    ;
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+enum { K_DENSE1 = 0, K_DIAG = 1, K_MUX = 4, K_CHAIN = 5, K_ROT = 6 };
+
+struct SpecGate {
+  int kind = 0, R = 0, type = 0, muxed = 0, unit_p = 0, E = 0, ctrl = -1, mat = 0, sync = 0;
+  int xb[2] = {-1, -1};
+  int dbits[6] = {-1, -1, -1, -1, -1, -1};
+  int rb[5] = {-1, -1, -1, -1, -1};
+  int tb[7] = {-1, -1, -1, -1, -1, -1, -1};
+  uint32_t targets = 0;   // mask of target tile bits
+  uint32_t reserved = 0;  // tile bits that must stay thread bits (control, extra table bits)
+};
+
+struct SpecPlan {
+  int dtype = 0, m = 0, L = 0, padL = 0, next = 0, mat_count = 0, rbits = 0;
+  int ext[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<SpecGate> g;
+};
+
+static inline int popc(uint32_t v) { return __builtin_popcount(v); }
+
+// exact bank-conflict count of the gate's tile accesses for warp 0: sum over the sampled register indices and the
+// phases of a warp-wide access of the largest number of lanes that need DIFFERENT 128-byte rows of the same bank group
+static int conflict_cost(const SpecGate &s, int rbits, int es, int padL) {
+  auto pbyte = [&](uint32_t e) -> uint32_t { return e * (uint32_t)es + (padL ? ((e >> padL) << 4) : 0u); };
+  const int lanes_per_phase = 128 / es;
+  const int D = 1 << rbits;
+  int cost = 0;
+  const int samples[3] = {0, D - 1, D / 2 - 1 > 0 ? D / 2 - 1 : 0};
+  for (int si = 0; si < 3; ++si) {
+    uint32_t so = 0;
+    for (int i = 0; i < rbits; ++i)
+      if ((samples[si] >> i) & 1) so |= 1u << s.rb[i];
+    for (int ph = 0; ph < 32 / lanes_per_phase; ++ph) {
+      uint32_t rows[16][16];
+      int cnt[16];
+      for (int c = 0; c < 16; ++c) cnt[c] = 0;
+      for (int l = 0; l < lanes_per_phase; ++l) {
+        const uint32_t tid = (uint32_t)(ph * lanes_per_phase + l);
+        uint32_t e = so;
+        for (int j = 0; j < 5; ++j) e |= ((tid >> j) & 1u) << s.tb[j];
+        const uint32_t a = pbyte(e);
+        const int chunk = (int)((a / (uint32_t)es) % (uint32_t)lanes_per_phase);
+        const uint32_t row = a / 128u;
+        bool seen = false;
+        for (int k = 0; k < cnt[chunk]; ++k) seen = seen || rows[chunk][k] == row;
+        if (!seen) rows[chunk][cnt[chunk]++] = row;
+      }
+      int deg = 1;
+      for (int c = 0; c < lanes_per_phase; ++c) deg = std::max(deg, cnt[c]);
+      cost += deg;
+    }
+  }
+  return cost;
+}
+
+// best register / thread mapping of one gate for warp bits W; returns its cost (conflicts first, then preferences)
+static int map_gate(SpecGate &s, int m, int rbits, int es, int padL, uint32_t W) {
+  const uint32_t all = (1u << m) - 1u;
+  const uint32_t free_bits = all & ~s.targets & ~W;
+  const int nf = rbits - popc(s.targets);
+  const uint32_t fill_cand = free_bits & ~s.reserved;
+  std::vector<int> cand;
+  for (int b = 0; b < m; ++b)
+    if ((fill_cand >> b) & 1u) cand.push_back(b);
+  int best = 1 << 30;
+  SpecGate best_s = s;
+  const int nc = (int)cand.size();
+  // enumerate filler subsets (nf of nc candidates) by bitmask
+  for (uint32_t sub = 0; sub < (1u << nc); ++sub) {
+    if (popc(sub) != nf) continue;
+    uint32_t fillers = 0;
+    for (int i = 0; i < nc; ++i)
+      if ((sub >> i) & 1u) fillers |= 1u << cand[i];
+    SpecGate t = s;
+    {
+      int r = s.R;
+      if (s.kind == K_DIAG) r = 0;
+      for (int b = m - 1; b >= 0; --b)
+        if ((fillers >> b) & 1u) t.rb[r++] = b;
+    }
+    const uint32_t lane_bits = free_bits & ~fillers;
+    std::vector<int> lb;
+    for (int b = 0; b < m; ++b)
+      if ((lane_bits >> b) & 1u) lb.push_back(b);
+    if ((int)lb.size() != 5) continue;
+    // which lane bits take the low lane positions: enumerate orderings by choosing the subset for lanes 0..nl-1
+    const int nl = es == 16 ? 3 : 4;
+    for (uint32_t lo = 0; lo < 32u; ++lo) {
+      if (popc(lo) != nl) continue;
+      int j = 0;
+      for (int i = 0; i < 5; ++i)
+        if ((lo >> i) & 1u) t.tb[j++] = lb[i];
+      for (int i = 0; i < 5; ++i)
+        if (!((lo >> i) & 1u)) t.tb[j++] = lb[i];
+      int w = 5;
+      for (int b = 0; b < m; ++b)
+        if ((W >> b) & 1u) t.tb[w++] = b;
+      int c = conflict_cost(t, rbits, es, padL) * 1000;
+      // preferences: control / extra bits outside the low lanes (table loads stay one broadcast per phase),
+      // fillers on high bits
+      for (int i = 0; i < nl; ++i)
+        if ((s.reserved >> t.tb[i]) & 1u) c += 10;
+      for (int b = 0; b < m; ++b)
+        if ((fillers >> b) & 1u) c += (m - 1 - b);
+      if (c < best) {
+        best = c;
+        best_s = t;
+      }
+    }
+  }
+  s = best_s;
+  return best;
+}
+
+static bool spec_plan(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPlan &P, std::string &why) {
+  const int m = ps.m, L = ps.L, h = ps.m - ps.L;
+  const int es = dtype == TQB_C128 ? 16 : 8;
+  P = SpecPlan();
+  P.dtype = dtype;
+  P.m = m;
+  P.L = L;
+  P.rbits = m - 7;
+  P.mat_count = ps.mat_count;
+  if (dtype == TQB_C128 ? P.rbits != 4 : (P.rbits != 4 && P.rbits != 5)) return why = "tile size", false;
+  if (ps.max_dense_k >= 0) return why = "not a lean pass", false;
+  if (ps.mat_count <= 0 || ps.mat_count > 2048) return why = "matrices not staged", false;
+  if (((size_t)es << L) < 128 || h < 1 || h > 6) return why = "run length", false;
+  if (ps.n_gates < 1 || ps.n_gates > 64) return why = "gate count", false;
+  auto code = [&](int8_t b, bool &ok) -> int {
+    const unsigned u = (uint8_t)b;
+    if (u == 127u) return -1;
+    if (u >= 64u) {
+      const int pos = (int)(u - 64u);
+      for (int j = 0; j < P.next; ++j)
+        if (P.ext[j] == pos) return 64 + j;
+      if (P.next >= 8) {
+        ok = false;
+        return -1;
+      }
+      P.ext[P.next] = pos;
+      return 64 + P.next++;
+    }
+    if ((int)u >= m) ok = false;
+    return (int)u;
+  };
+  for (int gi = 0; gi < ps.n_gates; ++gi) {
+    const tqb_gate &q = gh[ps.gate_begin + gi];
+    SpecGate s;
+    bool ok = true;
+    if (q.mat_bstride != 0) return why = "per-member matrices", false;
+    s.mat = (int)q.mat_off - ps.mat_begin;
+    if (s.mat < 0 || s.mat >= ps.mat_count) return why = "matrix range", false;
+    auto target = [&](int i, int8_t b) {
+      if (b < 0 || b >= m || ((s.targets >> b) & 1u)) ok = false;
+      else {
+        s.rb[i] = b;
+        s.targets |= 1u << b;
+      }
+    };
+    auto reserve = [&](int c) {
+      if (c >= 0 && c < 64) {
+        if ((s.targets >> c) & 1u) ok = false;
+        s.reserved |= 1u << c;
+      }
+    };
+    switch (q.kind) {
+      case TQB_GATE_DENSE:
+        if (q.k != 1) return why = "dense k > 1", false;
+        s.kind = K_DENSE1;
+        s.R = 1;
+        target(0, q.bits[0]);
+        break;
+      case TQB_GATE_MUX:
+        s.kind = K_MUX;
+        s.R = 1;
+        target(0, q.bits[0]);
+        s.ctrl = code(q.bits[1], ok);
+        if (s.ctrl < 0) ok = false;
+        reserve(s.ctrl);
+        break;
+      case TQB_GATE_CHAIN: {
+        s.R = q.k;
+        if (q.k < 2 || q.k > 4 || q.k > P.rbits) return why = "chain length", false;
+        for (int i = 0; i < q.k; ++i) target(i, q.bits[i]);
+        s.ctrl = code(q.bits[q.k], ok);
+        reserve(s.ctrl);
+        if (q.off_a >= 4u) {
+          s.kind = K_ROT;
+          s.type = (int)((q.off_a >> 1) & 1u);
+          s.muxed = (int)(q.off_a & 1u);
+          s.E = (int)(q.off_b & 3u);
+          s.unit_p = (q.off_b & 128u) ? 1 : 0;
+          if (s.E > 2 || q.k + 1 + s.E > TQB_MAX_GATE_BITS) return why = "extra bits", false;
+          for (int j = 0; j < s.E; ++j) {
+            s.xb[j] = code(q.bits[q.k + 1 + j], ok);
+            if (s.xb[j] < 0) ok = false;
+            reserve(s.xb[j]);
+          }
+        } else if (q.off_a == 0u && q.k <= 3) {
+          s.kind = K_CHAIN;
+        } else {
+          return why = "chain form", false;
+        }
+        break;
+      }
+      case TQB_GATE_DIAG:
+        s.kind = K_DIAG;
+        s.R = q.k;
+        if (q.k < 1 || q.k > 6) return why = "diag size", false;
+        for (int j = 0; j < q.k; ++j) {
+          s.dbits[j] = code(q.bits[j], ok);
+          if (s.dbits[j] < 0) ok = false;
+        }
+        break;
+      default:
+        return why = "gate kind", false;
+    }
+    if (!ok) return why = "bad gate bits", false;
+    P.g.push_back(s);
+  }
+  const int ng = (int)P.g.size();
+  const uint32_t all = (1u << m) - 1u;
+
+  // segments: maximal runs of gates that leave >= 2 tile bits untargeted (the warp bits of the segment)
+  struct Seg { int lo, hi; uint32_t C; };
+  std::vector<Seg> segs;
+  for (int i = 0; i < ng;) {
+    uint32_t C = all;
+    int j = i;
+    while (j < ng) {
+      const uint32_t C2 = C & ~P.g[j].targets;
+      if (popc(C2) < 2 && j > i) break;
+      C = C2;
+      ++j;
+    }
+    if (popc(C) < 2) return why = "no warp bits", false;
+    segs.push_back({i, j, C});
+    i = j;
+  }
+  int best_total = 1 << 30;
+  std::vector<SpecGate> best_g;
+  int best_pad = 0;
+  const bool can_pad = L >= 1 && L <= 7 && h > 0;
+  for (int pad = 0; pad < (can_pad ? 2 : 1); ++pad) {
+    const int padL = pad ? L : 0;
+    std::vector<SpecGate> cur = P.g;
+    int total = 0;
+    for (const Seg &sg : segs) {
+      int seg_best = 1 << 30;
+      std::vector<SpecGate> seg_g;
+      for (int a = 0; a < m; ++a)
+        for (int b = a + 1; b < m; ++b) {
+          if (!((sg.C >> a) & 1u) || !((sg.C >> b) & 1u)) continue;
+          const uint32_t W = (1u << a) | (1u << b);
+          int c = 0;
+          std::vector<SpecGate> tmp(P.g.begin() + sg.lo, P.g.begin() + sg.hi);
+          bool feasible = true;
+          for (SpecGate &s : tmp) {
+            if (s.kind == K_DIAG) continue;
+            // the fillers must exist outside targets, W and the reserved bits
+            if (popc(all & ~s.targets & ~W & ~s.reserved) < P.rbits - popc(s.targets)) { feasible = false; break; }
+            c += map_gate(s, m, P.rbits, es, padL, W);
+          }
+          if (!feasible) continue;
+          c -= (a + b);   // tie: higher warp bits
+          if (c < seg_best) {
+            seg_best = c;
+            seg_g = tmp;
+          }
+        }
+      if (seg_best == (1 << 30)) return why = "no feasible warp bits", false;
+      total += seg_best;
+      for (int i = sg.lo; i < sg.hi; ++i) cur[i] = seg_g[i - sg.lo];
+    }
+    if (total < best_total) {
+      best_total = total;
+      best_g = cur;
+      best_pad = padL;
+    }
+  }
+  P.g = best_g;
+  P.padL = best_pad;
+  // DIAG gates ride on a neighbour's mapping (same thread, same amplitudes: no synchronisation in between)
+  for (int i = 0; i < ng; ++i) {
+    if (P.g[i].kind != K_DIAG) continue;
+    int src = -1;
+    for (int j = i - 1; j >= 0 && src < 0; --j)
+      if (P.g[j].kind != K_DIAG) src = j;
+    for (int j = i + 1; j < ng && src < 0; ++j)
+      if (P.g[j].kind != K_DIAG) src = j;
+    if (src >= 0) {
+      for (int k = 0; k < 5; ++k) P.g[i].rb[k] = P.g[src].rb[k];
+      for (int k = 0; k < 7; ++k) P.g[i].tb[k] = P.g[src].tb[k];
+    } else {  // a pass of diagonal gates only: registers on the top bits, lanes on the low bits
+      for (int k = 0; k < P.rbits; ++k) P.g[i].rb[k] = m - 1 - k;
+      for (int k = 0; k < 7; ++k) P.g[i].tb[k] = k;
+    }
+  }
+  for (int i = 0; i < ng; ++i) {
+    SpecGate &s = P.g[i];
+    if (i == 0) {
+      s.sync = 0;
+      continue;
+    }
+    const SpecGate &p = P.g[i - 1];
+    bool same = true;
+    uint32_t ra = 0, rb = 0;
+    for (int k = 0; k < P.rbits; ++k) {
+      ra |= 1u << s.rb[k];
+      rb |= 1u << p.rb[k];
+    }
+    same = ra == rb;
+    for (int k = 0; k < 7; ++k) same = same && s.tb[k] == p.tb[k];
+    const bool same_w = s.tb[5] == p.tb[5] && s.tb[6] == p.tb[6];
+    s.sync = same ? -1 : (same_w ? 1 : 2);
+  }
+  // sanity: register bits and thread bits partition the tile bits
+  for (const SpecGate &s : P.g) {
+    uint32_t seen = 0;
+    for (int k = 0; k < P.rbits; ++k) {
+      if (s.rb[k] < 0 || s.rb[k] >= m || ((seen >> s.rb[k]) & 1u)) return why = "internal: register bits", false;
+      seen |= 1u << s.rb[k];
+    }
+    for (int k = 0; k < 7; ++k) {
+      if (s.tb[k] < 0 || s.tb[k] >= m || ((seen >> s.tb[k]) & 1u)) return why = "internal: thread bits", false;
+      seen |= 1u << s.tb[k];
+    }
+    if (seen != all) return why = "internal: partition", false;
+    for (int k = 0; k < P.rbits; ++k)
+      if ((s.reserved >> s.rb[k]) & 1u) return why = "internal: reserved bit in registers", false;
+  }
+  return true;
+}
+
+static std::string spec_header(const SpecPlan &P) {
+  std::string o;
+  char buf[512];
+  o += "namespace tqbs {\n";
+  o += P.dtype == TQB_C128 ? "typedef double T;\n" : "typedef float T;\n";
+  snprintf(buf, sizeof buf, "constexpr int M = %d, L = %d, PADL = %d, NG = %d, NEXT = %d, MAT_COUNT = %d, RBITS = %d;\n", P.m, P.L,
+           P.padL, (int)P.g.size(), P.next, P.mat_count, P.rbits);
+  o += buf;
+  o += "struct GateC { int kind, R, type, muxed, unit_p, E, ctrl, mat, sync; int xb[2]; int dbits[6]; int rb[5]; int tb[7]; };\n";
+  o += "constexpr GateC G[NG] = {\n";
+  for (const SpecGate &s : P.g) {
+    snprintf(buf, sizeof buf,
+             "  {%d, %d, %d, %d, %d, %d, %d, %d, %d, {%d, %d}, {%d, %d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d, %d, %d}},\n",
+             s.kind, s.R, s.type, s.muxed, s.unit_p, s.E, s.ctrl, s.mat, s.sync, s.xb[0], s.xb[1], s.dbits[0], s.dbits[1],
+             s.dbits[2], s.dbits[3], s.dbits[4], s.dbits[5], s.rb[0], s.rb[1], s.rb[2], s.rb[3], s.rb[4], s.tb[0], s.tb[1],
+             s.tb[2], s.tb[3], s.tb[4], s.tb[5], s.tb[6]);
+    o += buf;
+  }
+  o += "};\n}\n";
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// NVRTC (loaded with dlopen: the library itself links only libcudart)
+// ------------------------------------------------------------------------------------------
+struct Nvrtc {
+  void *h = nullptr;
+  int (*CreateProgram)(void **, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+  int (*CompileProgram)(void *, int, const char *const *) = nullptr;
+  int (*GetCUBINSize)(void *, size_t *) = nullptr;
+  int (*GetCUBIN)(void *, char *) = nullptr;
+  int (*GetProgramLogSize)(void *, size_t *) = nullptr;
+  int (*GetProgramLog)(void *, char *) = nullptr;
+  int (*DestroyProgram)(void **) = nullptr;
+  int (*Version)(int *, int *) = nullptr;
+  std::string err;
+};
+
+static Nvrtc *nvrtc() {
+  static Nvrtc N;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    std::vector<std::string> cands;
+    if (const char *e = getenv("TQB_NVRTC")) cands.push_back(e);
+    cands.push_back("libnvrtc.so.12");
+    cands.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+    cands.push_back("libnvrtc.so");
+    for (const std::string &c : cands) {
+      N.h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+      if (N.h) break;
+    }
+    if (!N.h) {
+      N.err = "libnvrtc.so.12 not found (set TQB_NVRTC)";
+      return;
+    }
+#define TQB_SYM(field, name)                                             \
+  N.field = reinterpret_cast<decltype(N.field)>(dlsym(N.h, name));       \
+  if (!N.field) N.err = std::string("nvrtc symbol missing: ") + name;
+    TQB_SYM(CreateProgram, "nvrtcCreateProgram")
+    TQB_SYM(CompileProgram, "nvrtcCompileProgram")
+    TQB_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    TQB_SYM(GetCUBIN, "nvrtcGetCUBIN")
+    TQB_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    TQB_SYM(GetProgramLog, "nvrtcGetProgramLog")
+    TQB_SYM(DestroyProgram, "nvrtcDestroyProgram")
+    TQB_SYM(Version, "nvrtcVersion")
+#undef TQB_SYM
+  });
+  return &N;
+}
+
+// header + template -> cubin (sm_100a).  Thread safe.
+static bool spec_compile(const std::string &header, std::vector<char> &cubin, std::string &log) {
+  Nvrtc *N = nvrtc();
+  if (!N->h || !N->err.empty()) {
+    log = N->err;
+    return false;
+  }
+  const std::string src = header + kSpecTemplate;
+  void *prog = nullptr;
+  if (N->CreateProgram(&prog, src.c_str(), "tqb_spec_pass.cu", 0, nullptr, nullptr) != 0) {
+    log = "nvrtcCreateProgram failed";
+    return false;
+  }
+  const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+  const int rc = N->CompileProgram(prog, 4, opts);
+  size_t ls = 0;
+  N->GetProgramLogSize(prog, &ls);
+  if (ls > 1) {
+    log.resize(ls);
+    N->GetProgramLog(prog, &log[0]);
+  }
+  bool ok = rc == 0;
+  if (ok) {
+    size_t cs = 0;
+    ok = N->GetCUBINSize(prog, &cs) == 0 && cs > 0;
+    if (ok) {
+      cubin.resize(cs);
+      ok = N->GetCUBIN(prog, cubin.data()) == 0;
+    }
+    if (!ok) log += " (no cubin)";
+  }
+  N->DestroyProgram(&prog);
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------
+// cache
+// ------------------------------------------------------------------------------------------
+struct SpecParams {  // must match tqbs::SpecParams in tqb_spec.cuh
+  void *state;
+  const void *mats;
+  uint64_t global_base;
+  long long batch;
+  int n;
+  int dbg;
+  signed char hb[16];
+  signed char ext[8];
+};
+
+struct SpecKernel {
+  enum State { PENDING, READY, FAILED };
+  std::atomic<int> state{PENDING};
+  std::string header;
+  std::vector<char> cubin;
+  std::string log;
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kern = nullptr;
+  bool loaded = false;
+  bool configured = false;
+  int resident = 0;
+  size_t smem = 0;
+  int64_t uses = 0;
+};
+
+static std::mutex g_jit_mu;
+static std::condition_variable g_jit_cv;
+static std::unordered_map<std::string, std::shared_ptr<SpecKernel>> g_cache;   // key: header text
+static std::unordered_map<std::string, std::string> g_reject;                  // pass signature -> why (not eligible)
+static std::deque<std::shared_ptr<SpecKernel>> g_queue;
+static std::vector<std::thread> g_workers;
+static int g_pending = 0;
+static std::atomic<int> g_jit_mode{1};
+static std::atomic<int> g_jit_dbg{0};
+static std::string g_cache_dir;
+static std::atomic<int64_t> g_spec_launches{0}, g_spec_compiles{0}, g_spec_disk_hits{0};
+
+static uint64_t fnv1a(const std::string &s, uint64_t h = 1469598103934665603ull) {
+  for (unsigned char c : s) {
+    h ^= c;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+static std::string disk_path(const std::string &header) {
+  if (g_cache_dir.empty()) return std::string();
+  static const uint64_t th = fnv1a(kSpecTemplate);
+  char name[64];
+  snprintf(name, sizeof name, "/spec_%016llx.cubin", (unsigned long long)fnv1a(header, th));
+  return g_cache_dir + name;
+}
+
+static void build_kernel(SpecKernel &k) {
+  const std::string path = disk_path(k.header);
+  if (!path.empty()) {
+    if (FILE *f = fopen(path.c_str(), "rb")) {
+      fseek(f, 0, SEEK_END);
+      const long sz = ftell(f);
+      fseek(f, 0, SEEK_SET);
+      if (sz > 0) {
+        k.cubin.resize((size_t)sz);
+        if (fread(k.cubin.data(), 1, (size_t)sz, f) == (size_t)sz) {
+          fclose(f);
+          g_spec_disk_hits.fetch_add(1);
+          k.state.store(SpecKernel::READY);
+          return;
+        }
+      }
+      fclose(f);
+      k.cubin.clear();
+    }
+  }
+  if (spec_compile(k.header, k.cubin, k.log)) {
+    g_spec_compiles.fetch_add(1);
+    if (!path.empty()) {
+      const std::string tmp = path + ".tmp" + std::to_string((long long)getpid()) + "_" + std::to_string((unsigned long long)fnv1a(k.header) & 0xffff);
+      if (FILE *f = fopen(tmp.c_str(), "wb")) {
+        const bool w = fwrite(k.cubin.data(), 1, k.cubin.size(), f) == k.cubin.size();
+        fclose(f);
+        if (w) rename(tmp.c_str(), path.c_str());
+        else remove(tmp.c_str());
+      }
+    }
+    k.state.store(SpecKernel::READY);
+  } else {
+    k.state.store(SpecKernel::FAILED);
+  }
+}
+
+static void worker_main() {
+  for (;;) {
+    std::shared_ptr<SpecKernel> k;
+    {
+      std::unique_lock<std::mutex> lk(g_jit_mu);
+      g_jit_cv.wait(lk, [] { return !g_queue.empty(); });
+      k = g_queue.front();
+      g_queue.pop_front();
+    }
+    build_kernel(*k);
+    {
+      std::lock_guard<std::mutex> lk(g_jit_mu);
+      --g_pending;
+    }
+    g_jit_cv.notify_all();
+  }
+}
+
+static std::string pass_signature(const tqb_pass &ps, const tqb_gate *gh, int dtype) {
+  std::string s;
+  s.append(reinterpret_cast<const char *>(&dtype), sizeof dtype);
+  s.append(reinterpret_cast<const char *>(&ps.m), sizeof(int32_t) * 2);
+  s.append(reinterpret_cast<const char *>(&ps.n_gates), sizeof(int32_t) * 4);
+  for (int i = 0; i < ps.n_gates; ++i) {
+    const tqb_gate &q = gh[ps.gate_begin + i];
+    s.append(reinterpret_cast<const char *>(&q), offsetof(tqb_gate, zmask));
+  }
+  return s;
+}
+
+// Try to run pass `ps` with its specialised kernel.  *used = false: the caller runs the generic kernel.
+int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t global_base, const tqb_pass &ps,
+                    const tqb_gate *gates_host, const void *mats_dev, const Workspace &ws, cudaStream_t st, bool *used) {
+  *used = false;
+  const int mode = g_jit_mode.load();
+  if (mode == 0 || !gates_host || n <= ps.m) return 0;
+  std::shared_ptr<SpecKernel> k;
+  SpecPlan plan;
+  {
+    // (planning is deterministic; rejected shapes are remembered by their raw signature)
+    const std::string sig = pass_signature(ps, gates_host, dtype);
+    {
+      std::lock_guard<std::mutex> lk(g_jit_mu);
+      if (g_reject.count(sig)) return 0;
+    }
+    std::string why;
+    if (!spec_plan(ps, gates_host, dtype, plan, why)) {
+      std::lock_guard<std::mutex> lk(g_jit_mu);
+      g_reject[sig] = why;
+      return 0;
+    }
+  }
+  const std::string header = spec_header(plan);
+  bool fresh = false;
+  {
+    std::lock_guard<std::mutex> lk(g_jit_mu);
+    auto it = g_cache.find(header);
+    if (it == g_cache.end()) {
+      k = std::make_shared<SpecKernel>();
+      k->header = header;
+      g_cache[header] = k;
+      fresh = true;
+      if (mode == 1) {
+        if (g_workers.empty()) {
+          unsigned nt = std::thread::hardware_concurrency();
+          nt = nt < 2 ? 1 : (nt > 8 ? 8 : nt / 2 + 1);
+          for (unsigned i = 0; i < nt; ++i) {
+            g_workers.emplace_back(worker_main);
+            g_workers.back().detach();
+          }
+        }
+        g_queue.push_back(k);
+        ++g_pending;
+      }
+    } else {
+      k = it->second;
+    }
+    ++k->uses;
+  }
+  if (fresh && mode == 1) {
+    g_jit_cv.notify_all();
+    return 0;
+  }
+  if (fresh && mode >= 2) build_kernel(*k);
+  if (mode >= 2 && k->state.load() == SpecKernel::PENDING) {   // another thread is compiling it
+    std::unique_lock<std::mutex> lk(g_jit_mu);
+    g_jit_cv.wait_for(lk, std::chrono::seconds(120), [&] { return k->state.load() != SpecKernel::PENDING; });
+  }
+  const int stt = k->state.load();
+  if (stt == SpecKernel::FAILED) {
+    if (mode >= 2) return fail("tqb_run_passes: NVRTC failed for a specialised pass: " + k->log);
+    return 0;
+  }
+  if (stt != SpecKernel::READY) return 0;
+  {
+    std::lock_guard<std::mutex> lk(g_jit_mu);
+    if (!k->loaded) {
+      cudaError_t e = cudaLibraryLoadData(&k->lib, k->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+      if (e == cudaSuccess) e = cudaLibraryGetKernel(&k->kern, k->lib, "tqb_spec_pass");
+      if (e != cudaSuccess) {
+        k->state.store(SpecKernel::FAILED);
+        k->log = std::string("cudaLibraryLoadData / GetKernel: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        if (mode >= 2) return fail("tqb_run_passes: " + k->log);
+        return 0;
+      }
+      k->loaded = true;
+    }
+  }
+  const int es = dtype == TQB_C128 ? 16 : 8;
+  const int h = ps.m - ps.L;
+  const size_t run_stride = ((size_t)es << ps.L) + (plan.padL ? 16 : 0);
+  const size_t smem = 2 * (run_stride << h) + 64 + (size_t)((ps.mat_count + 1) & ~1) * es + ((size_t)8 << h);
+  if (smem > (size_t)ws.max_smem_optin) return 0;
+  const void *fn = reinterpret_cast<const void *>(k->kern);
+  if (!k->configured) {
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int resident = 0;
+    TQB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fn, 160, smem));
+    if (resident < 1) {
+      k->state.store(SpecKernel::FAILED);
+      k->log = "specialised kernel does not fit on an SM";
+      return 0;
+    }
+    k->resident = resident;
+    k->smem = smem;
+    k->configured = true;
+  }
+  SpecParams prm;
+  memset(&prm, 0, sizeof prm);
+  prm.state = state;
+  prm.mats = static_cast<const char *>(mats_dev) + (size_t)ps.mat_begin * es;
+  prm.global_base = global_base;
+  prm.batch = (long long)batch;
+  prm.n = n;
+  prm.dbg = g_jit_dbg.load();
+  for (int i = 0; i < h && i < 16; ++i) prm.hb[i] = ps.hb[i];
+  for (int j = 0; j < plan.next; ++j) prm.ext[j] = (signed char)plan.ext[j];
+  const unsigned long long total = (unsigned long long)batch << (n - ps.m);
+  unsigned long long grid = (unsigned long long)ws.sm_count * k->resident;
+  if (grid > total) grid = total;
+  void *args[] = {&prm};
+  cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(160), args, smem, st);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail(std::string("tqb_spec_pass launch failed: ") + cudaGetErrorString(e));
+  g_spec_launches.fetch_add(1);
+  *used = true;
+  return 0;
+}
+
+}  // namespace tqb
+
+using namespace tqb;
+
+extern "C" {
+
+int tqb_set_jit(int mode) {
+  if (mode >= 256) {   // 256 + flags: profiling switches of the specialised kernels (results are WRONG with any flag set)
+    g_jit_dbg.store(mode - 256);
+    return g_jit_mode.load();
+  }
+  return g_jit_mode.exchange(mode < 0 ? 0 : (mode > 2 ? 2 : mode));
+}
+
+int tqb_set_jit_cache(const char *dir) {
+  std::lock_guard<std::mutex> lk(g_jit_mu);
+  g_cache_dir = dir ? dir : "";
+  if (!g_cache_dir.empty()) mkdir(g_cache_dir.c_str(), 0755);
+  return 0;
+}
+
+int tqb_jit_wait(void) {
+  std::unique_lock<std::mutex> lk(g_jit_mu);
+  g_jit_cv.wait(lk, [] { return g_pending == 0; });
+  return 0;
+}
+
+int tqb_jit_stats(int64_t *out4) {
+  std::lock_guard<std::mutex> lk(g_jit_mu);
+  out4[0] = g_spec_launches.load();
+  out4[1] = g_spec_compiles.load();
+  out4[2] = g_spec_disk_hits.load();
+  out4[3] = (int64_t)g_cache.size();
+  return 0;
+}
+
+// The generated constants + the kernel template of one pass (what NVRTC would compile); returns the length needed
+// (including the terminating 0), or a negative value when the pass is not eligible (tqb_last_error() says why).
+int64_t tqb_spec_source(const tqb_pass *pass, const tqb_gate *gates_host, int dtype, int with_template, char *buf,
+                        int64_t cap) {
+  if (!pass || !gates_host) return fail("tqb_spec_source: null argument");
+  SpecPlan plan;
+  std::string why;
+  if (!spec_plan(*pass, gates_host, dtype, plan, why)) return fail("pass not eligible for specialisation: " + why);
+  std::string s = spec_header(plan);
+  if (with_template) s += kSpecTemplate;
+  if (buf && cap > 0) {
+    const size_t n = std::min((size_t)cap - 1, s.size());
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)s.size() + 1;
+}
+
+// NVRTC-compile one pass for sm_100a without launching anything (works without a GPU); fills the disk cache.
+int tqb_spec_compile(const tqb_pass *pass, const tqb_gate *gates_host, int dtype) {
+  if (!pass || !gates_host) return fail("tqb_spec_compile: null argument");
+  SpecPlan plan;
+  std::string why;
+  if (!spec_plan(*pass, gates_host, dtype, plan, why)) return fail("pass not eligible for specialisation: " + why);
+  SpecKernel k;
+  k.header = spec_header(plan);
+  build_kernel(k);
+  if (k.state.load() != SpecKernel::READY) return fail("NVRTC: " + k.log);
+  return (int)k.cubin.size();
+}
+
+}  // extern "C"

@@ -428,119 +428,6 @@ tile_pass_lean_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const lon
   }
 }
 
-// ---- ring variant: one CTA per SM, one producer warp, G consumer groups, NB-deep tile ring ----------
-// With one tile in flight per CTA (two buffers) the memory system sees at most 3 x 32 KiB per SM and only
-// while a CTA is not computing (ncu: DRAM 59 % busy, FP64 40 % busy, time = sum of both).  Here a single
-// CTA owns all of the SM's shared memory as a ring of NB tiles: tile `it` lives in buffer it % NB, is computed
-// by consumer group it % G (128 threads, named barrier 1 + group), loads run K = NB - S tiles ahead and up
-// to S bulk stores drain behind, so loads, stores and G computations overlap inside one CTA.
-template <typename T, int MAXK>
-__global__ void __launch_bounds__(608, 1)
-tile_pass_ring_kernel(cplx<T> *__restrict__ state, const TileGeom geo, const long long batch,
-                      const tqb_gate *__restrict__ gates, const int n_gates, const cplx<T> *__restrict__ mats,
-                      const int NB, const int G, const int S, const int PW) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: NB tiles | 16 mbarrier slots (full[8], done[8]) | staged matrices | run-offset table | descriptors
-  const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NB * tile_bytes);
-  uint64_t *done = full + 8;
-  cplx<T> *smats = reinterpret_cast<cplx<T> *>(full + 16);
-  uint64_t *roff = reinterpret_cast<uint64_t *>(smats + geo.mat_count);
-  tqb_gate *sg = reinterpret_cast<tqb_gate *>(roff + (1u << geo.h));
-
-  const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int ncons = nthreads - 32 * PW;  // the last PW warps are producers; producer w moves runs j = w (mod PW)
-  const int gsize = ncons / G;  // threads per consumer group
-  const int lane = tid & 31;
-  const bool producer = tid >= ncons;
-  for (uint32_t j = tid; j < (1u << geo.h); j += nthreads) roff[j] = run_offset(geo, j);
-  for (int i = tid; i < geo.mat_count; i += nthreads) smats[i] = mats[geo.mat_begin + i];
-  {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(gates);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(sg);
-    const int nw = n_gates * (int)(sizeof(tqb_gate) / 4);
-    for (int i = tid; i < nw; i += nthreads) dst[i] = src[i];
-  }
-  if (tid == 0) {
-    for (int i = 0; i < NB; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&done[i], (uint32_t)gsize);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const int tb = geo.n - geo.m;
-  const unsigned long long total = (unsigned long long)batch << tb;
-  const unsigned long long first = blockIdx.x, stride = gridDim.x;
-  const unsigned long long count = first < total ? (total - first + stride - 1) / stride : 0;
-  const uint32_t nruns = 1u << geo.h;
-  const uint32_t run_elems = 1u << geo.L;
-  const uint32_t run_bytes = (uint32_t)(sizeof(cplx<T>) << geo.L);
-
-  if (producer) {
-    const unsigned long long K = (unsigned long long)(NB - S);  // prefetch distance
-    const int pw = (tid - ncons) >> 5;
-    const uint32_t jstep = 32u * (uint32_t)PW, j0 = (uint32_t)(pw * 32 + lane);
-    auto tile_ptr = [&](unsigned long long it) -> cplx<T> * {
-      const unsigned long long tt = first + it * stride;
-      return state + ((tt >> tb) << geo.n) + tile_base(geo, tt & ((1ull << tb) - 1ull));
-    };
-    auto issue_load = [&](unsigned long long it) {
-      const int b = (int)(it % NB);
-      cplx<T> *dst = reinterpret_cast<cplx<T> *>(smem_raw + (size_t)b * tile_bytes);
-      const cplx<T> *src = tile_ptr(it);
-      if (pw == 0 && lane == 0) mbar_expect_tx(&full[b], (uint32_t)tile_bytes);
-      __syncwarp();
-      for (uint32_t j = j0; j < nruns; j += jstep) bulk_load(dst + (size_t)j * run_elems, src + roff[j], run_bytes, &full[b]);
-    };
-    for (unsigned long long it = 0; it < K && it < count; ++it) issue_load(it);
-    for (unsigned long long it = 0; it < count; ++it) {
-      const int b = (int)(it % NB);
-      mbar_wait(&done[b], (uint32_t)((it / NB) & 1));  // group it % G finished tile it
-      cplx<T> *dstg = tile_ptr(it);
-      const cplx<T> *srcs = reinterpret_cast<const cplx<T> *>(smem_raw + (size_t)b * tile_bytes);
-      for (uint32_t j = j0; j < nruns; j += jstep) bulk_store(dstg + roff[j], srcs + (size_t)j * run_elems, run_bytes);
-      bulk_commit();
-      if (it + K < count) {
-        // tile it+K reuses the buffer of tile it+K-NB = it-S: all but the S newest bulk stores have read their source
-        if (S == 1) bulk_wait_read<1>();
-        else if (S == 2) bulk_wait_read<2>();
-        else bulk_wait_read<3>();
-        __syncwarp();
-        issue_load(it + K);
-      }
-    }
-    bulk_wait_all0();
-    return;
-  }
-
-  const int group = tid / gsize;
-  const int gtid = tid - group * gsize;
-  for (unsigned long long it = (unsigned long long)group; it < count; it += (unsigned long long)G) {
-    const int b = (int)(it % NB);
-    mbar_wait(&full[b], (uint32_t)((it / NB) & 1));
-    const unsigned long long tt = first + it * stride;
-    const unsigned long long bm = tt >> tb;
-    const uint64_t base = tile_base(geo, tt & ((1ull << tb) - 1ull));
-    cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw + (size_t)b * tile_bytes);
-    if (geo.mat_count > 0) {
-      const cplx<T> *sm = smats - geo.mat_begin;
-      for (int gi = 0; gi < n_gates; ++gi) {
-        tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], sm, (size_t)0, gtid, gsize);
-        if (gi + 1 < n_gates) asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(gsize) : "memory");
-      }
-    } else {
-      for (int gi = 0; gi < n_gates; ++gi) {
-        tile_apply_gate<T, MAXK>(tile, geo, roff, geo.global_base | base, sg[gi], mats, (size_t)bm, gtid, gsize);
-        if (gi + 1 < n_gates) asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(gsize) : "memory");
-      }
-    }
-    fence_proxy_async();
-    mbar_arrive(&done[b]);
-  }
-}
-
 template <typename T>
 __global__ void init_basis_kernel(cplx<T> *state, int n, long long batch, unsigned long long local_index,
                                   int present) {
@@ -594,8 +481,8 @@ static int launch_pass_tma(void *state, const TileGeom &geo, int64_t batch, cons
   if (threads > max_threads) threads = max_threads;
   const size_t smem = NB * (sizeof(cplx<T>) << geo.m) + 64 + (sizeof(uint64_t) << geo.h) +
                       (size_t)geo.mat_count * sizeof(cplx<T>) + (size_t)n_gates * sizeof(tqb_gate);
-  // caller falls back (fewer buffers, then the single-buffer kernel); 3 buffers only with >= 2 CTAs per SM
-  if (smem > (size_t)ws.max_smem_optin || (NB == 3 && 2 * (smem + 1024) > (size_t)228 * 1024)) return 0;
+  // caller falls back to the single-buffer kernel
+  if (smem > (size_t)ws.max_smem_optin) return 0;
   auto kern = tile_pass_tma_kernel<T, MAXK, NB>;
   static thread_local bool configured = false;
   if (!configured) {
@@ -652,40 +539,6 @@ static int launch_pass_lean(void *state, const TileGeom &geo, int64_t batch, con
   return 0;
 }
 
-template <typename T, int MAXK>
-static int launch_pass_ring(void *state, const TileGeom &geo, int64_t batch, const tqb_gate *gates, int n_gates,
-                            const void *mats, int threads, const Workspace &ws, cudaStream_t st, bool *used) {
-  *used = false;
-  const size_t tile_bytes = sizeof(cplx<T>) << geo.m;
-  const size_t extras = 128 + (sizeof(uint64_t) << geo.h) + (size_t)geo.mat_count * sizeof(cplx<T>) + (size_t)n_gates * sizeof(tqb_gate);
-  if (extras + 3 * tile_bytes > (size_t)ws.max_smem_optin) return 0;
-  int NB = (int)(((size_t)ws.max_smem_optin - extras) / tile_bytes);
-  if (NB > 8) NB = 8;
-  const int G = NB >= 6 ? 3 : (NB >= 4 ? 2 : 1);
-  const int S = NB - G >= 3 ? 2 : 1;   // loads run NB - S tiles ahead
-  if (threads > 160) threads = 160;
-  if (threads < 32) threads = 32;
-  threads = (threads / 32) * 32;
-  const size_t smem = extras + (size_t)NB * tile_bytes;
-  auto kern = tile_pass_ring_kernel<T, MAXK>;
-  static thread_local bool configured = false;
-  if (!configured) {
-    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws.max_smem_optin));
-    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    configured = true;
-  }
-  const unsigned long long total = (unsigned long long)batch << (geo.n - geo.m);
-  unsigned long long grid = (unsigned long long)ws.sm_count;
-  if (grid > total) grid = total;
-  const int PW = 4;
-  const int block = G * threads + 32 * PW;
-  kern<<<(unsigned)grid, block, smem, st>>>(reinterpret_cast<cplx<T> *>(state), geo, (long long)batch, gates, n_gates,
-                                             reinterpret_cast<const cplx<T> *>(mats), NB, G, S, PW);
-  TQB_CHECK_LAUNCH("tile_pass_ring_kernel");
-  *used = true;
-  return 0;
-}
-
 }  // namespace tqb
 
 using namespace tqb;
@@ -700,7 +553,7 @@ int tqb_set_tma(int mode) {
     g_dbg.store(mode - 256);
     return g_use_tma.load();
   }
-  const int old = g_use_tma.exchange(mode < 0 ? 0 : (mode > 4 ? 1 : mode));
+  const int old = g_use_tma.exchange(mode < 0 ? 0 : (mode > 2 ? 1 : mode));
   return old;
 }
 
@@ -768,6 +621,13 @@ int tqb_init_basis(void *state, int n, int64_t batch, int dtype, uint64_t global
 int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global_base, const tqb_pass *passes,
                    int n_passes, const tqb_gate *gates_dev, const void *mats_dev, int threads, int ctas_per_sm,
                    void *stream) {
+  return tqb_run_passes2(state, n, batch, dtype, global_base, passes, n_passes, gates_dev, nullptr, mats_dev, threads,
+                         ctas_per_sm, stream);
+}
+
+int tqb_run_passes2(void *state, int n, int64_t batch, int dtype, uint64_t global_base, const tqb_pass *passes,
+                    int n_passes, const tqb_gate *gates_dev, const tqb_gate *gates_host, const void *mats_dev,
+                    int threads, int ctas_per_sm, void *stream) {
   TQB_REQUIRE(state && n >= 0 && n < 48 && batch >= 1, "tqb_run_passes: bad state arguments");
   TQB_REQUIRE(dtype == TQB_C64 || dtype == TQB_C128, "tqb_run_passes: bad dtype");
   TQB_REQUIRE(threads >= 32 && threads <= 1024 && threads % 32 == 0, "tqb_run_passes: bad CTA size");
@@ -801,7 +661,13 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
     if (g_use_tma.load() && run_bytes >= 128 && n > ps.m) {
       bool used = false;
       rc = 0;
-      if (ps.max_dense_k < 0 && g_lean.load() && g_use_tma.load() != 4) {
+      if (ps.max_dense_k < 0 && gates_host && g_lean.load()) {
+        // the pass's own specialised kernel (tqb_jit.cu), when it is compiled and loaded
+        rc = spec_try_launch(state, geo.n, batch, dtype, global_base, ps, gates_host, mats_dev, *ws, st, &used);
+        if (rc) return rc;
+        if (used) continue;
+      }
+      if (ps.max_dense_k < 0 && g_lean.load()) {
 #define TQB_LEAN(T, GM, PAD) launch_pass_lean<T, 2, 128, GM, PAD>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
         const bool pad = ps.max_dense_k == -2;   // the planner's request for the padded tile layout
         if (dtype == TQB_C128) {
@@ -816,22 +682,7 @@ int tqb_run_passes(void *state, int n, int64_t batch, int dtype, uint64_t global
         if (used) continue;
       }
 #ifndef TQB_LEAN_ONLY  // (defined only for quick SASS inspection builds of the lean kernel: tools/sass_lean.sh)
-      if (g_use_tma.load() == 4) {  // ring: one CTA per SM, G consumer groups, NB-deep tile ring
-        if (dtype == TQB_C128)
-          rc = heavy ? launch_pass_ring<double, 4>(state, geo, batch, g, ps.n_gates, mats_dev, threads, *ws, st, &used)
-                     : launch_pass_ring<double, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, *ws, st, &used);
-        else
-          rc = heavy ? launch_pass_ring<float, 4>(state, geo, batch, g, ps.n_gates, mats_dev, threads, *ws, st, &used)
-                     : launch_pass_ring<float, 2>(state, geo, batch, g, ps.n_gates, mats_dev, threads, *ws, st, &used);
-        if (rc) return rc;
-        if (used) continue;
-      }
 #define TQB_TMA(T, MK, NB) launch_pass_tma<T, MK, NB>(state, geo, batch, g, ps.n_gates, mats_dev, threads, ctas_per_sm, *ws, st, &used)
-      if (g_use_tma.load() == 3) {  // 3 = three buffers when two CTAs still fit; 1 (auto) and 2 = two buffers
-        if (dtype == TQB_C128) rc = heavy ? TQB_TMA(double, 4, 3) : TQB_TMA(double, 2, 3);
-        else rc = heavy ? TQB_TMA(float, 4, 3) : TQB_TMA(float, 2, 3);
-        if (rc) return rc;
-      }
       if (!used) {
         if (dtype == TQB_C128) rc = heavy ? TQB_TMA(double, 4, 2) : TQB_TMA(double, 2, 2);
         else rc = heavy ? TQB_TMA(float, 4, 2) : TQB_TMA(float, 2, 2);

@@ -60,6 +60,7 @@ class DeviceProgram:
         self.dtype = dtype
         self.h2d_bytes = 0
         self._passes = np.ascontiguousarray(prog.passes)
+        self._gates_host = np.ascontiguousarray(prog.gates)   # host copy: lets the library pick specialised kernels
         with torch.cuda.device(self.device):
             g_host = torch.from_numpy(prog.gates.view(np.uint8).reshape(-1).copy()).pin_memory() if prog.gates.size else None
             self.gates_dev = (g_host.to(self.device, non_blocking=True) if g_host is not None
@@ -98,9 +99,10 @@ class DeviceProgram:
                 raise _lib.TqbError(f"program compiled for n={self.prog.n}, state has n={n}")
             if self.prog.n_passes:
                 t = self.prog.tile
-                _lib.check(_lib.load().tqb_run_passes(
+                _lib.check(_lib.load().tqb_run_passes2(
                     ptr, n, batch, dt, global_base, self._passes.ctypes.data, self.prog.n_passes,
-                    self.gates_dev.data_ptr(), self.mats_dev.data_ptr(), t.threads, t.ctas_per_sm, stream))
+                    self.gates_dev.data_ptr(), self._gates_host.ctypes.data, self.mats_dev.data_ptr(), t.threads,
+                    t.ctas_per_sm, stream))
         return state
 
 
