@@ -19,9 +19,12 @@ typedef void (*gate_fn)(char *, const amp *, unsigned, unsigned);
 struct NoSync {
   void operator()() const {}
 };
+static amp g_v[D];   // a thread's register block: lives across gates that are fused in registers (sync == -1)
 template <int GI>
 static void run_gate(char *tile, const amp *sm, unsigned tid, unsigned extv) {
-  apply_gate<GI>(tile, sm, tid, extv, NoSync());
+  if (!fuse_in(GI))
+    for (int s = 0; s < D; ++s) g_v[s] = amp{(T)1e300, (T)-1e300};   // poison: a gate that is not fused must load
+  apply_gate<GI>(tile, sm, tid, extv, g_v, NoSync());
 }
 
 extern "C" int spec_emu_run(void *state_v, int n, long long batch, unsigned long long global_base, const signed char *hb,

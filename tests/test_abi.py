@@ -26,7 +26,7 @@ def test_library_builds_and_exports_header_symbols():
         assert hasattr(lib, s), f"{s} declared in include/tyxonq_b200.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == syms
-    assert lib.tqb_abi_version() == 1
+    assert lib.tqb_abi_version() == 2
 
 
 def test_struct_layouts_match_header():

@@ -113,9 +113,11 @@ static int map_gate(SpecGate &s, int m, int rbits, int es, int padL, uint32_t W)
   int best = 1 << 30;
   SpecGate best_s = s;
   const int nc = (int)cand.size();
-  // enumerate filler subsets (nf of nc candidates) by bitmask
-  for (uint32_t sub = 0; sub < (1u << nc); ++sub) {
+  // enumerate filler subsets (nf of nc candidates) by bitmask, at most 24 of them (high bits first)
+  int tried = 0;
+  for (uint32_t sub = (1u << nc); sub-- > 0;) {
     if (popc(sub) != nf) continue;
+    if (++tried > 24) break;
     uint32_t fillers = 0;
     for (int i = 0; i < nc; ++i)
       if ((sub >> i) & 1u) fillers |= 1u << cand[i];
@@ -160,7 +162,8 @@ static int map_gate(SpecGate &s, int m, int rbits, int es, int padL, uint32_t W)
   return best;
 }
 
-static bool spec_plan(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPlan &P, std::string &why) {
+// cheap half: the pass in normalised form (outside-the-tile bits as slots, matrix offsets relative to the pass)
+static bool spec_parse(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPlan &P, std::string &why) {
   const int m = ps.m, L = ps.L, h = ps.m - ps.L;
   const int es = dtype == TQB_C128 ? 16 : 8;
   P = SpecPlan();
@@ -266,66 +269,114 @@ static bool spec_plan(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPla
     if (!ok) return why = "bad gate bits", false;
     P.g.push_back(s);
   }
+  return true;
+}
+
+// The shape of a parsed pass: everything the generated constants depend on (NOT the outside-the-tile bit positions).
+static std::string shape_key(const SpecPlan &P) {
+  std::string k;
+  auto put = [&](int v) { k.append(reinterpret_cast<const char *>(&v), sizeof v); };
+  put(P.dtype); put(P.m); put(P.L); put(P.mat_count); put(P.next); put((int)P.g.size());
+  for (const SpecGate &s : P.g) {
+    put(s.kind); put(s.R); put(s.type); put(s.muxed); put(s.unit_p); put(s.E); put(s.ctrl); put(s.mat);
+    put(s.xb[0]); put(s.xb[1]);
+    for (int j = 0; j < 6; ++j) put(s.dbits[j]);
+    for (int j = 0; j < 5; ++j) put(s.kind == K_DIAG ? -1 : (j < s.R ? s.rb[j] : -1));
+  }
+  return k;
+}
+
+// expensive half: segments, warp bits, register / lane maps, tile layout (a search with exact bank-conflict counts)
+static bool spec_search(SpecPlan &P, std::string &why) {
+  const int m = P.m, L = P.L, h = P.m - P.L;
+  const int es = P.dtype == TQB_C128 ? 16 : 8;
   const int ng = (int)P.g.size();
   const uint32_t all = (1u << m) - 1u;
 
-  // segments: maximal runs of gates that leave >= 2 tile bits untargeted (the warp bits of the segment)
-  struct Seg { int lo, hi; uint32_t C; };
-  std::vector<Seg> segs;
-  for (int i = 0; i < ng;) {
-    uint32_t C = all;
-    int j = i;
-    while (j < ng) {
-      const uint32_t C2 = C & ~P.g[j].targets;
-      if (popc(C2) < 2 && j > i) break;
-      C = C2;
-      ++j;
-    }
-    if (popc(C) < 2) return why = "no warp bits", false;
-    segs.push_back({i, j, C});
-    i = j;
-  }
+  // Segments and warp bits.  A segment is a run of gates that leaves >= 2 tile bits untargeted: those become the warp
+  // bits W of the segment (gates inside it are separated by __syncwarp() only), segments are separated by the
+  // consumers' barrier.  cost[g][W] = bank conflicts of gate g's best mapping under W (memoised: map_gate is a search);
+  // a dynamic program over the segment boundaries minimises conflicts + BARRIER per boundary, for the plain and the
+  // padded tile layout.
+  const int BARRIER = 4000;
+  std::vector<uint32_t> pairs;
+  for (int a = 0; a < m; ++a)
+    for (int b = a + 1; b < m; ++b) pairs.push_back((1u << a) | (1u << b));
+  const int np = (int)pairs.size();
   int best_total = 1 << 30;
   std::vector<SpecGate> best_g;
   int best_pad = 0;
   const bool can_pad = L >= 1 && L <= 7 && h > 0;
   for (int pad = 0; pad < (can_pad ? 2 : 1); ++pad) {
     const int padL = pad ? L : 0;
-    std::vector<SpecGate> cur = P.g;
-    int total = 0;
-    for (const Seg &sg : segs) {
-      int seg_best = 1 << 30;
-      std::vector<SpecGate> seg_g;
-      for (int a = 0; a < m; ++a)
-        for (int b = a + 1; b < m; ++b) {
-          if (!((sg.C >> a) & 1u) || !((sg.C >> b) & 1u)) continue;
-          const uint32_t W = (1u << a) | (1u << b);
+    // memo over (targets, reserved, kind-independent): gates of the same shape share the search
+    std::unordered_map<uint64_t, std::pair<int, SpecGate>> memo;
+    auto gate_cost = [&](int gi, int pi) -> std::pair<int, SpecGate> {
+      const SpecGate &s0 = P.g[gi];
+      const uint32_t W = pairs[pi];
+      const uint64_t key = ((uint64_t)s0.targets << 40) ^ ((uint64_t)s0.reserved << 16) ^ (uint64_t)pi ^ ((uint64_t)s0.R << 60);
+      auto it = memo.find(key);
+      if (it != memo.end()) {
+        // same shape: copy the mapping, keep the gate's own fields
+        SpecGate t = s0;
+        const SpecGate &src = it->second.second;
+        // (targets are listed in the gate's own layer order; fillers follow)
+        for (int k = s0.kind == K_DIAG ? 0 : s0.R; k < 5; ++k) t.rb[k] = src.rb[k];
+        for (int k = 0; k < 7; ++k) t.tb[k] = src.tb[k];
+        return {it->second.first, t};
+      }
+      SpecGate t = s0;
+      int c;
+      if (popc(all & ~t.targets & ~W & ~t.reserved) < P.rbits - popc(t.targets)) c = 1 << 28;
+      else c = map_gate(t, m, P.rbits, es, padL, W);
+      memo[key] = {c, t};
+      return {c, t};
+    };
+    // dp[i] = best cost of gates i.. ; choice[i] = (j, pair)
+    std::vector<int> dp(ng + 1, 1 << 30), nxt(ng + 1, -1), pick(ng + 1, -1);
+    dp[ng] = 0;
+    for (int i = ng - 1; i >= 0; --i) {
+      uint32_t C = all;
+      for (int j = i + 1; j <= ng; ++j) {
+        C &= ~P.g[j - 1].targets;
+        if (popc(C) < 2) break;
+        if (dp[j] >= (1 << 28)) continue;
+        for (int pi = 0; pi < np; ++pi) {
+          if ((pairs[pi] & C) != pairs[pi]) continue;
           int c = 0;
-          std::vector<SpecGate> tmp(P.g.begin() + sg.lo, P.g.begin() + sg.hi);
-          bool feasible = true;
-          for (SpecGate &s : tmp) {
-            if (s.kind == K_DIAG) continue;
-            // the fillers must exist outside targets, W and the reserved bits
-            if (popc(all & ~s.targets & ~W & ~s.reserved) < P.rbits - popc(s.targets)) { feasible = false; break; }
-            c += map_gate(s, m, P.rbits, es, padL, W);
-          }
-          if (!feasible) continue;
-          c -= (a + b);   // tie: higher warp bits
-          if (c < seg_best) {
-            seg_best = c;
-            seg_g = tmp;
+          for (int g = i; g < j && c < (1 << 28); ++g)
+            if (P.g[g].kind != K_DIAG) c += gate_cost(g, pi).first;
+          if (c >= (1 << 28)) continue;
+          c += dp[j] + (j < ng ? BARRIER : 0);
+          // tie: prefer longer segments, then higher warp bits
+          if (c < dp[i] || (c == dp[i] && (j > nxt[i] || (j == nxt[i] && pairs[pi] > pairs[pick[i]])))) {
+            dp[i] = c;
+            nxt[i] = j;
+            pick[i] = pi;
           }
         }
-      if (seg_best == (1 << 30)) return why = "no feasible warp bits", false;
-      total += seg_best;
-      for (int i = sg.lo; i < sg.hi; ++i) cur[i] = seg_g[i - sg.lo];
+      }
     }
-    if (total < best_total) {
-      best_total = total;
+    if (dp[0] >= (1 << 28)) continue;
+    std::vector<SpecGate> cur = P.g;
+    for (int i = 0; i < ng;) {
+      const int j = nxt[i], pi = pick[i];
+      for (int g = i; g < j; ++g)
+        if (P.g[g].kind != K_DIAG) cur[g] = gate_cost(g, pi).second;
+        else {   // remember the segment's warp bits on diagonal gates too (used when the whole segment is diagonal)
+          int w = 5;
+          for (int b = 0; b < m; ++b)
+            if ((pairs[pi] >> b) & 1u) cur[g].tb[w++] = b;
+        }
+      i = j;
+    }
+    if (dp[0] < best_total) {
+      best_total = dp[0];
       best_g = cur;
       best_pad = padL;
     }
   }
+  if (best_total == (1 << 30)) return why = "no feasible warp bits", false;
   P.g = best_g;
   P.padL = best_pad;
   // DIAG gates ride on a neighbour's mapping (same thread, same amplitudes: no synchronisation in between)
@@ -378,6 +429,10 @@ static bool spec_plan(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPla
       if ((s.reserved >> s.rb[k]) & 1u) return why = "internal: reserved bit in registers", false;
   }
   return true;
+}
+
+static bool spec_plan(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPlan &P, std::string &why) {
+  return spec_parse(ps, gh, dtype, P, why) && spec_search(P, why);
 }
 
 static std::string spec_header(const SpecPlan &P) {
@@ -503,6 +558,7 @@ struct SpecParams {  // must match tqbs::SpecParams in tqb_spec.cuh
 struct SpecKernel {
   enum State { PENDING, READY, FAILED };
   std::atomic<int> state{PENDING};
+  SpecPlan plan;        // parsed by the launching thread, searched by build_kernel
   std::string header;
   std::vector<char> cubin;
   std::string log;
@@ -510,6 +566,7 @@ struct SpecKernel {
   cudaKernel_t kern = nullptr;
   bool loaded = false;
   bool configured = false;
+  bool rejected = false;   // the search found no mapping: the generic kernel runs the pass (not an error)
   int resident = 0;
   size_t smem = 0;
   int64_t uses = 0;
@@ -517,8 +574,7 @@ struct SpecKernel {
 
 static std::mutex g_jit_mu;
 static std::condition_variable g_jit_cv;
-static std::unordered_map<std::string, std::shared_ptr<SpecKernel>> g_cache;   // key: header text
-static std::unordered_map<std::string, std::string> g_reject;                  // pass signature -> why (not eligible)
+static std::unordered_map<std::string, std::shared_ptr<SpecKernel>> g_cache;   // key: shape_key() of the parsed pass
 static std::deque<std::shared_ptr<SpecKernel>> g_queue;
 static std::vector<std::thread> g_workers;
 static int g_pending = 0;
@@ -544,6 +600,16 @@ static std::string disk_path(const std::string &header) {
 }
 
 static void build_kernel(SpecKernel &k) {
+  if (k.header.empty()) {
+    std::string why;
+    if (!spec_search(k.plan, why)) {
+      k.log = "not eligible: " + why;
+      k.rejected = true;
+      k.state.store(SpecKernel::FAILED);
+      return;
+    }
+    k.header = spec_header(k.plan);
+  }
   const std::string path = disk_path(k.header);
   if (!path.empty()) {
     if (FILE *f = fopen(path.c_str(), "rb")) {
@@ -598,18 +664,6 @@ static void worker_main() {
   }
 }
 
-static std::string pass_signature(const tqb_pass &ps, const tqb_gate *gh, int dtype) {
-  std::string s;
-  s.append(reinterpret_cast<const char *>(&dtype), sizeof dtype);
-  s.append(reinterpret_cast<const char *>(&ps.m), sizeof(int32_t) * 2);
-  s.append(reinterpret_cast<const char *>(&ps.n_gates), sizeof(int32_t) * 4);
-  for (int i = 0; i < ps.n_gates; ++i) {
-    const tqb_gate &q = gh[ps.gate_begin + i];
-    s.append(reinterpret_cast<const char *>(&q), offsetof(tqb_gate, zmask));
-  }
-  return s;
-}
-
 // Try to run pass `ps` with its specialised kernel.  *used = false: the caller runs the generic kernel.
 int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t global_base, const tqb_pass &ps,
                     const tqb_gate *gates_host, const void *mats_dev, const Workspace &ws, cudaStream_t st, bool *used) {
@@ -617,30 +671,20 @@ int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t globa
   const int mode = g_jit_mode.load();
   if (mode == 0 || !gates_host || n <= ps.m) return 0;
   std::shared_ptr<SpecKernel> k;
-  SpecPlan plan;
+  SpecPlan parsed;
   {
-    // (planning is deterministic; rejected shapes are remembered by their raw signature)
-    const std::string sig = pass_signature(ps, gates_host, dtype);
-    {
-      std::lock_guard<std::mutex> lk(g_jit_mu);
-      if (g_reject.count(sig)) return 0;
-    }
     std::string why;
-    if (!spec_plan(ps, gates_host, dtype, plan, why)) {
-      std::lock_guard<std::mutex> lk(g_jit_mu);
-      g_reject[sig] = why;
-      return 0;
-    }
+    if (!spec_parse(ps, gates_host, dtype, parsed, why)) return 0;
   }
-  const std::string header = spec_header(plan);
+  const std::string key = shape_key(parsed);
   bool fresh = false;
   {
     std::lock_guard<std::mutex> lk(g_jit_mu);
-    auto it = g_cache.find(header);
+    auto it = g_cache.find(key);
     if (it == g_cache.end()) {
       k = std::make_shared<SpecKernel>();
-      k->header = header;
-      g_cache[header] = k;
+      k->plan = parsed;
+      g_cache[key] = k;
       fresh = true;
       if (mode == 1) {
         if (g_workers.empty()) {
@@ -669,8 +713,9 @@ int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t globa
     g_jit_cv.wait_for(lk, std::chrono::seconds(120), [&] { return k->state.load() != SpecKernel::PENDING; });
   }
   const int stt = k->state.load();
+  const SpecPlan &plan = k->plan;   // (searched: padL is final; the outside-the-tile positions come from `parsed`)
   if (stt == SpecKernel::FAILED) {
-    if (mode >= 2) return fail("tqb_run_passes: NVRTC failed for a specialised pass: " + k->log);
+    if (mode >= 2 && !k->rejected) return fail("tqb_run_passes: NVRTC failed for a specialised pass: " + k->log);
     return 0;
   }
   if (stt != SpecKernel::READY) return 0;
@@ -718,7 +763,7 @@ int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t globa
   prm.n = n;
   prm.dbg = g_jit_dbg.load();
   for (int i = 0; i < h && i < 16; ++i) prm.hb[i] = ps.hb[i];
-  for (int j = 0; j < plan.next; ++j) prm.ext[j] = (signed char)plan.ext[j];
+  for (int j = 0; j < parsed.next && j < 8; ++j) prm.ext[j] = (signed char)parsed.ext[j];
   const unsigned long long total = (unsigned long long)batch << (n - ps.m);
   unsigned long long grid = (unsigned long long)ws.sm_count * k->resident;
   if (grid > total) grid = total;

@@ -107,6 +107,21 @@ SPEC_HD unsigned diag_tvar(int s) {
   return t;
 }
 
+// Register fusion: a gate whose mapping equals its predecessor's (sync == -1: same thread, same amplitudes) takes its
+// block straight from the predecessor's registers instead of a shared-memory round trip -- unless it is a rotation
+// chain with a run-time control, whose loads rename the inputs.
+SPEC_HD bool fuse_in(int gi) {
+  return gi > 0 && gi < NG && G[gi].sync == -1 && !(G[gi].kind == K_ROT && G[gi].ctrl >= 0);
+}
+// register index of gate GI that holds tile element offset o (o is a union of GI's register bits)
+template <int GI>
+SPEC_HD int reg_of_offset(unsigned o) {
+  int s = 0;
+  for (int i = 0; i < RBITS; ++i)
+    if ((o >> G[GI].rb[i]) & 1u) s |= 1 << i;
+  return s;
+}
+
 // tile element index of the thread's block (register bits zero)
 template <int GI>
 SPEC_DEV unsigned thread_base(unsigned tid) {
@@ -247,14 +262,35 @@ SPEC_DEV amp cmul(const amp a, const amp b) { return amp{a.x * b.x - a.y * b.y, 
 // tile: byte address of the tile buffer; sm: the pass's staged matrices; extv: values of the outside-the-tile bits;
 // sync(): called once, right before the first tile access (after the address arithmetic)
 template <int GI, class Sync>
-SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv, Sync sync) {
+SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv, amp (&v)[D], Sync sync) {
   constexpr int KIND = G[GI].kind;
   constexpr int R = G[GI].R;
+  constexpr bool FIN = fuse_in(GI), FOUT = fuse_in(GI + 1);
   const unsigned base = thread_base<GI>(tid);
   char *const tb0 = tile + pbyte(base);
   constexpr int MAT = G[GI].mat;
   const amp *const Mg = sm + MAT;
-  amp v[D];
+  if constexpr (FIN) {   // rename the predecessor's registers into this gate's register order (no instructions)
+    amp t[D];
+    static_for<D>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      constexpr int sp = reg_of_offset<(GI > 0 ? GI - 1 : 0)>(soff<GI>(s));
+      t[s] = v[sp];
+    });
+    static_for<D>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      v[s] = t[s];
+    });
+  }
+  // plain load of the block (element s -> register s)
+  auto load_block = [&]() {
+    if constexpr (!FIN) {
+      static_for<D>([&](auto sc) {
+        constexpr int s = decltype(sc)::value;
+        v[s] = *reinterpret_cast<const amp *>(tb0 + pbyte(soff<GI>(s)));
+      });
+    }
+  };
 
   if constexpr (KIND == K_ROT) {
     constexpr int TYPE = G[GI].type;
@@ -270,7 +306,12 @@ SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv,
     unsigned x = 0;
     if constexpr (E > 0) x |= bit_value<GI, G[GI].xb[0]>(base, extv);
     if constexpr (E > 1) x |= bit_value<GI, G[GI].xb[1]>(base, extv) << 1;
-    const amp *const P = Mg + (x << R) + (cv ? TAB : 0u);
+    // table entry of register s is P[(s & mask) ^ cv] (the gate's second table copy is the first with index bit 0
+    // flipped): even registers read at +cv, odd ones at -cv, so lanes with different control values read ADJACENT
+    // entries -- different banks, one wavefront -- instead of two copies 2^(R+E) entries apart
+    const amp *const P = Mg + (x << R);
+    const amp *const Pe = P + cv;
+    const amp *const Po = P - cv;
     const amp *const coef = Mg + (HAS_CTRL ? 2u * TAB : TAB);
     const T a0 = coef[0].x;
     T r0 = coef[0].y;
@@ -291,9 +332,11 @@ SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv,
     static_for<D>([&](auto sc) {
       constexpr int s = decltype(sc)::value;
       constexpr unsigned o = pbyte(soff<GI>(s & ~1));
-      const amp in = *reinterpret_cast<const amp *>(((s & 1) ? pb : pa) + o);
+      amp in;
+      if constexpr (FIN) in = v[s];
+      else in = *reinterpret_cast<const amp *>(((s & 1) ? pb : pa) + o);
       if constexpr (G[GI].unit_p != 0) v[s] = in;
-      else v[s] = cmul(in, P[s & ((1 << R) - 1)]);
+      else v[s] = cmul(in, ((s & 1) ? Po : Pe)[s & ((1 << R) - 1)]);
     });
     rot_layer<0, TYPE, false>(v, a0, r0);
     if constexpr (R > 1) rot_layer_scaled<(R > 1 ? 1 : 0), TYPE, MUXED>(v, kk[1], inv[1]);
@@ -304,10 +347,7 @@ SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv,
     // control, layer i > 0 by register bit i-1 after layer i-1
     const unsigned cv = bit_value<GI, G[GI].ctrl>(base, extv);
     sync();
-    static_for<D>([&](auto sc) {
-      constexpr int s = decltype(sc)::value;
-      v[s] = *reinterpret_cast<const amp *>(tb0 + pbyte(soff<GI>(s)));
-    });
+    load_block();
     layer_dense<0, -1>(v, Mg + 4u * cv, Mg);
     if constexpr (R > 1) layer_dense<(R > 1 ? 1 : 0), 0>(v, Mg + 8, Mg + 12);
     if constexpr (R > 2) layer_dense<(R > 2 ? 2 : 0), 1>(v, Mg + 16, Mg + 20);
@@ -315,10 +355,7 @@ SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv,
     unsigned cv = 0;
     if constexpr (KIND == K_MUX) cv = bit_value<GI, G[GI].ctrl>(base, extv);
     sync();
-    static_for<D>([&](auto sc) {
-      constexpr int s = decltype(sc)::value;
-      v[s] = *reinterpret_cast<const amp *>(tb0 + pbyte(soff<GI>(s)));
-    });
+    load_block();
     layer_dense<0, -1>(v, Mg + 4u * cv, Mg);
   } else {  // K_DIAG: table index bit j = bit dbits[j] (register bit, thread bit or outside bit)
     unsigned tfix = 0;
@@ -334,14 +371,18 @@ SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv,
     static_for<D>([&](auto sc) {
       constexpr int s = decltype(sc)::value;
       constexpr unsigned tvar = diag_tvar<GI>(s);
-      const amp in = *reinterpret_cast<const amp *>(tb0 + pbyte(soff<GI>(s)));
+      amp in;
+      if constexpr (FIN) in = v[s];
+      else in = *reinterpret_cast<const amp *>(tb0 + pbyte(soff<GI>(s)));
       v[s] = cmul(in, tab[tvar]);
     });
   }
-  static_for<D>([&](auto sc) {
-    constexpr int s = decltype(sc)::value;
-    *reinterpret_cast<amp *>(tb0 + pbyte(soff<GI>(s))) = v[s];
-  });
+  if constexpr (!FOUT) {
+    static_for<D>([&](auto sc) {
+      constexpr int s = decltype(sc)::value;
+      *reinterpret_cast<amp *>(tb0 + pbyte(soff<GI>(s))) = v[s];
+    });
+  }
 }
 
 #ifndef TQB_SPEC_EMU
@@ -526,9 +567,10 @@ extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const Spe
     if (prm.dbg & 1) {
       mbar_wait(&full[b], parity);
     } else {
+      amp v[D];
       static_for<NG>([&](auto gc) {
         constexpr int GI = decltype(gc)::value;
-        apply_gate<GI>(tile, smats, (unsigned)tid, extv, [&]() {
+        apply_gate<GI>(tile, smats, (unsigned)tid, extv, v, [&]() {
           constexpr int S = G[GI].sync;
           if constexpr (S == 0) mbar_wait(&full[b], parity);
           else if constexpr (S == 1) __syncwarp();
