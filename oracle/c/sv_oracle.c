@@ -26,6 +26,17 @@ int orc_max_threads(void) {
 #endif
 }
 
+/* Set the OpenMP thread count (torchrun exports OMP_NUM_THREADS=1); returns the count in effect. */
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 static inline uint64_t insert_zero(uint64_t g, int p) { return ((g >> p) << (p + 1)) | (g & ((1ull << p) - 1ull)); }
 
 #define DEFINE_KERNELS(T, SUF)                                                                       \

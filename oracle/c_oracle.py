@@ -28,12 +28,18 @@ def lib() -> C.CDLL:
             getattr(L, f"orc_expect_z_{suf}").restype = C.c_double
             getattr(L, f"orc_init_zero_{suf}").argtypes = [C.c_void_p, C.c_int]
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_threads.restype = C.c_int
+        L.orc_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def set_threads(n: int) -> int:
+    return int(lib().orc_set_threads(int(n)))
 
 
 def _suf(psi: np.ndarray) -> str:

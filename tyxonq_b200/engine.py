@@ -34,9 +34,30 @@ def _as_float(x: Any) -> float:
     return float(x)
 
 
+_TWO_Q = ("cx", "cz", "iswap", "swap", "rxx", "ryy", "rzz", "cry")
+
+
+def _op_wires(op: Sequence[Any]) -> Tuple[int, ...]:
+    """Qubits an op acts on, by op name (the positional qubit arguments the reference attenuates, engine.py:56-115):
+    never inferred from argument types (an integer angle is not a wire, a numpy integer is)."""
+    nm = op[0]
+    if nm in _TWO_Q or (nm == "unitary" and len(op) == 4):
+        return (int(op[1]), int(op[2]))
+    return (int(op[1]),)
+
+
+def modes_agree(circuit: Any) -> bool:
+    """True when ``run`` and ``state`` evolve the circuit identically: no ``cry`` (run only, engine.py:76-79 vs
+    918-949) and no initial state (state only)."""
+    if getattr(circuit, "_initial_state", None) is not None:
+        return False
+    return all(not (isinstance(op, (list, tuple)) and op and op[0] == "cry") for op in getattr(circuit, "ops", []))
+
+
 class StatevectorEngine:
     name = "statevector"
     capabilities = {"supports_shots": True}
+    LAST: Dict[str, int] = {}   # transfer counters of the most recent run() of any instance (the driver owns the engine)
 
     def __init__(self, backend_name: str | None = None, *, device: str | torch.device | None = None,
                  dtype: torch.dtype = torch.complex128, tile: Optional[TileConfig] = None) -> None:
@@ -57,7 +78,9 @@ class StatevectorEngine:
             backend_name = str(getattr(backend_name, "name", backend_name))
         self.backend_name = backend_name or "numpy"
         if self.backend_name not in ("numpy", "pytorch", "torch", "b200", "cuda"):
-            raise ValueError(f"unknown backend {backend_name!r}")
+            # another array backend of the reference (e.g. cupynumeric) is live: hand back numpy arrays, which every
+            # ArrayBackend accepts, instead of refusing to construct (the driver calls Engine() with no arguments)
+            self.backend_name = "numpy"
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self.dtype = dtype
         self.tile = tile
@@ -65,6 +88,7 @@ class StatevectorEngine:
         self.last_d2h_bytes = 0
         self.last_passes = 0
         self.last_gates = 0
+        self._kept: Optional[Tuple[int, int, torch.Tensor]] = None   # (id(circuit), len(ops), state) of a kept run
 
     # ------------------------------------------------------------------------------------
     # op interpretation
@@ -127,7 +151,7 @@ class StatevectorEngine:
             g = lower_op(fixed, n, mode=mode, unitary_cache=ucache)
             if g is not None:
                 pending.append(g)
-                touched.append((nm, tuple(int(a) for a in fixed[1:] if isinstance(a, int))))
+                touched.append((nm, _op_wires(fixed)))
         self._flush(state, pending)
         self._touched = touched
         return state, measures, None
@@ -160,6 +184,12 @@ class StatevectorEngine:
     # public API (reference engine.py:43-473)
     # ------------------------------------------------------------------------------------
     def run(self, circuit: Any, shots: int | None = None, **kwargs: Any) -> Dict[str, Any]:
+        out = self._run(circuit, shots, **kwargs)
+        StatevectorEngine.LAST = {"h2d_bytes": self.last_h2d_bytes, "d2h_bytes": self.last_d2h_bytes,
+                                  "passes": self.last_passes, "gates": self.last_gates}
+        return out
+
+    def _run(self, circuit: Any, shots: int | None = None, **kwargs: Any) -> Dict[str, Any]:
         shots = int(shots or 0)
         n = int(getattr(circuit, "num_qubits", 0))
         if kwargs.get("three_level"):
@@ -168,6 +198,8 @@ class StatevectorEngine:
         noise = kwargs.get("noise") if use_noise else None
         ntype = str((noise or {}).get("type", "")).lower() if noise else ""
         state, measures, _ = self._evolve(circuit, "run")
+        if kwargs.get("_keep_state"):   # the driver's shots == 0 epilogue asks for state(circuit) next (install.py)
+            self._kept = (id(circuit), len(getattr(circuit, "ops", [])), state)
         if shots > 0 and len(measures) > 0:
             # host-supplied uniforms (kwarg) or a fresh unseeded generator, like nb.rng(None) (engine.py:381)
             u = kwargs.get("uniforms")
@@ -224,8 +256,17 @@ class StatevectorEngine:
         if has_grad_params(circuit):
             psi = circuit_state_autograd(self, circuit)
         else:
-            psi, _, _ = self._evolve(circuit, "state")
+            psi = self.state_device(circuit)
         return self._export(psi)
+
+    def state_device(self, circuit: Any) -> torch.Tensor:
+        """The evolved state as a device tensor.  Reuses the state a preceding ``run(circuit, _keep_state=True)`` left
+        behind when both modes evolve the circuit identically, instead of simulating a second time."""
+        kept, self._kept = self._kept, None
+        if kept is not None and kept[0] == id(circuit) and kept[1] == len(getattr(circuit, "ops", [])) and modes_agree(circuit):
+            return kept[2]
+        psi, _, _ = self._evolve(circuit, "state")
+        return psi
 
     def _export(self, psi: torch.Tensor) -> Any:
         if self.backend_name in ("b200", "cuda"):

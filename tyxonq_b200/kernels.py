@@ -49,6 +49,62 @@ def _back(t: torch.Tensor, how: str) -> Any:
     return c.numpy() if how == "numpy" else c
 
 
+def _needs_grad(*xs: Any) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad for x in xs)
+
+
+class _ApplyUnitary(torch.autograd.Function):
+    """y = U_qubits x as one device pass, differentiable like the reference's einsum kernels (statevector.py:28-129):
+    backward is grad_x = U^H grad_y (one more pass) and, when the gate itself requires grad, grad_U[a, b] =
+    sum_rest grad_y[a, rest] conj(x[b, rest]) from the device reduction tqb_grad_dense (k <= 2)."""
+
+    @staticmethod
+    def forward(ctx, state: torch.Tensor, gate: torch.Tensor, qubits: tuple, n: int):  # type: ignore[override]
+        t, how = _to_dev(state)
+        U = _to_np(gate).reshape(1 << len(qubits), 1 << len(qubits))
+        P.apply_gates(t, [classify_unitary(U, list(qubits), n)])
+        ctx.qubits, ctx.n, ctx.U = tuple(qubits), int(n), U
+        ctx.gate_meta = (gate.dtype, gate.device, gate.shape) if isinstance(gate, torch.Tensor) else None
+        ctx.state_meta = (state.dtype, state.device, state.shape)
+        ctx.need_gate = bool(isinstance(gate, torch.Tensor) and gate.requires_grad)
+        if ctx.need_gate:
+            ctx.save_for_backward(state)
+        out = _back(t, how)
+        return out.reshape(state.shape) if isinstance(out, torch.Tensor) else out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):  # type: ignore[override]
+        qubits, n, U = ctx.qubits, ctx.n, ctx.U
+        gy, _ = _to_dev(grad_out)
+        g_state = None
+        if ctx.needs_input_grad[0]:
+            gx = gy.clone()
+            P.apply_gates(gx, [classify_unitary(U.conj().T.copy(), list(qubits), n)])
+            dt, dv, shp = ctx.state_meta
+            g_state = gx.to(dv).to(dt).reshape(shp)
+        g_gate = None
+        if ctx.need_gate:
+            k = len(qubits)
+            if k > 2:
+                raise NotImplementedError("gradient with respect to a k > 2 gate matrix is not supported on the device path")
+            from .autograd import grad_dense
+            (x,) = ctx.saved_tensors
+            xd, _ = _to_dev(x)
+            d = 1 << k
+            out = torch.zeros(2 * d * d, dtype=torch.float64, device=gy.device)
+            bits = [n - 1 - int(q) for q in reversed(qubits)]   # matrix-index bit j (LSB first) -> index bit
+            for a in range(d):
+                for b in range(d):
+                    E = np.zeros((d, d), dtype=np.complex128)
+                    E[b, a] = 1.0
+                    grad_dense(xd, gy, bits, E, 1.0, out, 2 * (a * d + b))            # Re G[a, b]
+                    grad_dense(xd, gy, bits, -1j * E, 1.0, out, 2 * (a * d + b) + 1)   # Im G[a, b]
+            G = torch.view_as_complex(out.reshape(d, d, 2).contiguous())
+            dt, dv, shp = ctx.gate_meta
+            g_gate = G.to(dv).to(dt if dt.is_complex else torch.complex128).reshape(shp)
+        return g_state, g_gate, None, None
+
+
 def init_statevector(num_qubits: int, backend: Any | None = None, *, device: Any = None, dtype: torch.dtype = torch.complex128) -> torch.Tensor:
     """statevector.py:19-25.  Returns a CUDA tensor (the reference builds a Python list of 2^n complex)."""
     return P.new_state(max(int(num_qubits), 0), dtype=dtype, device=device or _device())
@@ -56,6 +112,8 @@ def init_statevector(num_qubits: int, backend: Any | None = None, *, device: Any
 
 def apply_1q_statevector(backend: Any, state: Any, gate2: Any, qubit: int, num_qubits: int) -> Any:
     """statevector.py:28-42."""
+    if _needs_grad(state, gate2):
+        return _ApplyUnitary.apply(state, gate2 if isinstance(gate2, torch.Tensor) else torch.as_tensor(_to_np(gate2)), (int(qubit),), int(num_qubits))
     t, how = _to_dev(state)
     P.apply_gates(t, [dense_gate(_to_np(gate2).reshape(2, 2), [int(qubit)], int(num_qubits))])
     return _back(t, how)
@@ -65,6 +123,8 @@ def apply_2q_statevector(backend: Any, state: Any, gate4: Any, q0: int, q1: int,
     """statevector.py:45-59 (returns the input unchanged when q0 == q1)."""
     if q0 == q1:
         return state
+    if _needs_grad(state, gate4):
+        return _ApplyUnitary.apply(state, gate4 if isinstance(gate4, torch.Tensor) else torch.as_tensor(_to_np(gate4)), (int(q0), int(q1)), int(num_qubits))
     t, how = _to_dev(state)
     P.apply_gates(t, [classify_unitary(_to_np(gate4).reshape(4, 4), [int(q0), int(q1)], int(num_qubits))])
     return _back(t, how)
@@ -77,6 +137,9 @@ def apply_kqubit_unitary(state: Any, unitary: Any, qubit_indices: Sequence[int],
         return state
     if k > 4:
         raise NotImplementedError("apply_kqubit_unitary: k > 4 dense blocks are not supported on the device path")
+    if _needs_grad(state, unitary):
+        return _ApplyUnitary.apply(state, unitary if isinstance(unitary, torch.Tensor) else torch.as_tensor(_to_np(unitary)),
+                                   tuple(int(q) for q in qubit_indices), int(num_qubits))
     t, how = _to_dev(state)
     P.apply_gates(t, [classify_unitary(_to_np(unitary), [int(q) for q in qubit_indices], int(num_qubits))])
     return _back(t, how)
