@@ -139,12 +139,17 @@ int tqb_run_passes2(void *state, int n, int64_t batch, int dtype, uint64_t globa
 /* Specialisation mode: 0 = off, 1 = asynchronous (default: new shapes compile on background threads while the
  * generic kernel runs them), 2 = synchronous (compile on first use; compile errors are returned).  256 + flags:
  * profiling switches of the specialised kernels (1 = skip gates, 2 = skip bulk loads, 4 = skip bulk stores; results
- * are WRONG with any flag set).  Returns the old mode.                                                    */
+ * are WRONG with any flag set).  512 + v: tile staging of the specialised kernels, v = 1 (default) one tensor copy
+ * per tile (cp.async.bulk.tensor through a CUtensorMap of the state, unpadded layouts), v = 0 one bulk copy per
+ * contiguous run.  Returns the old mode.                                                                   */
 int tqb_set_jit(int mode);
 /* Directory of the on-disk cubin cache (NULL or "" = none).                                              */
 int tqb_set_jit_cache(const char *dir);
 /* Block until every queued specialisation has been compiled (asynchronous mode).                          */
 int tqb_jit_wait(void);
+/* Stop the background compilation threads (drops queued shapes, waits for the compilations in flight).  Called at
+ * process exit; a host that unloads the library earlier calls it first.                                   */
+int tqb_jit_shutdown(void);
 /* out4 = { specialised launches, NVRTC compilations, disk-cache hits, shapes known }.                    */
 int tqb_jit_stats(int64_t *out4);
 /* Source of one pass's specialised kernel: the generated constants (+ the kernel template when with_template != 0)

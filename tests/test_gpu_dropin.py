@@ -65,9 +65,16 @@ def _build(tq, n, seed, depth=6):
     return c
 
 
+def _payload(r):
+    """The facade (devices/base.py:252-420 + Circuit.run) hands the driver's result dict back NESTED under
+    ``result_meta`` (its own top-level ``expectations`` / ``result`` stay empty for simulator tasks): unwrap it."""
+    r = r[0] if isinstance(r, list) else r
+    inner = r.get("result_meta")
+    return inner if isinstance(inner, dict) and "expectations" in inner else r
+
+
 def _run_exact(c):
-    r = c.compile().device(provider="simulator", device="statevector").run(shots=0)
-    return r[0] if isinstance(r, list) else r
+    return _payload(c.compile().device(provider="simulator", device="statevector").run(shots=0))
 
 
 @pytest.mark.parametrize("n,seed", [(3, 1), (8, 2), (13, 3), (16, 4)])
@@ -101,15 +108,12 @@ def test_circuit_run_counts_format_and_oracle(tq, installed):
     for q in range(n):
         c.measure_z(q)
     u = np.random.default_rng(11).random(shots)
-    r = c.device(provider="simulator", device="statevector").run(shots=shots, uniforms=u)
-    r = r[0] if isinstance(r, list) else r
+    r = _payload(c.device(provider="simulator", device="statevector").run(shots=shots, uniforms=u))
     assert r["error"] == ""
     counts = r["result"]
     assert sum(counts.values()) == shots and all(len(k) == n for k in counts)
     psi = np.asarray(c.state())
-    idx = O.sample_indices(psi, u)
-    vals, cnts = np.unique(idx, return_counts=True)
-    assert counts == {format(int(v), f"0{n}b"): int(k) for v, k in zip(vals, cnts)}
+    assert counts == O.counts_from_indices(O.sample_indices(O.probabilities(psi), u), n)
 
 
 def test_state_and_expectation_match_reference(tq):
@@ -191,8 +195,7 @@ def test_exact_run_is_lazy_and_simulates_once(tq):
         eng.run(c, shots=0)
         one_run = _lib.launch_count() - before
         before = _lib.launch_count()
-        r = c.device(provider="simulator", device="statevector").run(shots=0)
-        r = r[0] if isinstance(r, list) else r
+        r = _payload(c.device(provider="simulator", device="statevector").run(shots=0))
         through_driver = _lib.launch_count() - before
         assert r["error"] == ""
         assert through_driver == one_run, (through_driver, one_run)

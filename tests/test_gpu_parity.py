@@ -321,12 +321,15 @@ def test_specialised_kernels_match_oracle(cuda_device):
         for n, ops in cases:
             ref, _ = O.evolve_ops(n, ops)
             for td, tol, m, L in ((torch.complex128, TOL128, 11, 5), (torch.complex64, TOL64, 12, 6), (torch.complex64, TOL64, 11, 6)):
-                before = _lib.jit_stats()["spec_launches"]
-                eng = _engine(cuda_device, "b200", td, TileConfig(m=m, L=L, threads=128))
-                psi, _, _ = eng._evolve(FakeCircuit(n, ops), "state")
-                err = np.abs(psi.cpu().numpy() - ref).max()
-                assert err < tol, (n, ops[0], td, m, err)
-                assert _lib.jit_stats()["spec_launches"] > before, "no specialised kernel ran"
+                for tensor_tma in (1, 0):   # tiles staged by one tensor copy (cp.async.bulk.tensor) / one bulk copy per run
+                    lib.tqb_set_jit(512 + tensor_tma)
+                    before = _lib.jit_stats()["spec_launches"]
+                    eng = _engine(cuda_device, "b200", td, TileConfig(m=m, L=L, threads=128))
+                    psi, _, _ = eng._evolve(FakeCircuit(n, ops), "state")
+                    err = np.abs(psi.cpu().numpy() - ref).max()
+                    assert err < tol, (n, ops[0], td, m, tensor_tma, err)
+                    assert _lib.jit_stats()["spec_launches"] > before, "no specialised kernel ran"
+        lib.tqb_set_jit(512 + 1)
         # batched states: the batch index is more tile-index bits
         n, ops = 14, O.qaoa_ring_ops(14, 3, rng.uniform(-np.pi, np.pi, 6))
         ref, _ = O.evolve_ops(n, ops)
@@ -338,6 +341,7 @@ def test_specialised_kernels_match_oracle(cuda_device):
         assert _lib.jit_stats()["spec_launches"] - before == prog.n_passes
         assert np.abs(st.cpu().numpy() - ref[None, :]).max() < TOL128
     finally:
+        lib.tqb_set_jit(512 + 1)
         lib.tqb_set_jit(old)
 
 

@@ -66,6 +66,7 @@ SIGNATURES = {
     "tqb_set_jit": (_i, [_i]),
     "tqb_set_jit_cache": (_i, [C.c_char_p]),
     "tqb_jit_wait": (_i, []),
+    "tqb_jit_shutdown": (_i, []),
     "tqb_jit_stats": (_i, [C.POINTER(_i64)]),
     "tqb_spec_source": (_i64, [_vp, _vp, _i, _i, _vp, _i64]),
     "tqb_spec_compile": (_i, [_vp, _vp, _i]),
@@ -123,6 +124,10 @@ def load() -> C.CDLL:
     lib.tqb_set_jit_cache(os.environ.get("TQB_JIT_CACHE", str(JIT_CACHE)).encode())
     if os.environ.get("TQB_JIT"):
         lib.tqb_set_jit(int(os.environ["TQB_JIT"]))
+    if os.environ.get("TQB_TENSOR_TMA"):   # 0 = stage tiles with one bulk copy per run instead of one tensor copy per tile
+        lib.tqb_set_jit(512 + int(os.environ["TQB_TENSOR_TMA"]))
+    import atexit
+    atexit.register(lib.tqb_jit_shutdown)   # before interpreter teardown: no compilation thread outlives the process
     _lib = lib
     return lib
 

@@ -15,6 +15,8 @@
 // Modes (tqb_set_jit): 0 = off (generic kernels only), 1 = asynchronous (default: shapes compile on background
 // threads while the generic lean kernel runs them; tqb_jit_wait() drains the queue), 2 = synchronous (compile on first
 // use, errors are returned to the caller).
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <sys/stat.h>
@@ -460,6 +462,7 @@ static std::string spec_header(const SpecPlan &P) {
 // ------------------------------------------------------------------------------------------
 // NVRTC (loaded with dlopen: the library itself links only libcudart)
 // ------------------------------------------------------------------------------------------
+static void jit_shutdown_hook();
 struct Nvrtc {
   void *h = nullptr;
   int (*CreateProgram)(void **, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
@@ -490,6 +493,7 @@ static Nvrtc *nvrtc() {
       N.err = "libnvrtc.so.12 not found (set TQB_NVRTC)";
       return;
     }
+    std::atexit(jit_shutdown_hook);   // (after the dlopen: runs before NVRTC's own exit-time destructors)
 #define TQB_SYM(field, name)                                             \
   N.field = reinterpret_cast<decltype(N.field)>(dlsym(N.h, name));       \
   if (!N.field) N.err = std::string("nvrtc symbol missing: ") + name;
@@ -553,7 +557,74 @@ struct SpecParams {  // must match tqbs::SpecParams in tqb_spec.cuh
   int dbg;
   signed char hb[16];
   signed char ext[8];
+  int use_tensor;
+  unsigned seg_mask[5];
+  signed char seg_start[8];
 };
+
+static std::atomic<int> g_tensor_tma{1};   // tqb_set_jit(512 + v): tensor-map staging on (1, default) / off (0)
+
+// Describe the state as a rank-5 tensor whose dimensions are the maximal runs of tile / non-tile index bits (runs of tile
+// bits longer than 7 are split: a box dimension holds at most 256 elements, two per amplitude) and encode the CUtensorMap whose box is one
+// tile.  Returns false when the tile does not fit the scheme (more than 5 runs, batch not a power of two, padded layout).
+static bool make_tensor_map(void *state, int n, int64_t batch, int dtype, const tqb_pass &ps, CUtensorMap *tm, SpecParams &prm) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    else
+      cudaGetLastError();
+  });
+  if (!encode || batch < 1 || (batch & (batch - 1))) return false;
+  int lb = 0;
+  while ((1ll << lb) < batch) ++lb;
+  const int N = n + lb;   // index bits of the whole array
+  const int h = ps.m - ps.L;
+  uint64_t tile_bits = (1ull << ps.L) - 1ull;
+  for (int j = 0; j < h; ++j) tile_bits |= 1ull << ps.hb[j];
+  struct Seg { int start, len; bool tile; };
+  Seg segs[8];
+  int ns = 0;
+  for (int b = 0; b < N;) {
+    const bool t = (tile_bits >> b) & 1ull;
+    int e = b;
+    while (e < N && (((tile_bits >> e) & 1ull) != 0) == t && (!t || e - b < 7) && (t || e - b < 31)) ++e;
+    if (ns >= 5) return false;
+    segs[ns++] = {b, e - b, t};
+    b = e;
+  }
+  if (!segs[0].tile) return false;
+  const int es = dtype == TQB_C128 ? 16 : 8;
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t box[5], estr[5];
+  for (int k = 0; k < 5; ++k) {
+    estr[k] = 1;
+    if (k < ns) {
+      gdim[k] = 1ull << segs[k].len;
+      box[k] = segs[k].tile ? (cuuint32_t)(1u << segs[k].len) : 1u;
+      if (k > 0) gstride[k - 1] = ((cuuint64_t)es) << segs[k].start;
+      prm.seg_start[k] = (signed char)segs[k].start;
+      prm.seg_mask[k] = segs[k].tile ? 0u : (unsigned)((1ull << segs[k].len) - 1ull);
+    } else {
+      gdim[k] = 1;
+      box[k] = 1;
+      gstride[k - 1] = ((cuuint64_t)es) << N;
+      prm.seg_start[k] = 0;
+      prm.seg_mask[k] = 0;
+    }
+  }
+  // dimension 0 in units of the amplitude's real components (no 16-byte element type exists)
+  gdim[0] *= 2;
+  box[0] *= 2;
+  if (box[0] > 256) return false;
+  const CUresult r = encode(tm, dtype == TQB_C128 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, state, gdim,
+                            gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 
 struct SpecKernel {
   enum State { PENDING, READY, FAILED };
@@ -572,15 +643,17 @@ struct SpecKernel {
   int64_t uses = 0;
 };
 
-static std::mutex g_jit_mu;
-static std::condition_variable g_jit_cv;
-static std::unordered_map<std::string, std::shared_ptr<SpecKernel>> g_cache;   // key: shape_key() of the parsed pass
-static std::deque<std::shared_ptr<SpecKernel>> g_queue;
-static std::vector<std::thread> g_workers;
+// The synchronisation objects, the cache and the queue are never destroyed: worker threads are detached and may be
+// blocked on the condition variable when the process exits (destroying a condition variable with waiters hangs).
+static std::mutex &g_jit_mu = *new std::mutex;
+static std::condition_variable &g_jit_cv = *new std::condition_variable;
+static std::unordered_map<std::string, std::shared_ptr<SpecKernel>> &g_cache = *new std::unordered_map<std::string, std::shared_ptr<SpecKernel>>;   // key: shape_key() of the parsed pass
+static std::deque<std::shared_ptr<SpecKernel>> &g_queue = *new std::deque<std::shared_ptr<SpecKernel>>;
+static std::vector<std::thread> &g_workers = *new std::vector<std::thread>;
 static int g_pending = 0;
 static std::atomic<int> g_jit_mode{1};
 static std::atomic<int> g_jit_dbg{0};
-static std::string g_cache_dir;
+static std::string &g_cache_dir = *new std::string;
 static std::atomic<int64_t> g_spec_launches{0}, g_spec_compiles{0}, g_spec_disk_hits{0};
 
 static uint64_t fnv1a(const std::string &s, uint64_t h = 1469598103934665603ull) {
@@ -646,23 +719,42 @@ static void build_kernel(SpecKernel &k) {
   }
 }
 
+static bool g_stop = false;      // set at shutdown: workers take no more jobs
+static int g_building = 0;       // compilations in flight
+
 static void worker_main() {
   for (;;) {
     std::shared_ptr<SpecKernel> k;
     {
       std::unique_lock<std::mutex> lk(g_jit_mu);
-      g_jit_cv.wait(lk, [] { return !g_queue.empty(); });
+      g_jit_cv.wait(lk, [] { return g_stop || !g_queue.empty(); });
+      if (g_stop) return;
       k = g_queue.front();
       g_queue.pop_front();
+      ++g_building;
     }
     build_kernel(*k);
     {
       std::lock_guard<std::mutex> lk(g_jit_mu);
       --g_pending;
+      --g_building;
     }
     g_jit_cv.notify_all();
   }
 }
+
+// Process exit must not pull NVRTC's own static state from under a compilation in flight: stop taking jobs, drop the
+// queue and wait (bounded) for the running ones.  Registered with atexit once NVRTC is loaded; also exported.
+static void jit_shutdown() {
+  std::unique_lock<std::mutex> lk(g_jit_mu);
+  g_stop = true;
+  g_pending -= (int)g_queue.size();
+  g_queue.clear();
+  g_jit_cv.notify_all();
+  g_jit_cv.wait_for(lk, std::chrono::seconds(60), [] { return g_building == 0; });
+}
+
+static void jit_shutdown_hook() { jit_shutdown(); }
 
 // Try to run pass `ps` with its specialised kernel.  *used = false: the caller runs the generic kernel.
 int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t global_base, const tqb_pass &ps,
@@ -686,7 +778,7 @@ int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t globa
       k->plan = parsed;
       g_cache[key] = k;
       fresh = true;
-      if (mode == 1) {
+      if (mode == 1 && !g_stop) {
         if (g_workers.empty()) {
           unsigned nt = std::thread::hardware_concurrency();
           nt = nt < 2 ? 1 : (nt > 8 ? 8 : nt / 2 + 1);
@@ -767,7 +859,11 @@ int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t globa
   const unsigned long long total = (unsigned long long)batch << (n - ps.m);
   unsigned long long grid = (unsigned long long)ws.sm_count * k->resident;
   if (grid > total) grid = total;
-  void *args[] = {&prm};
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof tmap);
+  prm.use_tensor = 0;
+  if (plan.padL == 0 && g_tensor_tma.load() && !(prm.dbg & 6) && make_tensor_map(state, n, batch, dtype, ps, &tmap, prm)) prm.use_tensor = 1;
+  void *args[] = {&prm, &tmap};
   cudaError_t e = cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(160), args, smem, st);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail(std::string("tqb_spec_pass launch failed: ") + cudaGetErrorString(e));
@@ -783,6 +879,10 @@ using namespace tqb;
 extern "C" {
 
 int tqb_set_jit(int mode) {
+  if (mode >= 512) {   // 512 + v: tensor-map staging (cp.async.bulk.tensor) on / off
+    g_tensor_tma.store(mode - 512 ? 1 : 0);
+    return g_jit_mode.load();
+  }
   if (mode >= 256) {   // 256 + flags: profiling switches of the specialised kernels (results are WRONG with any flag set)
     g_jit_dbg.store(mode - 256);
     return g_jit_mode.load();
@@ -797,9 +897,14 @@ int tqb_set_jit_cache(const char *dir) {
   return 0;
 }
 
+int tqb_jit_shutdown(void) {
+  jit_shutdown();
+  return 0;
+}
+
 int tqb_jit_wait(void) {
   std::unique_lock<std::mutex> lk(g_jit_mu);
-  g_jit_cv.wait(lk, [] { return g_pending == 0; });
+  g_jit_cv.wait(lk, [] { return g_pending <= 0 || g_stop; });
   return 0;
 }
 

@@ -438,7 +438,32 @@ struct SpecParams {
   int dbg;                   // profiling only: 1 = skip the gates, 2 = skip bulk loads, 4 = skip bulk stores
   signed char hb[16];        // index bit of high tile bit j (ascending)
   signed char ext[8];        // index bit of outside-the-tile slot j
+  // tensor-map staging (use_tensor != 0): the state is a rank-5 tensor whose dimensions are the maximal runs of
+  // tile / non-tile index bits; coordinate k of a tile = (element index >> seg_start[k]) & seg_mask[k] (0 for tile runs)
+  int use_tensor;
+  unsigned seg_mask[5];
+  signed char seg_start[8];
 };
+
+struct alignas(64) TensorMap {   // CUtensorMap (cuda.h): 128 opaque bytes written by cuTensorMapEncodeTiled on the host
+  unsigned long long opaque[16];
+};
+
+// One instruction moves a whole tile: the TMA engine walks the 2^H runs itself (SASS UTMALDG / UTMASTG) instead of the
+// producer warp issuing one bulk copy per run (UBLKCP, ~70 cycles of issue each: 128 per tile).
+__device__ __forceinline__ void tensor_load(void *dst_smem, const TensorMap *tm, const int (&c)[5], u64 *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<u64>(tm)), "r"(smem_u32(bar)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+      : "memory");
+}
+__device__ __forceinline__ void tensor_store(const TensorMap *tm, const int (&c)[5], const void *src_smem) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<u64>(tm)),
+               "r"(smem_u32(src_smem)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+               : "memory");
+}
 
 constexpr int NB = 2;
 constexpr u32 NRUNS = 1u << H;
@@ -451,7 +476,8 @@ constexpr u32 SMEM_MATS = SMEM_BARS + 64;
 constexpr u32 SMEM_ROFF = SMEM_MATS + (u32)(((MAT_COUNT + 1) & ~1) * ES);
 constexpr u32 SMEM_TOTAL = SMEM_ROFF + 8u * NRUNS;
 
-extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const SpecParams prm) {
+extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const SpecParams prm,
+                                                                        const __grid_constant__ TensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   u64 *full = reinterpret_cast<u64 *>(smem_raw + SMEM_BARS);
   u64 *done = full + 4;
@@ -512,6 +538,39 @@ extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const Spe
       __syncwarp();
       for (u32 j = lane; j < NRUNS; j += 32) bulk_load(dst + j * RUN_STRIDE, src + roff[j], RUN_BYTES, &full[b]);
     };
+    if (prm.use_tensor) {
+      // tensor-map staging: one elected lane, one instruction per tile and direction
+      if (lane == 0) {
+        auto coords = [&](u64 it, int (&c)[5]) {
+          const u64 tt = first + it * stride;
+          const u64 idx = ((tt >> tbits) << prm.n) + tile_index(tt);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) c[k] = (int)((idx >> prm.seg_start[k]) & (u64)prm.seg_mask[k]);
+        };
+        int c[5];
+        for (u64 it = 0; it < (u64)NB && it < count; ++it) {
+          const int b = (int)(it % NB);
+          coords(it, c);
+          mbar_expect_tx(&full[b], TILE_BYTES);
+          tensor_load(smem_raw + b * TILE_STRIDE, &tmap, c, &full[b]);
+        }
+        for (u64 it = 0; it < count; ++it) {
+          const int b = (int)(it % NB);
+          mbar_wait(&done[b], (u32)((it / NB) & 1));
+          coords(it, c);
+          tensor_store(&tmap, c, smem_raw + b * TILE_STRIDE);
+          bulk_commit();
+          if (it + NB < count) {
+            bulk_wait_read<0>();   // the store has read the buffer: refill it
+            coords(it + NB, c);
+            mbar_expect_tx(&full[b], TILE_BYTES);
+            tensor_load(smem_raw + b * TILE_STRIDE, &tmap, c, &full[b]);
+          }
+        }
+        bulk_wait_all0();
+      }
+      return;
+    }
     // every buffer cycles compute -> store drain -> refill; the refill of a run is issued right behind its own store
     // (a lane waits only until ITS earlier store has been read out of shared memory)
     for (u64 it = 0; it < (u64)NB && it < count; ++it) issue_load(it);

@@ -34,6 +34,7 @@ class TileConfig:
     ctas_per_sm: int = 0
     max_gates: int = 384
     rot_layers: int = 4   # longest rotation-form chain (4 needs the 128-thread kernel variant for complex128)
+    max_work: int = 0     # cap on the non-diagonal gates (1-qubit layers after fusion) of one pass; 0 = no cap
 
     @property
     def h(self) -> int:
@@ -98,6 +99,7 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
     is_diag = [g.kind == DIAG for g in gates]
 
     max_gates = tile.max_gates
+    max_work = tile.max_work or (1 << 30)
 
     def select(start: int, window: int) -> Tuple[List[int], int, int, int]:
         """window < 0: budget mode (i); else only gates whose needs lie inside ``window`` run.  Returns
@@ -143,6 +145,8 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
                     blocked_nd |= mk
             if blocked_nd == all_bits or len(chosen) >= max_gates or seen >= 4096:
                 break
+            if nd >= max_work:   # the pass is full: everything else waits (diagonal gates ride with their consumers)
+                break
         return chosen, H, nH, nd
 
     while remaining:
@@ -180,7 +184,7 @@ def _prepare(gates: Sequence[LGate], n: int, tile: TileConfig, chain: Optional[b
     """Effective tile, the pass schedule (diagonals sunk to their consumers when chains are grouped) and the chain switch."""
     m_eff = min(tile.m, n)
     tile = TileConfig(m=m_eff, L=min(tile.L, m_eff), threads=tile.threads, ctas_per_sm=tile.ctas_per_sm,
-                      max_gates=tile.max_gates, rot_layers=tile.rot_layers)
+                      max_gates=tile.max_gates, rot_layers=tile.rot_layers, max_work=tile.max_work)
     sched = schedule(gates, n, tile)
     if chain is None:
         chain = bool(getattr(gates, "chain_after_schedule", False))
