@@ -189,6 +189,24 @@ int tqb_expect_pauli_sum(const void *state, int n, int64_t batch, int dtype, uin
                          const uint64_t *group_x, const int32_t *group_ptr, int n_groups,
                          const uint64_t *term_z, const double *term_coef, double *out_dev,
                          void *stream);
+/* The same expectation value, tile-staged: the xmask groups are sorted into tile LAYOUTS (tile bits = the L lowest index
+ * bits + hb[], as in tqb_pass; every xmask of a layout's groups lies inside its tile bits) and each layout is ONE read of
+ * the state: a CTA stages a tile in shared memory and evaluates all the layout's groups from there.  Per group g the
+ * xmask is given in TILE-LOCAL bit positions (group_xl), per term t the z mask is split into its tile-local part
+ * (term_zl, tile-local positions) and the rest (term_zout, index bits; shard bits >= n included).  group_ptr indexes the
+ * term arrays as in tqb_expect_pauli_sum; a layout covers groups [group_begin, group_begin + n_groups) and n_terms terms.
+ * flags bit 0: every group is a Hermitian operator (real Pauli coefficients): the pairs (j, j ^ x) are visited once and
+ * the result is real; bit 1: every coefficient (with i^#Y folded in) is real.  layouts: HOST array; everything else on the device.  out_dev[b] = (re, im), overwritten.     */
+typedef struct tqb_pauli_layout {
+  int32_t m, L;
+  int32_t group_begin, n_groups, n_terms;
+  int8_t hb[TQB_MAX_TILE_HIGH];
+} tqb_pauli_layout; /* 36 bytes */
+int tqb_expect_pauli_tiled(const void *state, int n, int64_t batch, int dtype, uint64_t global_base,
+                           const tqb_pauli_layout *layouts_host, int n_layouts, const uint32_t *group_xl_dev,
+                           const int32_t *group_ptr_dev, const uint32_t *term_zl_dev,
+                           const uint64_t *term_zout_dev, const double *term_coef_dev, int flags,
+                           double *out_dev, void *stream);
 /* replaces apply_op (applications/chem/chem_libs/hamiltonians_chem_library/
  * hamiltonian_builders.py:283-318) without densifying H: out = H psi, same term layout.    */
 int tqb_apply_pauli_sum(const void *state, void *out, int n, int64_t batch, int dtype,

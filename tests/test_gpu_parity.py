@@ -239,6 +239,38 @@ def test_pauli_sum(cuda_device, golden):
     assert abs(eng.expval(FakeCircuit(n, [], inputs=st), lst) - O.expect_pauli_sum(st, terms, w)) < TOL128
 
 
+def test_pauli_sum_tiled_kernel(cuda_device):
+    """Tile-staged Pauli sums (expect_pauli_tiled_kernel) against the oracle and against the gather kernel: several tile
+    layouts (streaming 64 KiB tiles at n = 16 / 17), Hermitian and non-Hermitian (complex-weight) sums, X/Y strings spread
+    over the register, batched states, complex64."""
+    import torch
+    from tyxonq_b200 import PauliSum
+    rng = np.random.default_rng(23)
+    for n, dt, tol, herm in ((16, torch.complex128, TOL128, True), (16, torch.complex128, TOL128, False),
+                             (17, torch.complex64, 2e-5, True), (9, torch.complex128, TOL128, False)):
+        terms = []
+        for _ in range(60):
+            t = [0] * n
+            for q in rng.choice(n, size=int(rng.integers(1, 7)), replace=False):
+                t[int(q)] = int(rng.integers(1, 4))
+            terms.append(t)
+        w = rng.normal(size=60) + (0 if herm else 1j * rng.normal(size=60))
+        ham = PauliSum.from_codes(terms, w.tolist())
+        assert ham.hermitian == herm
+        B = 3
+        st = rng.normal(size=(B, 1 << n)) + 1j * rng.normal(size=(B, 1 << n))
+        st /= np.linalg.norm(st, axis=1, keepdims=True)
+        d = torch.from_numpy(st).to(cuda_device).to(dt)
+        plan = ham._tiled_plan(n, d.element_size(), d.device)
+        assert plan is not None and (n < 14 or plan[1] >= 2), "expected several tile layouts"
+        got = ham.expectation(d, tiled=True).cpu().numpy()
+        old = ham.expectation(d, tiled=False).cpu().numpy()
+        for b in range(B):
+            ref = O.expect_pauli_sum(st[b], terms, w.tolist()) if herm else complex(np.vdot(st[b], O.apply_pauli_sum(st[b], terms, w.tolist())))
+            assert abs(got[b] - ref) < tol, (n, dt, herm, b, got[b], ref)
+            assert abs(old[b] - ref) < tol
+
+
 def test_tfim_vqe_energy(cuda_device):
     """examples/vqetfim_benchmark.py exact_energy on the device vs the oracle restatement."""
     from tyxonq_b200.vqe import TFIMVqe

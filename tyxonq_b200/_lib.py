@@ -75,6 +75,7 @@ SIGNATURES = {
     "tqb_expect_z_bits": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_expect_zmasks": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp]),
     "tqb_expect_pauli_sum": (_i, [_vp, _i, _i64, _i, _u64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "tqb_expect_pauli_tiled": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "tqb_apply_pauli_sum": (_i, [_vp, _vp, _i, _i64, _i, _u64, _vp, _vp, _i, _vp, _vp, _vp]),
     "tqb_inner": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp]),
     "tqb_grad_pair": (_i, [_vp, _vp, _i, _i, _vp, _d, _vp, _i, _vp]),
@@ -93,6 +94,15 @@ SIGNATURES = {
     "tqb_sample_shard": (_i, [_vp, _i, _i, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "tqb_copy": (_i, [_vp, _vp, _i64, _i, _vp]),
 }
+
+
+class PauliLayout(C.Structure):
+    """tqb_pauli_layout (include/tyxonq_b200.h)."""
+    _fields_ = [("m", C.c_int32), ("L", C.c_int32), ("group_begin", C.c_int32), ("n_groups", C.c_int32), ("n_terms", C.c_int32),
+                ("hb", C.c_int8 * MAX_TILE_HIGH)]
+
+
+assert C.sizeof(PauliLayout) == 36
 
 
 class TqbError(RuntimeError):

@@ -294,6 +294,96 @@ __global__ void __launch_bounds__(RT) apply_pauli_kernel(const cplx<T> *__restri
   }
 }
 
+// ---- tile-staged Pauli sums ---------------------------------------------------------------------------------
+// The kernel above gathers psi_{j ^ x_g} from global memory once per group and re-reads every term's mask and
+// coefficient per amplitude.  Here a CTA stages a tile of 2^m amplitudes (the L lowest index bits + the high bits hb[],
+// like a gate pass) in shared memory ONCE and evaluates every group whose xmask lies inside the tile bits from there:
+//   * partner amplitudes come from shared memory (xmask in tile-local coordinates, xl);
+//   * a term's z mask is split into its tile-local part zl (tile-local coordinates) and the part outside the tile,
+//     whose parity is constant for the tile: it is folded into the coefficient once per tile (sc[]);
+//   * HERM (every group is a Hermitian operator, i.e. real Pauli coefficients): the pair (j, j ^ x) contributes
+//     2 Re(conj(psi_{j^x}) phase(j) psi_j), so only the half of the tile with the lowest xmask bit clear is visited.
+// The host groups the xmasks into tile layouts (pauli.py plan_layouts): one read of the state per layout.
+struct PauliTile {
+  int n, m, L, h;
+  int g0, ng;          // groups [g0, g0 + ng) of gxl / gptr
+  int layout, n_layouts;
+  int8_t hb[16];
+};
+
+template <typename T, bool HERM, bool REALC>   // REALC: every coefficient (i^#Y folded in) is real
+__global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *__restrict__ state, PauliTile pt, uint64_t global_base,
+                                                                const uint32_t *__restrict__ gxl, const int *__restrict__ gptr,
+                                                                const uint32_t *__restrict__ zl, const uint64_t *__restrict__ zout,
+                                                                const double *__restrict__ coef, double *partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[(RT / 32) * 2];
+  const int m = pt.m, L = pt.L, h = pt.h;
+  const uint32_t nel = 1u << m;
+  cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
+  uint64_t *roff = reinterpret_cast<uint64_t *>(tile + nel);
+  const int t0 = gptr[pt.g0], nt = gptr[pt.g0 + pt.ng] - t0;
+  double2 *sc = reinterpret_cast<double2 *>(roff + (1u << h));   // signed coefficients of this tile
+  uint32_t *szl = reinterpret_cast<uint32_t *>(sc + nt);
+  const int tid = threadIdx.x;
+  for (uint32_t j = tid; j < (1u << h); j += RT) {
+    uint64_t o = 0;
+    for (int i = 0; i < h; ++i) o |= (uint64_t)((j >> i) & 1u) << pt.hb[i];
+    roff[j] = o;
+  }
+  for (int t = tid; t < nt; t += RT) szl[t] = zl[t0 + t];
+  const cplx<T> *sb = state + ((size_t)blockIdx.y << pt.n);
+  const uint64_t ntiles = 1ull << (pt.n - m);
+  double acc[2] = {0.0, 0.0};
+  constexpr int V = 16 / (int)sizeof(cplx<T>);
+  for (uint64_t tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
+    uint64_t base = tt << L;
+    for (int j = 0; j < h; ++j) {
+      const uint32_t p = (uint32_t)pt.hb[j];
+      base = ((base >> p) << (p + 1u)) | (base & ((1ull << p) - 1ull));
+    }
+    __syncthreads();   // the previous tile is done with tile[] / sc[]
+    for (uint32_t i = tid; i < nel / V; i += RT) {
+      const uint32_t e = i * V;
+      const uint64_t idx = base | roff[e >> L] | (uint64_t)(e & ((1u << L) - 1u));
+      *reinterpret_cast<cvec<T, V> *>(tile + e) = *reinterpret_cast<const cvec<T, V> *>(sb + idx);
+    }
+    const uint64_t gidx = global_base | base;
+    for (int t = tid; t < nt; t += RT) {
+      const bool odd = __popcll(gidx & zout[t0 + t]) & 1;
+      const double cr = coef[2 * (t0 + t)], ci = coef[2 * (t0 + t) + 1];
+      sc[t] = odd ? make_double2(-cr, -ci) : make_double2(cr, ci);
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < nel; e += RT) {
+      const cplx<T> a = tile[e];
+      const double ar = a.x, ai = a.y;
+      double hr = 0.0, hi = 0.0;   // sum_g conj(psi_{e^x}) phase_g(e)   (weight 2 for the pairs of a Hermitian group)
+      for (int g = 0; g < pt.ng; ++g) {
+        const uint32_t xl = gxl[pt.g0 + g];
+        const bool paired = HERM && xl != 0u;
+        if (paired && (e & (xl & (0u - xl)))) continue;
+        const int a0 = gptr[pt.g0 + g] - t0, a1 = gptr[pt.g0 + g + 1] - t0;
+        double pr = 0.0, pi = 0.0;
+        for (int t = a0; t < a1; ++t) {
+          const double2 c = sc[t];
+          const bool odd = __popc(e & szl[t]) & 1;
+          pr += odd ? -c.x : c.x;
+          if (!REALC) pi += odd ? -c.y : c.y;
+        }
+        const cplx<T> b = tile[e ^ xl];
+        const double w = paired ? 2.0 : 1.0;
+        const double br = w * (double)b.x, bi = -w * (double)b.y;
+        hr += br * pr - bi * pi;
+        hi += br * pi + bi * pr;
+      }
+      acc[0] += hr * ar - hi * ai;
+      if (!HERM) acc[1] += hr * ai + hi * ar;
+    }
+  }
+  block_reduce<2>(acc, red, partial + (((size_t)blockIdx.y * pt.n_layouts + pt.layout) * gridDim.x + blockIdx.x) * 2);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(RT) inner_kernel(const cplx<T> *__restrict__ a, const cplx<T> *__restrict__ b, Seg sg,
                                                    double *partial) {
@@ -596,9 +686,17 @@ __global__ void __launch_bounds__(128) sample_kernel(const E *__restrict__ state
     const double pre = p[lo];
     double run = 0.0;
     size_t cnt = 0;
+    // The test is fl(cdf / total) <= u with the division correctly rounded.  A cdf safely below / above u * total
+    // decides it without dividing (relative margin 2^-49 >> the 2^-53 roundings of the product and the quotient);
+    // only values inside the margin take the exact division -- same indices, bit for bit, without ~4096 DDIVs a shot.
+    const double ut = __dmul_rn(u, total);
+    const double safe_lo = __dmul_rn(ut, 1.0 - 0x1p-49), safe_hi = __dmul_rn(ut, 1.0 + 0x1p-49);
     for (; cnt < clen; ++cnt) {
       run = __dadd_rn(run, prob_of(sc[cnt]));
-      if (!(__ddiv_rn(__dadd_rn(pre, run), total) <= u)) break;
+      const double v = __dadd_rn(pre, run);
+      if (v < safe_lo) continue;
+      if (v > safe_hi) break;
+      if (!(__ddiv_rn(v, total) <= u)) break;
     }
     idx = (lo << chunk_bits) + (long long)cnt;
   }
@@ -757,6 +855,67 @@ int tqb_expect_pauli_sum(const void *state, int n, int64_t batch, int dtype, uin
     return -1;
   TQB_CHECK_LAUNCH("expect_pauli_kernel");
   finish_kernel<<<(unsigned)batch, 32, 0, st>>>(partial, nbx, 2, 2, out_dev, 2);
+  TQB_CHECK_LAUNCH("finish_kernel");
+  return 0;
+}
+
+int tqb_expect_pauli_tiled(const void *state, int n, int64_t batch, int dtype, uint64_t global_base,
+                           const tqb_pauli_layout *layouts_host, int n_layouts, const uint32_t *group_xl_dev,
+                           const int32_t *group_ptr_dev, const uint32_t *term_zl_dev, const uint64_t *term_zout_dev,
+                           const double *term_coef_dev, int flags, double *out_dev, void *stream) {
+  TQB_REQUIRE(state && out_dev && layouts_host && n_layouts >= 1 && n_layouts <= 64 && group_xl_dev && group_ptr_dev && term_zl_dev &&
+                  term_zout_dev && term_coef_dev && n >= 1 && n < 48 && batch >= 1 && batch <= 65535,
+              "tqb_expect_pauli_tiled: bad arguments");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  const int es = dtype == TQB_C128 ? 16 : 8;
+  if (dtype != TQB_C128 && dtype != TQB_C64) return fail("bad dtype");
+  cudaStream_t st = as_stream(stream);
+  // CTAs per batch member: about 4 per SM overall, a power of two, at most one per tile
+  int nbx = 1;
+  double *partial = (double *)ws->ptr;
+  for (int li = 0; li < n_layouts; ++li) {
+    const tqb_pauli_layout &lay = layouts_host[li];
+    TQB_REQUIRE(lay.m >= 1 && lay.m <= n && lay.m <= 14 && lay.L >= 0 && lay.L <= lay.m && lay.m - lay.L <= 16 && lay.n_groups >= 1 &&
+                    lay.n_terms >= 1, "tqb_expect_pauli_tiled: bad layout");
+    if (li == 0) {
+      const long long tiles = 1ll << (n - lay.m);
+      long long want = ((long long)ws->sm_count * 4 + batch - 1) / batch;
+      while (nbx < want && nbx < tiles) nbx <<= 1;
+      TQB_REQUIRE((size_t)batch * n_layouts * nbx * 2 * sizeof(double) <= ws->bytes, "tqb_expect_pauli_tiled: workspace too small");
+    }
+    PauliTile pt;
+    pt.n = n; pt.m = lay.m; pt.L = lay.L; pt.h = lay.m - lay.L; pt.g0 = lay.group_begin; pt.ng = lay.n_groups;
+    pt.layout = li; pt.n_layouts = n_layouts;
+    int prev = lay.L - 1;
+    for (int i = 0; i < 16; ++i) {
+      pt.hb[i] = i < pt.h ? lay.hb[i] : 0;
+      if (i < pt.h) {
+        TQB_REQUIRE(lay.hb[i] > prev && lay.hb[i] < n, "tqb_expect_pauli_tiled: hb must be ascending, >= L and < n");
+        prev = lay.hb[i];
+      }
+    }
+    const size_t smem = ((size_t)es << lay.m) + ((size_t)8 << pt.h) + (size_t)lay.n_terms * 20 + 16;
+    TQB_REQUIRE(smem <= (size_t)ws->max_smem_optin, "tqb_expect_pauli_tiled: tile + terms exceed shared memory");
+#define TQB_PT(T, HERM, REALC, PTR)                                                                                              \
+  do {                                                                                                                            \
+    auto kern = expect_pauli_tiled_kernel<T, HERM, REALC>;                                                                        \
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->max_smem_optin));                  \
+    kern<<<dim3((unsigned)nbx, (unsigned)batch), RT, smem, st>>>(PTR(state), pt, global_base, group_xl_dev, group_ptr_dev,       \
+                                                                   term_zl_dev, term_zout_dev, term_coef_dev, partial);         \
+  } while (0)
+    const int f = flags & 3;
+    if (dtype == TQB_C128) {
+      if (f == 3) TQB_PT(double, true, true, CD); else if (f == 1) TQB_PT(double, true, false, CD);
+      else if (f == 2) TQB_PT(double, false, true, CD); else TQB_PT(double, false, false, CD);
+    } else {
+      if (f == 3) TQB_PT(float, true, true, CF); else if (f == 1) TQB_PT(float, true, false, CF);
+      else if (f == 2) TQB_PT(float, false, true, CF); else TQB_PT(float, false, false, CF);
+    }
+#undef TQB_PT
+    TQB_CHECK_LAUNCH("expect_pauli_tiled_kernel");
+  }
+  finish_kernel<<<(unsigned)batch, 32, 0, st>>>(partial, nbx * n_layouts, 2, 2, out_dev, 2);
   TQB_CHECK_LAUNCH("finish_kernel");
   return 0;
 }

@@ -187,6 +187,21 @@ class ShotEnergy:
         self.tile = tile
         self.n_params = 1 + max([a.index for op in self.template for a in op if isinstance(a, Param)], default=-1)
         self.passes = 0
+        # the reference's rule (hea_device_runtime.py:180-262) shifts the PARAMETER by +-pi/2: exact only when every
+        # parameter drives exactly one rotation gate exp(-i theta/2 P) with unit scale -- anything else is refused
+        # instead of returning a silently wrong gradient (AdjointEnergy / ShardedStatevectorEngine.energy_and_grad
+        # differentiate per gate occurrence and take such templates)
+        seen: dict = {}
+        for op in self.template:
+            for a in op:
+                if isinstance(a, Param):
+                    if op[0] not in ("rx", "ry", "rz", "rxx", "ryy", "rzz"):
+                        raise NotImplementedError(f"parameter shift: no two-term rule for parametrised op {op[0]!r}")
+                    if a.scale != 1.0:
+                        raise NotImplementedError("parameter shift on the parameter needs Param.scale == 1 (scaled angles: use AdjointEnergy)")
+                    if a.index in seen:
+                        raise NotImplementedError("parameter shift on the parameter needs every parameter in exactly one gate (shared parameters: use AdjointEnergy)")
+                    seen[a.index] = True
 
     def states(self, params: np.ndarray) -> torch.Tensor:
         params = np.asarray(params, dtype=np.float64).reshape(-1, max(self.n_params, 1))

@@ -68,7 +68,12 @@ class ShardedStatevectorEngine:
             if g is not None:
                 gates.append(g)
         from .fuse import fuse
-        st = ShardedState(n, self.dtype, self.device, self.group, backend=self.local_backend)
+        # one shard + one exchange buffer per engine, reused by every call (a fresh pair per call would hold four
+        # shard-sized buffers from the second call on: half the largest state the devices can run)
+        st = self.last_state
+        if st is None or st.n != n:
+            self.last_state = st = None   # release the old buffers BEFORE allocating the new ones
+            st = ShardedState(n, self.dtype, self.device, self.group, backend=self.local_backend)
         plan = plan_sharded(fuse(gates), n, st.g)
         st.init_zero()
         st.run(plan, cache=False)
