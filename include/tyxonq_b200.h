@@ -283,6 +283,16 @@ int tqb_cdf_chunks(const void *state, int n, int64_t batch, int dtype, double *c
 int tqb_sample(const void *state, int n, int64_t batch, int dtype, const double *chunk_prefix_dev,
                const double *uniforms_dev, int64_t shots, int64_t *idx_dev, void *stream);
 
+/* The same two calls with a table of in-chunk partial sums: sub_prefix_dev (batch * n_chunks * 32 doubles, NULL = none;
+ * used when n >= 12) receives every chunk's sequential running sum after each 128 amplitudes -- the values the in-chunk
+ * scan passes through anyway -- and tqb_sample2 enters a chunk at the 128-amplitude block that holds the sample, so a
+ * shot reads at most 128 amplitudes instead of up to 4096.  Same CDF, same indices, bit for bit.                    */
+int tqb_cdf_chunks2(const void *state, int n, int64_t batch, int dtype, double *chunk_prefix_dev,
+                    double *sub_prefix_dev, void *stream);
+int tqb_sample2(const void *state, int n, int64_t batch, int dtype, const double *chunk_prefix_dev,
+                const double *sub_prefix_dev, const double *uniforms_dev, int64_t shots, int64_t *idx_dev,
+                void *stream);
+
 /* replaces term_expectation_from_counts / expval_pauli_sum (postprocessing/counts_expval.py:7-20,
  * 87-112) for the shots > 0 VQE path (applications/chem/runtimes/hea_device_runtime.py:120-262):
  * idx_dev holds `batch` rows of `shots` sampled indices (tqb_sample); row b belongs to measurement

@@ -55,20 +55,20 @@ def test_parameter_shift_from_shots_matches_oracle(cuda_device):
     ham = [(0.4, [("Z", 0), ("Z", 1)]), (-0.7, [("X", 1)]), (0.3, [("Y", 0), ("Y", 2)]), (0.2, []), (0.15, [("Z", 2), ("X", 3)]),
            (-0.25, [("Z", 0)]), (0.35, [("X", 1), ("X", 3)])]
     template = [("h", 0), ("ry", 0, Param(0)), ("rx", 1, Param(1)), ("cx", 0, 1), ("rz", 2, Param(2)), ("h", 2), ("rzz", 1, 2, Param(3)),
-                ("cx", 2, 3), ("ry", 3, Param(4, 2.0)), ("rxx", 0, 3, Param(0, -1.0))]
+                ("cx", 2, 3), ("ry", 3, Param(4)), ("rxx", 0, 3, Param(5))]
 
     def build(p):
         return [("h", 0), ("ry", 0, p[0]), ("rx", 1, p[1]), ("cx", 0, 1), ("rz", 2, p[2]), ("h", 2), ("rzz", 1, 2, p[3]),
-                ("cx", 2, 3), ("ry", 3, 2.0 * p[4]), ("rxx", 0, 3, -p[0])]
+                ("cx", 2, 3), ("ry", 3, p[4]), ("rxx", 0, 3, p[5])]
 
     gm = GroupedMeasurement.from_pauli_list(n, ham, device=cuda_device)
     identity, groups = MO.group_hamiltonian_pauli_terms(ham, n)
     assert gm.G == len(groups) and gm.identity == identity
     se = ShotEnergy(n, template, gm)
-    assert se.n_params == 5
-    params = np.array([0.3, -0.8, 1.1, 0.45, -0.6])
+    assert se.n_params == 6
+    params = np.array([0.3, -0.8, 1.1, 0.45, -0.6, 0.2])
     shots = 300
-    u = np.random.default_rng(11).random(((1 + 2 * 5) * gm.G, shots))
+    u = np.random.default_rng(11).random(((1 + 2 * 6) * gm.G, shots))
     e, g = se.energy_and_grad(params, u)
     e_ref, g_ref = MO.grouped_shot_energy_and_grad(n, build, params, identity, groups, u)
     assert abs(e - e_ref) < 1e-12 and np.abs(g - g_ref).max() < 1e-12
@@ -77,3 +77,8 @@ def test_parameter_shift_from_shots_matches_oracle(cuda_device):
     st = se.states(np.stack([params, params * 0.5])).cpu().numpy()
     for row, p in zip(st, (params, params * 0.5)):
         assert np.abs(row - O.evolve_ops(n, build(p), mode="run")[0]).max() < 1e-12
+    # scaled or shared parameters: energies and states work, the parameter-shift gradient is refused (its rule would be wrong)
+    tied = ShotEnergy(n, [("ry", 0, Param(0)), ("rxx", 0, 3, Param(0, -1.0)), ("ry", 3, Param(1, 2.0))], gm)
+    tied.energy(np.array([0.3, 0.1]), u[:gm.G])
+    with pytest.raises(NotImplementedError):
+        tied.energy_and_grad(np.array([0.3, 0.1]), u[:5 * gm.G])

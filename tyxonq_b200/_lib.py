@@ -86,6 +86,8 @@ SIGNATURES = {
     "tqb_probabilities": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_cdf_chunks": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_sample": (_i, [_vp, _i, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
+    "tqb_cdf_chunks2": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),
+    "tqb_sample2": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp]),
     "tqb_reduced_1q": (_i, [_vp, _i, _i64, _i, _i, _vp, _vp]),
     "tqb_dm_diag": (_i, [_vp, _i, _i64, _i, _vp, _vp]),
     "tqb_expval_from_samples": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),

@@ -311,11 +311,22 @@ struct PauliTile {
   int8_t hb[16];
 };
 
+// c with the sign (-1)^popc(v): the parity goes straight into the sign bit
+__device__ __forceinline__ float flip_sign(float c, uint32_t v) { return __int_as_float(__float_as_int(c) ^ (int)(__popc(v) << 31)); }
+__device__ __forceinline__ double flip_sign(double c, uint32_t v) {
+  return __hiloint2double(__double2hiint(c) ^ (int)(__popc(v) << 31), __double2loint(c));
+}
+
+template <typename R> struct Pair2 { R x, y; };
+
+// Arithmetic type R = the state's component type (complex64 states: float products and float partial sums over the few
+// iterations a thread spends on one group of one tile, added to the float64 accumulator once per group and tile).
 template <typename T, bool HERM, bool REALC>   // REALC: every coefficient (i^#Y folded in) is real
 __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *__restrict__ state, PauliTile pt, uint64_t global_base,
                                                                 const uint32_t *__restrict__ gxl, const int *__restrict__ gptr,
                                                                 const uint32_t *__restrict__ zl, const uint64_t *__restrict__ zout,
                                                                 const double *__restrict__ coef, double *partial) {
+  typedef T R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[(RT / 32) * 2];
   const int m = pt.m, L = pt.L, h = pt.h;
@@ -323,8 +334,10 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
   cplx<T> *tile = reinterpret_cast<cplx<T> *>(smem_raw);
   uint64_t *roff = reinterpret_cast<uint64_t *>(tile + nel);
   const int t0 = gptr[pt.g0], nt = gptr[pt.g0 + pt.ng] - t0;
-  double2 *sc = reinterpret_cast<double2 *>(roff + (1u << h));   // signed coefficients of this tile
+  Pair2<R> *sc = reinterpret_cast<Pair2<R> *>(roff + (((1u << h) + 1u) & ~1u));   // signed coefficients of this tile
   uint32_t *szl = reinterpret_cast<uint32_t *>(sc + nt);
+  uint32_t *sgx = szl + nt;               // per group: xmask (tile-local) ...
+  int *sgp = reinterpret_cast<int *>(sgx + pt.ng);   // ... and term range (relative), ng + 1 entries
   const int tid = threadIdx.x;
   for (uint32_t j = tid; j < (1u << h); j += RT) {
     uint64_t o = 0;
@@ -332,6 +345,8 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
     roff[j] = o;
   }
   for (int t = tid; t < nt; t += RT) szl[t] = zl[t0 + t];
+  for (int g = tid; g < pt.ng; g += RT) sgx[g] = gxl[pt.g0 + g];
+  for (int g = tid; g <= pt.ng; g += RT) sgp[g] = gptr[pt.g0 + g] - t0;
   const cplx<T> *sb = state + ((size_t)blockIdx.y << pt.n);
   const uint64_t ntiles = 1ull << (pt.n - m);
   double acc[2] = {0.0, 0.0};
@@ -352,33 +367,57 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
     for (int t = tid; t < nt; t += RT) {
       const bool odd = __popcll(gidx & zout[t0 + t]) & 1;
       const double cr = coef[2 * (t0 + t)], ci = coef[2 * (t0 + t) + 1];
-      sc[t] = odd ? make_double2(-cr, -ci) : make_double2(cr, ci);
+      sc[t] = odd ? Pair2<R>{(R)-cr, (R)-ci} : Pair2<R>{(R)cr, (R)ci};
     }
     __syncthreads();
-    for (uint32_t e = tid; e < nel; e += RT) {
-      const cplx<T> a = tile[e];
-      const double ar = a.x, ai = a.y;
-      double hr = 0.0, hi = 0.0;   // sum_g conj(psi_{e^x}) phase_g(e)   (weight 2 for the pairs of a Hermitian group)
-      for (int g = 0; g < pt.ng; ++g) {
-        const uint32_t xl = gxl[pt.g0 + g];
-        const bool paired = HERM && xl != 0u;
-        if (paired && (e & (xl & (0u - xl)))) continue;
-        const int a0 = gptr[pt.g0 + g] - t0, a1 = gptr[pt.g0 + g + 1] - t0;
-        double pr = 0.0, pi = 0.0;
-        for (int t = a0; t < a1; ++t) {
-          const double2 c = sc[t];
-          const bool odd = __popc(e & szl[t]) & 1;
-          pr += odd ? -c.x : c.x;
-          if (!REALC) pi += odd ? -c.y : c.y;
+    // groups outside, the thread's amplitudes inside: a group's metadata is read once, nothing is carried from one
+    // amplitude to the next but the running sums, and the inner iterations are independent (instruction-level overlap)
+    for (int g = 0; g < pt.ng; ++g) {
+      const uint32_t xl = sgx[g];
+      const int a0 = sgp[g], a1 = sgp[g + 1];
+      const bool paired = HERM && xl != 0u;
+      // a Hermitian group visits each pair (e, e ^ x) once: e runs over the indices with the lowest xmask bit clear
+      const uint32_t pbit = paired ? (uint32_t)(__ffs((int)xl) - 1) : 0u;
+      const uint32_t plow = (1u << pbit) - 1u;
+      const uint32_t count = paired ? nel >> 1 : nel;
+      R sr = 0, si = 0;
+      if (REALC && a1 - a0 <= 2) {
+        // one or two real terms (XX + YY of a Heisenberg bond, a single string): everything in registers
+        const R c0 = sc[a0].x, c1 = a1 - a0 == 2 ? sc[a0 + 1].x : (R)0;
+        const uint32_t z0 = szl[a0], z1 = a1 - a0 == 2 ? szl[a0 + 1] : 0u;
+#pragma unroll 4
+        for (uint32_t k = tid; k < count; k += RT) {
+          const uint32_t e = paired ? (((k & ~plow) << 1) | (k & plow)) : k;
+          const R pr = flip_sign(c0, e & z0) + flip_sign(c1, e & z1);
+          const cplx<T> a = tile[e], b = tile[e ^ xl];
+          sr += (b.x * a.x + b.y * a.y) * pr;
+          if (!HERM) si += (b.x * a.y - b.y * a.x) * pr;
         }
-        const cplx<T> b = tile[e ^ xl];
-        const double w = paired ? 2.0 : 1.0;
-        const double br = w * (double)b.x, bi = -w * (double)b.y;
-        hr += br * pr - bi * pi;
-        hi += br * pi + bi * pr;
+      } else {
+#pragma unroll 2
+        for (uint32_t k = tid; k < count; k += RT) {
+          const uint32_t e = paired ? (((k & ~plow) << 1) | (k & plow)) : k;
+          R pr = 0, pi = 0;
+          for (int t = a0; t < a1; ++t) {
+            const Pair2<R> c = sc[t];
+            const uint32_t v = e & szl[t];
+            pr += flip_sign(c.x, v);
+            if (!REALC) pi += flip_sign(c.y, v);
+          }
+          const cplx<T> a = tile[e], b = tile[e ^ xl];
+          const R qr = b.x * a.x + b.y * a.y, qi = b.x * a.y - b.y * a.x;   // conj(b) * a
+          if (REALC) {
+            sr += qr * pr;
+            if (!HERM) si += qi * pr;
+          } else {
+            sr += qr * pr - qi * pi;
+            if (!HERM) si += qr * pi + qi * pr;
+          }
+        }
       }
-      acc[0] += hr * ar - hi * ai;
-      if (!HERM) acc[1] += hr * ai + hi * ar;
+      const double w = paired ? 2.0 : 1.0;
+      acc[0] += w * (double)sr;
+      if (!HERM) acc[1] += w * (double)si;
     }
   }
   block_reduce<2>(acc, red, partial + (((size_t)blockIdx.y * pt.n_layouts + pt.layout) * gridDim.x + blockIdx.x) * 2);
@@ -609,7 +648,10 @@ __global__ void __launch_bounds__(RT) dm_diag_kernel(const cplx<T> *__restrict__
 constexpr int CW = 4;  // warps per CTA
 template <typename E>
 __global__ void __launch_bounds__(CW * 32) chunk_totals_kernel(const E *__restrict__ state, int n, int chunk_bits,
-                                                               long long n_chunks_total, double *totals) {
+                                                               long long n_chunks_total, double *totals, double *sub) {
+  // sub != nullptr (chunk_bits == 12 only): sub[chunk * 32 + b] = the chunk's sequential running sum after its first
+  // 128 (b + 1) amplitudes -- the SAME partial sums the sequential in-chunk scan passes through, recorded on the way, so
+  // that a sample can enter its chunk at a 128-amplitude boundary (sample_kernel) without changing one rounding.
   __shared__ double buf[CW][32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const long long group = (long long)blockIdx.x * CW + w;  // 32 chunks per group
@@ -626,6 +668,7 @@ __global__ void __launch_bounds__(CW * 32) chunk_totals_kernel(const E *__restri
     }
     __syncwarp();
     for (int e = 0; e < width; ++e) acc = __dadd_rn(acc, buf[w][lane][e]);
+    if (sub && (s0 & 127) == 96 && c0 + lane < n_chunks_total) sub[(size_t)(c0 + lane) * 32 + (s0 >> 7)] = acc;
     __syncwarp();
   }
   if (c0 + lane < n_chunks_total) totals[c0 + lane] = acc;
@@ -662,7 +705,7 @@ template <typename E>
 __global__ void __launch_bounds__(128) sample_kernel(const E *__restrict__ state, int n, int chunk_bits, long long nc,
                                                      long long c_first, long long c_count, long long tail_index,
                                                      const double *__restrict__ prefix, const double *__restrict__ uniforms,
-                                                     long long shots, long long *idx_out) {
+                                                     long long shots, long long *idx_out, const double *__restrict__ sub) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= shots) return;
   const long long b = blockIdx.y;
@@ -686,12 +729,31 @@ __global__ void __launch_bounds__(128) sample_kernel(const E *__restrict__ state
     const double pre = p[lo];
     double run = 0.0;
     size_t cnt = 0;
+    size_t clen_eff = clen;
+    if (sub) {
+      // enter the chunk at the first 128-amplitude block whose LAST running sum fails the test (the test is monotone
+      // along the chunk): the scan then covers at most 128 amplitudes instead of up to 4096
+      const double *sr = sub + ((size_t)b * (size_t)c_count + (size_t)(lo - c_first)) * 32;
+      int blo = 0, bhi = 32;
+      while (blo < bhi) {
+        const int mid = (blo + bhi) >> 1;
+        if (__ddiv_rn(__dadd_rn(pre, sr[mid]), total) <= u) blo = mid + 1; else bhi = mid;
+      }
+      if (blo >= 32) {
+        cnt = clen;      // every amplitude of the chunk passes (rounding at the chunk end): same result as the full scan
+        clen_eff = 0;
+      } else {
+        cnt = (size_t)blo << 7;
+        run = blo ? sr[blo - 1] : 0.0;
+        clen_eff = cnt + 128;
+      }
+    }
     // The test is fl(cdf / total) <= u with the division correctly rounded.  A cdf safely below / above u * total
     // decides it without dividing (relative margin 2^-49 >> the 2^-53 roundings of the product and the quotient);
     // only values inside the margin take the exact division -- same indices, bit for bit, without ~4096 DDIVs a shot.
     const double ut = __dmul_rn(u, total);
     const double safe_lo = __dmul_rn(ut, 1.0 - 0x1p-49), safe_hi = __dmul_rn(ut, 1.0 + 0x1p-49);
-    for (; cnt < clen; ++cnt) {
+    for (; cnt < clen_eff; ++cnt) {
       run = __dadd_rn(run, prob_of(sc[cnt]));
       const double v = __dadd_rn(pre, run);
       if (v < safe_lo) continue;
@@ -895,12 +957,12 @@ int tqb_expect_pauli_tiled(const void *state, int n, int64_t batch, int dtype, u
         prev = lay.hb[i];
       }
     }
-    const size_t smem = ((size_t)es << lay.m) + ((size_t)8 << pt.h) + (size_t)lay.n_terms * 20 + 16;
-    TQB_REQUIRE(smem <= (size_t)ws->max_smem_optin, "tqb_expect_pauli_tiled: tile + terms exceed shared memory");
+    const size_t smem = ((size_t)es << lay.m) + 8 * ((((size_t)1 << pt.h) + 1) & ~(size_t)1) + (size_t)lay.n_terms * 20 + (size_t)lay.n_groups * 8 + 32;
+    TQB_REQUIRE(smem + 1024 <= (size_t)ws->max_smem_optin, "tqb_expect_pauli_tiled: tile + terms exceed shared memory");
 #define TQB_PT(T, HERM, REALC, PTR)                                                                                              \
   do {                                                                                                                            \
     auto kern = expect_pauli_tiled_kernel<T, HERM, REALC>;                                                                        \
-    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->max_smem_optin));                  \
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->max_smem_optin - 1024));           \
     kern<<<dim3((unsigned)nbx, (unsigned)batch), RT, smem, st>>>(PTR(state), pt, global_base, group_xl_dev, group_ptr_dev,       \
                                                                    term_zl_dev, term_zout_dev, term_coef_dev, partial);         \
   } while (0)
@@ -1105,16 +1167,17 @@ int tqb_probabilities(const void *state, int n, int64_t batch, int dtype, double
   return 0;
 }
 
-static int launch_chunk_totals(const void *state, int n, int64_t batch, int dtype, double *totals, cudaStream_t st) {
+static int launch_chunk_totals(const void *state, int n, int64_t batch, int dtype, double *totals, cudaStream_t st, double *sub = nullptr) {
   const int chunk_bits = n < 12 ? n : 12;  // TQB_SCAN_BLOCK = 4096
   const long long nct = (1ll << (n - chunk_bits)) * batch;
   const long long groups = (nct + 31) / 32;
   const long long blocks = (groups + CW - 1) / CW;
   if (dtype == TQB_F64) {
-    chunk_totals_kernel<double><<<(unsigned)blocks, CW * 32, 0, st>>>((const double *)state, n, chunk_bits, nct, totals);
+    if (chunk_bits != 12) sub = nullptr;
+    chunk_totals_kernel<double><<<(unsigned)blocks, CW * 32, 0, st>>>((const double *)state, n, chunk_bits, nct, totals, sub);
   } else
-  if (by_dtype(dtype, [&] { chunk_totals_kernel<cplx<double>><<<(unsigned)blocks, CW * 32, 0, st>>>(CD(state), n, chunk_bits, nct, totals); },
-               [&] { chunk_totals_kernel<cplx<float>><<<(unsigned)blocks, CW * 32, 0, st>>>(CF(state), n, chunk_bits, nct, totals); })) return -1;
+  if (by_dtype(dtype, [&] { chunk_totals_kernel<cplx<double>><<<(unsigned)blocks, CW * 32, 0, st>>>(CD(state), n, chunk_bits, nct, totals, chunk_bits == 12 ? sub : nullptr); },
+               [&] { chunk_totals_kernel<cplx<float>><<<(unsigned)blocks, CW * 32, 0, st>>>(CF(state), n, chunk_bits, nct, totals, chunk_bits == 12 ? sub : nullptr); })) return -1;
   TQB_CHECK_LAUNCH("chunk_totals_kernel");
   return 0;
 }
@@ -1135,6 +1198,11 @@ int tqb_dm_diag(const void *rho, int n, int64_t batch, int dtype, double *out_de
 }
 
 int tqb_cdf_chunks(const void *state, int n, int64_t batch, int dtype, double *chunk_prefix_dev, void *stream) {
+  return tqb_cdf_chunks2(state, n, batch, dtype, chunk_prefix_dev, nullptr, stream);
+}
+
+int tqb_cdf_chunks2(const void *state, int n, int64_t batch, int dtype, double *chunk_prefix_dev, double *sub_prefix_dev,
+                    void *stream) {
   TQB_REQUIRE(state && chunk_prefix_dev && n >= 0 && n < 48 && batch >= 1, "tqb_cdf_chunks: bad arguments");
   Workspace *ws = workspace();
   if (!ws) return -1;
@@ -1143,7 +1211,7 @@ int tqb_cdf_chunks(const void *state, int n, int64_t batch, int dtype, double *c
   TQB_REQUIRE((size_t)(nc * batch) * sizeof(double) <= ws->bytes, "tqb_cdf_chunks: workspace too small for the chunk totals");
   double *totals = (double *)ws->ptr;
   cudaStream_t st = as_stream(stream);
-  if (launch_chunk_totals(state, n, batch, dtype, totals, st)) return -1;
+  if (launch_chunk_totals(state, n, batch, dtype, totals, st, sub_prefix_dev)) return -1;
   chunk_prefix_kernel<<<(unsigned)batch, RT, 0, st>>>(totals, nc, chunk_prefix_dev);
   TQB_CHECK_LAUNCH("chunk_prefix_kernel");
   return 0;
@@ -1163,18 +1231,24 @@ int tqb_chunk_prefix(const double *totals_dev, int64_t n_chunks, int64_t batch, 
 
 int tqb_sample(const void *state, int n, int64_t batch, int dtype, const double *chunk_prefix_dev, const double *uniforms_dev,
                int64_t shots, int64_t *idx_dev, void *stream) {
+  return tqb_sample2(state, n, batch, dtype, chunk_prefix_dev, nullptr, uniforms_dev, shots, idx_dev, stream);
+}
+
+int tqb_sample2(const void *state, int n, int64_t batch, int dtype, const double *chunk_prefix_dev, const double *sub_prefix_dev,
+                const double *uniforms_dev, int64_t shots, int64_t *idx_dev, void *stream) {
   TQB_REQUIRE(state && chunk_prefix_dev && uniforms_dev && idx_dev && n >= 0 && n < 48 && batch >= 1 && batch <= 65535 && shots >= 1,
               "tqb_sample: bad arguments");
   const int chunk_bits = n < 12 ? n : 12;
   const long long nc = 1ll << (n - chunk_bits);
   dim3 grid((unsigned)((shots + 127) / 128), (unsigned)batch);
   cudaStream_t st = as_stream(stream);
+  const double *sub = chunk_bits == 12 ? sub_prefix_dev : nullptr;
   if (dtype == TQB_F64) {
-    sample_kernel<double><<<grid, 128, 0, st>>>((const double *)state, n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev);
+    sample_kernel<double><<<grid, 128, 0, st>>>((const double *)state, n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev, sub);
   } else
   if (by_dtype(dtype,
-               [&] { sample_kernel<cplx<double>><<<grid, 128, 0, st>>>(CD(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
-               [&] { sample_kernel<cplx<float>><<<grid, 128, 0, st>>>(CF(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
+               [&] { sample_kernel<cplx<double>><<<grid, 128, 0, st>>>(CD(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev, sub); },
+               [&] { sample_kernel<cplx<float>><<<grid, 128, 0, st>>>(CF(state), n, chunk_bits, nc, 0, nc, 1ll << n, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev, sub); }))
     return -1;
   TQB_CHECK_LAUNCH("sample_kernel");
   return 0;
@@ -1204,8 +1278,8 @@ int tqb_sample_shard(const void *state, int n_local, int dtype, const double *ch
   dim3 grid((unsigned)((shots + 127) / 128), 1);
   cudaStream_t st = as_stream(stream);
   if (by_dtype(dtype,
-               [&] { sample_kernel<cplx<double>><<<grid, 128, 0, st>>>(CD(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); },
-               [&] { sample_kernel<cplx<float>><<<grid, 128, 0, st>>>(CF(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev); }))
+               [&] { sample_kernel<cplx<double>><<<grid, 128, 0, st>>>(CD(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev, nullptr); },
+               [&] { sample_kernel<cplx<float>><<<grid, 128, 0, st>>>(CF(state), n_local, chunk_bits, (long long)n_chunks_total, (long long)chunk_first, c_count, (long long)tail_index, chunk_prefix_dev, uniforms_dev, (long long)shots, (long long *)idx_dev, nullptr); }))
     return -1;
   TQB_CHECK_LAUNCH("sample_kernel");
   return 0;

@@ -187,10 +187,12 @@ class ShotEnergy:
         self.tile = tile
         self.n_params = 1 + max([a.index for op in self.template for a in op if isinstance(a, Param)], default=-1)
         self.passes = 0
-        # the reference's rule (hea_device_runtime.py:180-262) shifts the PARAMETER by +-pi/2: exact only when every
-        # parameter drives exactly one rotation gate exp(-i theta/2 P) with unit scale -- anything else is refused
-        # instead of returning a silently wrong gradient (AdjointEnergy / ShardedStatevectorEngine.energy_and_grad
-        # differentiate per gate occurrence and take such templates)
+
+    def _check_shift_rule(self) -> None:
+        """The reference's rule (hea_device_runtime.py:180-262) shifts the PARAMETER by +-pi/2: exact only when every
+        parameter drives exactly one rotation gate exp(-i theta/2 P) with unit scale -- anything else is refused instead
+        of returning a silently wrong gradient (AdjointEnergy / ShardedStatevectorEngine.energy_and_grad differentiate
+        per gate occurrence and take such templates)."""
         seen: dict = {}
         for op in self.template:
             for a in op:
@@ -221,6 +223,7 @@ class ShotEnergy:
 
     def energy_and_grad(self, params: Sequence[float], uniforms: Any) -> Tuple[float, np.ndarray]:
         """uniforms: [(1 + 2P) * G, shots], circuit order base, (+0, -0), (+1, -1), ... each over all groups."""
+        self._check_shift_rule()
         base = np.asarray(params, dtype=np.float64).reshape(-1)
         Pn = base.size
         variants = np.tile(base, (1 + 2 * Pn, 1))

@@ -193,9 +193,12 @@ def sample(state: torch.Tensor, uniforms: torch.Tensor) -> torch.Tensor:
         raise _lib.TqbError("uniforms must be [shots] or [batch, shots]")
     nc = 1 << (n - min(n, 12))
     prefix = torch.empty((batch, nc + 1), dtype=torch.float64, device=state.device)
+    # in-chunk partial sums every 128 amplitudes (n >= 12): a shot then scans <= 128 amplitudes of its chunk
+    sub = torch.empty((batch, nc, 32), dtype=torch.float64, device=state.device) if n >= 12 else None
     idx = torch.empty(u.shape, dtype=torch.int64, device=state.device)
     with torch.cuda.device(state.device):
         lib = _lib.load()
-        _lib.check(lib.tqb_cdf_chunks(ptr, n, batch, dt, prefix.data_ptr(), stream))
-        _lib.check(lib.tqb_sample(ptr, n, batch, dt, prefix.data_ptr(), u.data_ptr(), shots, idx.data_ptr(), stream))
+        sp = sub.data_ptr() if sub is not None else None
+        _lib.check(lib.tqb_cdf_chunks2(ptr, n, batch, dt, prefix.data_ptr(), sp, stream))
+        _lib.check(lib.tqb_sample2(ptr, n, batch, dt, prefix.data_ptr(), sp, u.data_ptr(), shots, idx.data_ptr(), stream))
     return idx
