@@ -216,6 +216,10 @@ def own_arm(args) -> None:
     dev = torch.device("cuda", local_rank)
     _lib.ensure_device(local_rank)
     if world > 1:
+        # the global<->local exchange is one big send/recv per peer: give NCCL's point-to-point path enough channels to
+        # fill NVLink (with 2 ranks the default left the link at 0.56 of the peer-copy peak, SCALE_r01)
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
         dist.init_process_group("nccl", device_id=dev)
     n = args.n or (30 + int(math.log2(world)))
     tdt = torch.complex128 if args.dtype == "complex128" else torch.complex64
@@ -338,6 +342,7 @@ def own_arm(args) -> None:
         # config 4 of BASELINE.json rides in the same line: TFIM Trotter evolution, complex64, 33 + log2(N) qubits
         # (36 qubits = 64 GiB per GPU on 8 GPUs), sharded by global qubits -- every rank takes part
         try:
+            sb_breakdown = sb.breakdown
             del sb
             torch.cuda.empty_cache()
             trotter = trotter_config4(world, rank, dev, peaks)
@@ -357,7 +362,7 @@ def own_arm(args) -> None:
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "specialised_launches": int(spec_launches), "roofline": roof,
             "hbm_gbps_per_gpu": achieved, "expz_checksum": float(z.sum().item())}
     if world > 1:
-        bd = sb.breakdown
+        bd = sb_breakdown if trotter is not None else sb.breakdown
         # combined roofline: local passes at the measured HBM peak + exchanges at the measured NVLink peer peak, no overlap
         ideal_ms = info["passes"] * alg_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3 + \
             bd["exchange_bytes_per_gpu_each_way"] / (bd["nvlink_peak_gbps"] * 1e9) * 1e3

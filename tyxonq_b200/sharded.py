@@ -264,6 +264,22 @@ def plan_restore(phys_in: Sequence[int], n: int, g: int) -> ShardPlan:
 # ------------------------------------------------------------------------------------------
 # the exchange
 # ------------------------------------------------------------------------------------------
+_LANES: dict = {}   # group -> extra NCCL communicators over the same ranks (parallel lanes of one exchange)
+
+
+def _exchange_lanes(group: Any, world: int) -> list:
+    """With few ranks one all-to-all is one send/recv pair per peer and NCCL leaves most of NVLink idle (2 ranks: 0.52 of
+    the peer-copy peak).  Extra communicators over the same ranks let slices of the exchange run as concurrent collectives.
+    TQB_EXCHANGE_LANES overrides the count (1 = a single all-to-all)."""
+    import os
+    key = id(group)
+    if key not in _LANES:
+        want = int(os.environ.get("TQB_EXCHANGE_LANES", "0")) or (4 if world <= 2 else (2 if world <= 4 else 1))
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
+        _LANES[key] = [dist.new_group(ranks=ranks, backend="nccl") for _ in range(max(0, want - 1))]
+    return _LANES[key]
+
+
 def exchange(out: torch.Tensor, inp: torch.Tensor, group: Any = None) -> None:
     """out[j] <- chunk `rank` of rank j's inp, for inp/out viewed as [G, chunk] (the global<->local swap)."""
     world = dist.get_world_size(group)
@@ -272,7 +288,25 @@ def exchange(out: torch.Tensor, inp: torch.Tensor, group: Any = None) -> None:
     out2 = out.view(world, -1)
     if dist.get_backend(group) == "nccl":
         # complex tensors go over the wire as reals
-        dist.all_to_all_single(torch.view_as_real(out2).reshape(world, -1), torch.view_as_real(inp2).reshape(world, -1), group=group)
+        o = torch.view_as_real(out2).reshape(world, -1)
+        i = torch.view_as_real(inp2).reshape(world, -1)
+        lanes = _exchange_lanes(group, world)
+        k = len(lanes) + 1
+        cols = o.shape[1]
+        if k == 1 or cols % k or cols < (1 << 20):
+            dist.all_to_all_single(o, i, group=group)
+            return
+        # lane l moves columns [l, l+1) * cols / k of every chunk: k concurrent all-to-alls on k communicators
+        w = cols // k
+        works = list(enumerate([group] + lanes))
+        # slices of a [world, cols] view are strided: exchange them through split lists (no staging copies)
+        hs = []
+        for l, g_l in works:
+            out_list = [o[j, l * w:(l + 1) * w] for j in range(world)]
+            in_list = [i[j, l * w:(l + 1) * w] for j in range(world)]
+            hs.append(dist.all_to_all(out_list, in_list, group=g_l, async_op=True))
+        for h in hs:
+            h.wait()
         return
     ops = []
     for j in range(world):
