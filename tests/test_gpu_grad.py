@@ -165,3 +165,24 @@ def test_b200_backend_value_and_grad(cuda_device):
     got = K.to_numpy(K.choice(np.random.default_rng(5), 8, size=64, p=K.array(p)))
     want = np.random.default_rng(5).choice(8, size=64, p=p / p.sum())
     assert np.array_equal(got, want)
+
+
+def test_ucc_pair_gates_match_reference_fixture(cuda_device):
+    """The device form of exp(theta G) -- ONE PAIR gate per excitation (ucc.excitation_gate) -- against the fixture
+    generated from the reference's own constants and apply_kqubit_unitary (tests/golden/make_golden_ucc.py; mode
+    'qubit': statevector_ops.py:42-43, 140-168).  With tests/test_ucc_host.py this pins the UCC evolution to reference
+    output in everything but the Jordan-Wigner sign vector (openfermion is not installable here)."""
+    import torch
+    from pathlib import Path
+    from tyxonq_b200 import program as P
+    from tyxonq_b200 import ucc
+    d = np.load(Path(__file__).resolve().parent / "golden" / "reference_ucc.npz")
+    n, psi0 = int(d["n"]), d["psi0"]
+    ex = [tuple(int(x) for x in r if x >= 0) for r in d["ex_ops"]]
+    for k, (f, t) in enumerate(zip(ex, d["thetas"])):
+        st = torch.from_numpy(psi0.copy()).to(cuda_device)
+        P.apply_gates(st, [ucc.excitation_gate(f, float(t), n, mode="qubit")])
+        assert np.abs(st.cpu().numpy() - d["each"][k]).max() < 1e-12, f
+    st = torch.from_numpy(psi0.copy()).to(cuda_device)
+    P.apply_gates(st, [ucc.excitation_gate(f, float(t), n, mode="qubit") for f, t in zip(ex, d["thetas"])])
+    assert np.abs(st.cpu().numpy() - d["sequence"]).max() < 1e-12

@@ -378,10 +378,10 @@ def test_specialised_kernels_match_oracle(cuda_device):
 
 
 def test_large_state_invariants(cuda_device):
-    """n = 28 (4 GiB complex128): GHZ amplitudes, norm, reversibility -- size-independent properties."""
+    """n = 30 (16 GiB complex128, the bench size): GHZ amplitudes, norm, reversibility -- size-independent properties."""
     import torch
     from tyxonq_b200 import program as P
-    n = 28
+    n = 30
     eng = _engine(cuda_device, "b200")
     ghz = [("h", 0)] + [("cx", q, q + 1) for q in range(n - 1)]
     psi, _, _ = eng._evolve(FakeCircuit(n, ghz), "state")
@@ -423,6 +423,45 @@ def test_batched_ansatz_expval_and_sampling(cuda_device):
             assert np.abs(st[b] - ref).max() < tol
             assert abs(ev[b] - O.expect_pauli_sum(ref, terms, w)) < tol * 50
             assert np.array_equal(idx[b], O.sample_indices(O.probabilities(st[b]), u[b]))
+
+
+def test_kqubit_unitary_above_four_qubits(cuda_device):
+    """apply_kqubit_unitary has no size limit in the reference (statevector.py:71-129): k = 5, 6 on scattered qubits."""
+    from scipy.stats import unitary_group
+    from tyxonq_b200 import kernels as K
+    rng = np.random.default_rng(41)
+    n = 9
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    psi /= np.linalg.norm(psi)
+    for k, qs in ((5, [7, 0, 3, 8, 2]), (6, [1, 5, 0, 4, 8, 6])):
+        U = unitary_group.rvs(1 << k, random_state=int(rng.integers(1 << 30)))
+        got = K.apply_kqubit_unitary(psi, U, qs, n)
+        assert isinstance(got, np.ndarray)
+        assert np.abs(got - O.apply_kq(psi, U, qs, n)).max() < TOL128
+
+
+def test_batched_config5_full_size(cuda_device):
+    """Config 5 at its own size: 20-qubit HWE-RY ansatz (4 layers), 8 parameter sets, the 57-term Heisenberg chain,
+    8192 shots per state -- states, expectation values (tiled kernel, two layouts) and sampled indices against the oracle."""
+    import torch
+    from tyxonq_b200 import PauliSum
+    from tyxonq_b200.batched import BatchedAnsatz
+    n, L, B, shots = 20, 4, 8, 8192
+    rng = np.random.default_rng(7)
+    params = rng.random((B, (L + 1) * n))
+    terms, w = O.heisenberg_terms(n, [(i, i + 1) for i in range(n - 1)], hzz=1.0, hxx=1.0, hyy=1.0)
+    ham = PauliSum.from_codes(terms, w)
+    assert ham.n_terms == 57
+    u = np.random.default_rng(99).random((B, shots))
+    ba = BatchedAnsatz(n, L, B, device=cuda_device, dtype=torch.complex64)
+    st = ba.run(params).cpu().numpy()
+    ev = ba.expvals(ham).cpu().numpy()
+    idx = ba.sample(torch.from_numpy(u)).cpu().numpy()
+    for b in range(B):
+        ref, _ = O.evolve_ops(n, O.hwe_ry_ops(n, L, params[b]))
+        assert np.abs(st[b] - ref).max() < 1e-5
+        assert abs(ev[b] - O.expect_pauli_sum(ref, terms, w)) < 2e-4
+        assert np.array_equal(idx[b], O.sample_indices(O.probabilities(st[b]), u[b]))
 
 
 def test_pauli_sum_on_shards_of_one_state(cuda_device):

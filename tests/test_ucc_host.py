@@ -89,3 +89,21 @@ def test_pauli_sum_constructors():
         terms = {tuple((q, "IXYZ"[c]) for q, c in enumerate(terms[t]) if c): w[t] for t in range(12)}
     c = PauliSum.from_qubit_operator(n, Q)
     assert np.abs(_pauli_sum_matvec(c, v) - _pauli_sum_matvec(a, v)).max() < 1e-12
+
+
+def test_oracle_matches_reference_excitation_fixture():
+    """tests/golden/reference_ucc.npz: exp(theta G) in the reference's mode != 'fermion' branch (statevector_ops.py:42-43,
+    140-168), evaluated by make_golden_ucc.py with the reference's own constants (applications/chem/constants.py:5-15) and
+    its apply_kqubit_unitary.  Pins everything of the UCC evolution except the Jordan-Wigner sign vector."""
+    import numpy as np
+    from pathlib import Path
+    from oracle import ucc_oracle as U
+    d = np.load(Path(__file__).resolve().parent / "golden" / "reference_ucc.npz")
+    n, psi0 = int(d["n"]), d["psi0"]
+    ex = [tuple(int(x) for x in r if x >= 0) for r in d["ex_ops"]]
+    assert np.array_equal(U.AD_A_HC, d["ad_a_hc"]) and np.array_equal(U.ADAD_AA_HC, d["adad_aa_hc"])
+    psi = psi0
+    for k, (f, t) in enumerate(zip(ex, d["thetas"])):
+        assert np.abs(U.evolve_excitation(psi0, f, float(t), n, mode="qubit") - d["each"][k]).max() < 1e-14
+        psi = U.evolve_excitation(psi, f, float(t), n, mode="qubit")
+    assert np.abs(psi - d["sequence"]).max() < 1e-14

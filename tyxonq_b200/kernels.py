@@ -131,18 +131,49 @@ def apply_2q_statevector(backend: Any, state: Any, gate4: Any, q0: int, q1: int,
 
 
 def apply_kqubit_unitary(state: Any, unitary: Any, qubit_indices: Sequence[int], num_qubits: int, backend: Any | None = None) -> Any:
-    """statevector.py:71-129 (first listed qubit = most significant bit of the matrix index); k <= 4."""
+    """statevector.py:71-129 (first listed qubit = most significant bit of the matrix index).  k <= 4: one fused device
+    pass; k > 4: one device GEMM (_apply_dense_large)."""
     k = len(qubit_indices)
     if k == 0:
         return state
     if k > 4:
-        raise NotImplementedError("apply_kqubit_unitary: k > 4 dense blocks are not supported on the device path")
+        return _apply_dense_large(state, unitary, [int(q) for q in qubit_indices], int(num_qubits))
     if _needs_grad(state, unitary):
         return _ApplyUnitary.apply(state, unitary if isinstance(unitary, torch.Tensor) else torch.as_tensor(_to_np(unitary)),
                                    tuple(int(q) for q in qubit_indices), int(num_qubits))
     t, how = _to_dev(state)
     P.apply_gates(t, [classify_unitary(_to_np(unitary), [int(q) for q in qubit_indices], int(num_qubits))])
     return _back(t, how)
+
+
+def _apply_dense_large(state: Any, unitary: Any, qubits: Sequence[int], n: int) -> Any:
+    """k > 4 target qubits (the reference has no limit, statevector.py:71-129): the 2^k x 2^k block is GEMM-shaped, so it
+    runs as ONE device matmul on the state viewed as [2^(n-k), 2^k] with the target axes moved last (a plain library
+    GEMM through torch, differentiable by torch itself); the fused pass kernels stop at 4-qubit blocks."""
+    k = len(qubits)
+    if len(set(qubits)) != k or any(q < 0 or q >= n for q in qubits):
+        raise ValueError("apply_kqubit_unitary: bad qubit indices")
+    dev = _device()
+    if isinstance(state, torch.Tensor):
+        how = "cuda" if state.is_cuda else "torch"
+        t = state.to(dev).to(torch.complex128).reshape(-1)
+    else:
+        how = "numpy"
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(state, dtype=np.complex128).reshape(-1))).to(dev)
+    U = unitary if isinstance(unitary, torch.Tensor) else torch.from_numpy(_to_np(unitary))
+    U = U.to(dev).to(torch.complex128).reshape(1 << k, 1 << k)
+    rest = [q for q in range(n) if q not in qubits]
+    perm = rest + list(qubits)                     # tensor axis q = qubit q (big-endian), first listed target = MSB of the block index
+    psi = t.reshape([2] * n).permute(perm).reshape(1 << (n - k), 1 << k)
+    out = (psi @ U.transpose(0, 1)).reshape([2] * n)
+    inv = [0] * n
+    for pos, q in enumerate(perm):
+        inv[q] = pos
+    out = out.permute(inv).reshape(-1)
+    if how == "cuda":
+        return out.reshape(state.shape)
+    c = out.cpu()
+    return c.numpy() if how == "numpy" else c.reshape(state.shape)
 
 
 def expect_z_statevector(state: Any, qubit: int, num_qubits: int, backend: Any | None = None) -> Any:
