@@ -605,8 +605,23 @@ def extras(dev, quick: bool = False) -> dict:
             e, g = v.energy_and_grad(p)
         ts.append((time.perf_counter() - t0) / 100)
     dt = float(np.median(ts))
+    pb = np.random.default_rng(1).normal(size=(1024, 20))
+    v.energy_and_grad_batch(pb)
+    tb = []
+    for _ in range(5):
+        t0 = time.perf_counter(); v.energy_and_grad_batch(pb); tb.append(time.perf_counter() - t0)
+    tg = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        for _ in range(50):
+            v.energy_and_grad(p, resident=False)
+        tg.append((time.perf_counter() - t0) / 50)
     out["tfim10_energy_grad"] = {"evals_per_s": 1.0 / dt, "energy": e, "repetitions": "5 x 100",
-                                 "note": "examples/vqetfim_benchmark.py ansatz + Hamiltonian, adjoint gradient, one CUDA graph per evaluation",
+                                 "batched_evals_per_s": 1024 / float(np.median(tb)), "batch": 1024,
+                                 "fused_pass_graph_path_evals_per_s": 1.0 / float(np.median(tg)),
+                                 "note": "examples/vqetfim_benchmark.py ansatz + Hamiltonian, adjoint gradient: CTA-resident kernel (csrc/tqb_vqe.cu), one "
+                                         "evaluation per call (host round trip included) and 1024 parameter vectors per launch; the round-1 path "
+                                         "(fused passes, one CUDA graph per evaluation) beside it",
                                  "cpu_baseline": RB.tfim10_energy_grad_reference(5) if have_ref else {"error": "baseline/_ref missing"}}
     del sv, v
     torch.cuda.empty_cache()

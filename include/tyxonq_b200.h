@@ -245,6 +245,28 @@ typedef struct tqb_pair_step {
 int tqb_pair_sweep(void *ket, void *bra, int n, int dtype, const tqb_pair_step *steps_dev, int n_steps,
                    int mode, double *out_dev, unsigned long long *sync_dev, void *stream);
 
+/* A whole variational evaluation -- forward circuit, bra = H ket, E = Re<ket|bra>, reverse sweep with the gradient inner
+ * products -- in ONE shared-memory-resident CTA per parameter vector (n <= 12 qubits, complex128): replaces value_and_grad
+ * of the reference's numerics backends (numpy_backend.py:386-454, pytorch_backend.py:446-564) around
+ * examples/vqetfim_benchmark.py:70-103 for small registers, where an evaluation is latency, not bandwidth.
+ * ops (device array): kind 0 = Pauli rotation exp(-i theta/2 P), P = i^popc(x&z) X^xmask Z^zmask on index bits,
+ * theta = scale * params[param] (param < 0: theta = scale); kind 1 / 2 = fixed 1- / 2-qubit matrix at fixed_mats[mat_off]
+ * (complex128 entries, row-major; 2-qubit index = 2 * bit(bit0) + bit(bit1)).  Hamiltonian in the layout of
+ * tqb_expect_pauli_sum with 32-bit masks.  params_dev: [batch][n_params]; out_dev: [batch][1 + n_params] = energy, gradient. */
+typedef struct tqb_vqe_op {
+  int32_t kind;
+  int32_t param;
+  uint32_t xmask, zmask;
+  int32_t bit0, bit1;
+  int32_t mat_off;
+  int32_t reserved;
+  double scale;
+} tqb_vqe_op; /* 40 bytes */
+int tqb_vqe_resident(int n, const tqb_vqe_op *ops_dev, int n_ops, const double *fixed_mats_dev,
+                     const uint32_t *ham_x_dev, const int32_t *ham_ptr_dev, int n_groups,
+                     const uint32_t *ham_z_dev, const double *ham_coef_dev, const double *params_dev,
+                     int n_params, int64_t batch, double *out_dev, void *stream);
+
 /* Reduced density matrix of index bit `bit`, per batch member: out_dev[4b..4b+4) = rho00, rho11,
  * Re rho01, Im rho01 with rho01 = sum psi_0 conj(psi_1).  Gives the Born probabilities
  * p_i = tr(K_i^+ K_i rho) of a 1-qubit Kraus channel in ONE read of the state (replaces the m

@@ -186,3 +186,62 @@ def test_ucc_pair_gates_match_reference_fixture(cuda_device):
     st = torch.from_numpy(psi0.copy()).to(cuda_device)
     P.apply_gates(st, [ucc.excitation_gate(f, float(t), n, mode="qubit") for f, t in zip(ex, d["thetas"])])
     assert np.abs(st.cpu().numpy() - d["sequence"]).max() < 1e-12
+
+
+def test_resident_vqe_kernel(cuda_device):
+    """The CTA-resident evaluation (csrc/tqb_vqe.cu: forward, H|psi>, energy, reverse sweep in one CTA per parameter vector)
+    against the oracle's energy and central differences, against the fused-pass / CUDA-graph path, and as a batch --
+    the TFIM ansatz of examples/vqetfim_benchmark.py and a template with fixed gates, fixed angles, scaled and shared
+    parameters."""
+    from tyxonq_b200.pauli import PauliSum
+    from tyxonq_b200.vqe import AdjointEnergy, Param, ResidentVQE, TFIMVqe
+    rng = np.random.default_rng(12)
+    # (1) TFIM-10, one layer
+    v = TFIMVqe(10, 1, device=cuda_device)
+    assert v._resident is not None
+    p = rng.normal(size=(2, 10))
+    e, g = v.energy_and_grad(p)
+    e2, g2 = v.energy_and_grad(p, resident=False)
+    assert abs(e - e2) < 1e-10 and np.abs(g - g2).max() < 1e-10
+    B = 37
+    pb = rng.normal(size=(B, 20))
+    eb, gb = v.energy_and_grad_batch(pb)
+    for b in (0, 5, B - 1):
+        e1, g1 = v.energy_and_grad(pb[b].reshape(2, 10), resident=False)
+        assert abs(eb[b] - e1) < 1e-10 and np.abs(gb[b] - g1.reshape(-1)).max() < 1e-10
+    # (2) a template with fixed gates / angles, scaled and shared parameters, Y strings in H
+    n = 6
+    tmpl = [("h", q) for q in range(n)] + [("cx", 0, 1), ("ry", 1, Param(0)), ("rzz", 1, 2, Param(1, 2.0)), ("cz", 2, 3), ("rx", 3, 0.3),
+            ("ryy", 3, 4, Param(0, -1.0)), ("s", 4), ("swap", 4, 5), ("rz", 5, Param(2)), ("rxx", 0, 5, Param(3)), ("sdg", 0),
+            ("rx", 2, Param(4)), ("x", 3), ("cx", 5, 2)]
+    ham_list = [(0.7, [("Z", 0), ("Z", 1)]), (-0.4, [("X", 1), ("Y", 3)]), (0.25, [("Y", 2)]), (0.6, [("X", 0), ("X", 5)]), (0.1, []),
+                (-0.3, [("Z", 4)]), (0.45, [("Y", 1), ("Y", 4), ("Z", 5)])]
+    ham = PauliSum.from_pauli_list(n, ham_list)
+    assert ResidentVQE.supports(n, tmpl) and not ResidentVQE.supports(n, tmpl + [("t", 0)])
+    ae = AdjointEnergy(n, tmpl, ham, device=cuda_device)
+    th = rng.uniform(-1, 1, 5)
+
+    def build(t):
+        out = []
+        for op in tmpl:
+            out.append(tuple(a.scale * t[a.index] if isinstance(a, Param) else a for a in op))
+        return out
+
+    codes = {"X": 1, "Y": 2, "Z": 3}
+    terms = []
+    for c, ops in ham_list:
+        ps = [0] * n
+        for pch, q in ops:
+            ps[q] = codes[pch]
+        terms.append(ps)
+    w = [c for c, _ in ham_list]
+
+    def energy(t):
+        psi, _ = O.evolve_ops(n, build(t), mode="state")
+        return O.expect_pauli_sum(psi, terms, w)
+
+    e, g = ae.energy_and_grad(th)
+    assert abs(e - energy(th)) < 1e-10
+    assert np.abs(g - O.central_fd_gradient(energy, th, 1e-6)).max() < 1e-7
+    e2, g2 = ae.energy_and_grad(th, resident=False)
+    assert abs(e - e2) < 1e-10 and np.abs(g - g2).max() < 1e-9

@@ -283,10 +283,12 @@ def test_tfim_vqe_energy(cuda_device):
     fd = O.central_fd_gradient(lambda x: O.tfim_vqe_energy(10, 1, x.reshape(2, 10)), p.reshape(-1), 1e-6)
     assert abs(e - O.tfim_vqe_energy(10, 1, p)) < TOL128
     assert np.abs(g.reshape(-1) - fd).max() < 1e-7
-    # later calls replay one CUDA graph with rewritten matrices
-    for scale in (0.5, -1.3):
+    # (that call ran the CTA-resident kernel, csrc/tqb_vqe.cu); the fused-pass path: later calls replay one CUDA graph
+    # with rewritten matrices
+    assert v._resident is not None
+    for scale in (1.0, 0.5, -1.3):
         q = p * scale
-        e2, g2 = v.energy_and_grad(q)
+        e2, g2 = v.energy_and_grad(q, resident=False)
         assert abs(e2 - O.tfim_vqe_energy(10, 1, q)) < TOL128
         fd2 = O.central_fd_gradient(lambda x: O.tfim_vqe_energy(10, 1, x.reshape(2, 10)), q.reshape(-1), 1e-6)
         assert np.abs(g2.reshape(-1) - fd2).max() < 1e-7

@@ -42,6 +42,11 @@ PAIR_STEP_DTYPE = np.dtype([
     ("k", "<i4"), ("slot", "<i4"), ("sbits", "i1", (MAX_GATE_BITS,)),
     ("off_a", "<u8"), ("off_b", "<u8"), ("zmask", "<u8"), ("c", "<f8"), ("s", "<f8"), ("scale", "<f8"),
 ], align=True)
+VQE_OP_DTYPE = np.dtype([
+    ("kind", "<i4"), ("param", "<i4"), ("xmask", "<u4"), ("zmask", "<u4"), ("bit0", "<i4"), ("bit1", "<i4"),
+    ("mat_off", "<i4"), ("reserved", "<i4"), ("scale", "<f8"),
+], align=True)
+assert VQE_OP_DTYPE.itemsize == 40, VQE_OP_DTYPE.itemsize
 assert PAIR_STEP_DTYPE.itemsize == 64, PAIR_STEP_DTYPE.itemsize
 assert GATE_DTYPE.itemsize == 48, GATE_DTYPE.itemsize
 assert PASS_DTYPE.itemsize == 44, PASS_DTYPE.itemsize
@@ -81,6 +86,7 @@ SIGNATURES = {
     "tqb_grad_pair": (_i, [_vp, _vp, _i, _i, _vp, _d, _vp, _i, _vp]),
     "tqb_grad_dense": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _d, _vp, _i, _vp]),
     "tqb_pair_sweep": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "tqb_vqe_resident": (_i, [_i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
     "tqb_project_z": (_i, [_vp, _i, _i64, _i, _i, _i, _vp]),
     "tqb_scale": (_i, [_vp, _i, _i64, _i, _d, _vp]),
     "tqb_probabilities": (_i, [_vp, _i, _i64, _i, _vp, _vp]),

@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libtyxonq_b200.so"
-SOURCES = ["tqb_tile.cu", "tqb_reduce.cu", "tqb_jit.cu"]
+SOURCES = ["tqb_tile.cu", "tqb_reduce.cu", "tqb_jit.cu", "tqb_vqe.cu"]
 HEADERS = ["tqb_core.cuh", "tqb_host.h", "tqb_spec.cuh", "../../include/tyxonq_b200.h"]
 
 NVCC_FLAGS = [

@@ -55,6 +55,7 @@ class AdjointEnergy:
         self._out_host = torch.zeros(1 + max(self.n_params, 1), dtype=torch.float64).pin_memory()
         self._graph = None
         self._calls = 0
+        self._resident = None   # set at the end of __init__ (ResidentVQE is defined below)
         # structure: lower once (theta = 0), compile the forward program and one un-apply pass per gate
         gates, self._refs = self._lower(np.zeros(max(self.n_params, 1)))
         self._ng = len(gates)
@@ -72,6 +73,8 @@ class AdjointEnergy:
             bits = (C.c_int * len(g.bits))(*[int(b) for b in g.bits])
             gen = np.ascontiguousarray(np.asarray(GEN[g.name], dtype=np.complex128).reshape(-1)).view(np.float64).copy()
             self._gen.append((bits, gen, 2.0 * ref.scale, ref.index, len(g.bits)))
+        if mode == "state" and ResidentVQE.supports(self.n, self.template, dtype):
+            self._resident = ResidentVQE(self.n, self.template, ham, device=self.device)
 
     def _lower(self, params: np.ndarray) -> Tuple[List[LGate], List[Optional[Param]]]:
         gates: List[LGate] = []
@@ -138,7 +141,22 @@ class AdjointEnergy:
         self._out[0:1].copy_(self._e[0:1])
         self._out[1:1 + self.n_params].copy_(self._gout[: self.n_params])
 
-    def energy_and_grad(self, params: Sequence[float], *, graph: bool = True) -> Tuple[float, np.ndarray]:
+    def energy_and_grad_batch(self, params: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Many parameter vectors at once ([B, n_params] -> energies [B], gradients [B, n_params]): one launch of the
+        CTA-resident kernel when the template qualifies, else one evaluation after the other."""
+        p = np.asarray(params, dtype=np.float64).reshape(-1, max(self.n_params, 1))
+        if self._resident is not None:
+            return self._resident.energy_and_grad_batch(p)
+        es, gs = zip(*(self.energy_and_grad(row) for row in p))
+        return np.array(es), np.stack([np.asarray(g).reshape(-1) for g in gs])
+
+    def energy_and_grad(self, params: Sequence[float], *, graph: bool = True, resident: Optional[bool] = None) -> Tuple[float, np.ndarray]:
+        """``resident``: None = the CTA-resident kernel when the template qualifies (n <= 12, complex128, Pauli rotations +
+        fixed Clifford-type gates), False = the fused-pass / CUDA-graph path below."""
+        if resident is not False and self._resident is not None:
+            return self._resident.energy_and_grad(params)
+        if resident:
+            raise NotImplementedError("template outside the resident kernel's op set")
         p = np.asarray(params, dtype=np.float64)
         shape = p.shape
         self._fill(p.reshape(-1))
@@ -158,6 +176,134 @@ class AdjointEnergy:
             torch.cuda.current_stream().synchronize()
         out = self._out_host.numpy()
         return float(out[0]), out[1:1 + self.n_params].reshape(shape).copy()
+
+
+# ---- CTA-resident evaluation (csrc/tqb_vqe.cu) ---------------------------------------------------------------------
+_PAULI_ROT = {"rx": "X", "ry": "Y", "rz": "Z", "rxx": "XX", "ryy": "YY", "rzz": "ZZ"}
+_SQ = 2 ** -0.5
+_FIXED_1Q = {
+    "h": np.array([[_SQ, _SQ], [_SQ, -_SQ]], dtype=np.complex128),
+    "x": np.array([[0, 1], [1, 0]], dtype=np.complex128),
+    "s": np.array([[1, 0], [0, 1j]], dtype=np.complex128),
+    "sdg": np.array([[1, 0], [0, -1j]], dtype=np.complex128),
+}   # exactly the fixed 1-qubit ops the reference engine executes (engine.py:52-374; y / z / t are silently skipped there:
+    # templates with other names keep the AdjointEnergy path, which mirrors that)
+_FIXED_2Q = {   # matrix index = 2 * (first qubit) + (second qubit), as the reference's 4x4 gates (kernels/gates.py)
+    "cx": np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128),
+    "cz": np.diag([1, 1, 1, -1]).astype(np.complex128),
+    "swap": np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.complex128),
+}
+
+
+class ResidentVQE:
+    """Energy + adjoint gradient of a template circuit for MANY parameter vectors in one launch: one shared-memory-resident
+    CTA per vector walks forward circuit, H|psi>, <psi|H|psi> and the reverse sweep (csrc/tqb_vqe.cu).  n <= 12 qubits,
+    complex128; ops: rx ry rz rxx ryy rzz with ``Param`` or fixed angles, h x s sdg cx cz swap.  Same numbers as
+    ``AdjointEnergy`` (1e-10), which routes here when the template qualifies."""
+
+    MAX_QUBITS = 12
+
+    @classmethod
+    def supports(cls, n: int, template: Sequence[Sequence[Any]], dtype: torch.dtype = torch.complex128) -> bool:
+        if n > cls.MAX_QUBITS or n < 1 or dtype != torch.complex128:
+            return False
+        for op in template:
+            nm = op[0]
+            if nm == "measure_z":
+                continue
+            if nm in _PAULI_ROT:
+                continue
+            if nm in _FIXED_1Q or nm in _FIXED_2Q:
+                if any(isinstance(a, Param) for a in op):
+                    return False
+                continue
+            return False
+        return True
+
+    def __init__(self, n: int, template: Sequence[Sequence[Any]], ham: PauliSum, *, device: str | torch.device = "cuda") -> None:
+        if not self.supports(n, template):
+            raise NotImplementedError("template outside the resident kernel's op set (or n > 12)")
+        self.n = int(n)
+        self.device = torch.device(device)
+        _lib.ensure_device(self.device.index or 0)
+        self.n_params = 1 + max([a.index for op in template for a in op if isinstance(a, Param)], default=-1)
+        ops = []
+        mats: List[np.ndarray] = []
+        moff = 0
+        bit = lambda q: self.n - 1 - int(q)   # noqa: E731  (qubit q = index bit n-1-q)
+        for op in template:
+            nm = op[0]
+            if nm == "measure_z":
+                continue
+            rec = np.zeros((), dtype=_lib.VQE_OP_DTYPE)
+            if nm in _PAULI_ROT:
+                ps = _PAULI_ROT[nm]
+                x = z = 0
+                for c, q in zip(ps, op[1:1 + len(ps)]):
+                    if c in "XY":
+                        x |= 1 << bit(q)
+                    if c in "YZ":
+                        z |= 1 << bit(q)
+                a = op[1 + len(ps)]
+                rec["kind"], rec["xmask"], rec["zmask"] = 0, x, z
+                if isinstance(a, Param):
+                    rec["param"], rec["scale"] = a.index, a.scale
+                else:
+                    rec["param"], rec["scale"] = -1, float(a)
+            elif nm in _FIXED_1Q:
+                rec["kind"], rec["param"], rec["bit0"], rec["mat_off"] = 1, -1, bit(op[1]), moff
+                mats.append(_FIXED_1Q[nm].reshape(-1))
+                moff += 4
+            else:
+                if int(op[1]) == int(op[2]):
+                    continue   # apply_2q_statevector returns its input for q0 == q1 (statevector.py:46-47)
+                rec["kind"], rec["param"], rec["bit0"], rec["bit1"], rec["mat_off"] = 2, -1, bit(op[1]), bit(op[2]), moff
+                mats.append(_FIXED_2Q[nm].reshape(-1))
+                moff += 16
+            ops.append(rec)
+        self._ops = torch.from_numpy(np.array(ops, dtype=_lib.VQE_OP_DTYPE).view(np.uint8).reshape(-1).copy()).to(self.device) if ops else \
+            torch.zeros(40, dtype=torch.uint8, device=self.device)
+        self._n_ops = len(ops)
+        m = np.concatenate(mats) if mats else np.zeros(1, dtype=np.complex128)
+        self._mats = torch.from_numpy(m.view(np.float64).copy()).to(self.device)
+        self._hx = torch.from_numpy(ham.group_x.astype(np.uint32).view(np.int32).copy()).to(self.device)
+        self._hp = torch.from_numpy(ham.group_ptr.astype(np.int32)).to(self.device)
+        self._hz = torch.from_numpy(ham.term_z.astype(np.uint32).view(np.int32).copy()).to(self.device)
+        self._hc = torch.from_numpy(ham.term_coef.view(np.float64).copy()).to(self.device)
+        self._ng = ham.n_groups
+        self._host = None
+
+    def energy_and_grad_batch(self, params: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """params [B, n_params] -> (energies [B], gradients [B, n_params]); one kernel launch."""
+        p = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1, max(self.n_params, 1)))
+        B = p.shape[0]
+        if self._host is None or self._host[0].shape[0] < B:
+            self._host = (torch.empty((B, max(self.n_params, 1)), dtype=torch.float64).pin_memory(),
+                          torch.empty((B, 1 + self.n_params), dtype=torch.float64).pin_memory(),
+                          torch.empty((B, max(self.n_params, 1)), dtype=torch.float64, device=self.device),
+                          torch.empty((B, 1 + self.n_params), dtype=torch.float64, device=self.device))
+        hp, ho, dp, do = self._host
+        hp.numpy()[:B] = p
+        with torch.cuda.device(self.device):
+            # few vectors: the kernel reads the parameters from and writes the result to PINNED HOST memory directly
+            # (unified addressing; a few hundred bytes over PCIe) -- no copy calls on the latency path of an optimiser loop
+            zero_copy = B <= 64
+            if not zero_copy:
+                dp[:B].copy_(hp[:B], non_blocking=True)
+            _lib.check(_lib.load().tqb_vqe_resident(self.n, self._ops.data_ptr(), self._n_ops, self._mats.data_ptr(), self._hx.data_ptr(),
+                                                    self._hp.data_ptr(), self._ng, self._hz.data_ptr(), self._hc.data_ptr(),
+                                                    (hp if zero_copy else dp).data_ptr(), self.n_params, B,
+                                                    (ho if zero_copy else do).data_ptr(), _lib.current_stream_ptr(self.device)))
+            if not zero_copy:
+                ho[:B].copy_(do[:B], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        out = ho[:B].numpy()
+        return out[:, 0].copy(), out[:, 1:1 + self.n_params].copy()
+
+    def energy_and_grad(self, params: Sequence[float]) -> Tuple[float, np.ndarray]:
+        p = np.asarray(params, dtype=np.float64)
+        e, g = self.energy_and_grad_batch(p.reshape(1, -1))
+        return float(e[0]), g[0].reshape(p.shape)
 
 
 def tfim_hamiltonian(n: int, Jx: float = 1.0, h: float = -1.0) -> PauliSum:
