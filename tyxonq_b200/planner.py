@@ -35,6 +35,7 @@ class TileConfig:
     max_gates: int = 384
     rot_layers: int = 4   # longest rotation-form chain (4 needs the 128-thread kernel variant for complex128)
     max_work: int = 0     # cap on the non-diagonal gates (1-qubit layers after fusion) of one pass; 0 = no cap
+    balance: int = 0      # target number of non-diagonal gates per pass (0 = off): low-bits-only gates beyond it wait
 
     @property
     def h(self) -> int:
@@ -101,8 +102,9 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
     max_gates = tile.max_gates
     max_work = tile.max_work or (1 << 30)
 
-    def select(start: int, window: int) -> Tuple[List[int], int, int, int]:
-        """window < 0: budget mode (i); else only gates whose needs lie inside ``window`` run.  Returns
+    def select(start: int, window: int, low_quota: int = 1 << 30) -> Tuple[List[int], int, int, int]:
+        """window < 0: budget mode (i); else only gates whose needs lie inside ``window`` run.  ``low_quota``: how many
+        gates that need NO high tile bit (they can run in any pass) may join; the others wait.  Returns
         (chosen, H, number of high bits used, number of non-diagonal gates chosen)."""
         H = 0
         nH = 0
@@ -127,7 +129,12 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
             elif mk & blocked:
                 blocked |= mk
                 blocked_nd |= mk
+            elif not needs[i] and low_quota <= 0:
+                blocked |= mk          # a low-bits-only gate over the quota: it waits for a pass with room
+                blocked_nd |= mk
             else:
+                if not needs[i]:
+                    low_quota -= 1
                 need = needs[i] & ~H
                 if budget:
                     cnt = need.bit_count()
@@ -155,8 +162,8 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
         chosen, H, nH, nd = select(first, -1)
         # windows of h contiguous high bits around the oldest pending non-diagonal gate
         j = first
-        while j < N and (done[j] or is_diag[j]):
-            j += 1
+        while j < N and (done[j] or is_diag[j] or (tile.balance > 0 and not needs[j])):
+            j += 1   # (balanced mode: the oldest pending gate that NEEDS a window; low-bits-only gates fit any pass)
         if j < N and needs[j] and h >= 2 and n - tile.L > h:
             nb = needs[j]
             lo_need = (nb & -nb).bit_length() - 1
@@ -166,6 +173,31 @@ def schedule(gates: Sequence[LGate], n: int, tile: TileConfig) -> List[Tuple[Lis
                 c2, H2, nH2, nd2 = select(first, window)
                 if nd2 > nd:
                     chosen, H, nH, nd = c2, H2, nH2, nd2
+        if tile.balance > 0 and nd > tile.balance:
+            # Balance (tile.balance = target number of non-diagonal gates per pass).  Gates on the always-local low bits
+            # can run in ANY pass; taking all of them as soon as they are ready piles the low 10 bits of several layers of
+            # a ladder circuit into one shared-memory-bound pass while the passes around it wait for HBM.  Re-select with
+            # the gates that need the window first and only as many low-bits-only gates as fit the target: the rest ride
+            # in later passes (their dependants lag by one period, nothing is lost).
+            best = None
+            cands = [(-1,)]
+            jj = first
+            while jj < N and (done[jj] or is_diag[jj] or not needs[jj]):
+                jj += 1
+            if jj < N and needs[jj] and h >= 2 and n - tile.L > h:
+                nb2 = needs[jj]
+                lo2 = (nb2 & -nb2).bit_length() - 1
+                hi2 = nb2.bit_length() - 1
+                cands += [(((1 << h) - 1) << st_,) for st_ in range(max(tile.L, hi2 - h + 1), min(lo2, n - h) + 1)]
+            for (w_,) in cands:
+                c0, H0, nH0, nd0 = select(first, w_, 0)          # window gates only
+                quota = max(0, tile.balance - nd0)
+                c1, H1, nH1, nd1 = select(first, w_, quota) if quota else (c0, H0, nH0, nd0)
+                score = (min(nd1, tile.balance), nd0)
+                if best is None or score > best[0]:
+                    best = (score, c1, H1, nH1, nd1)
+            if best is not None and best[4] > 0:
+                _, chosen, H, nH, nd = best
         for c in chosen:
             done[c] = True
         remaining -= len(chosen)
@@ -184,7 +216,7 @@ def _prepare(gates: Sequence[LGate], n: int, tile: TileConfig, chain: Optional[b
     """Effective tile, the pass schedule (diagonals sunk to their consumers when chains are grouped) and the chain switch."""
     m_eff = min(tile.m, n)
     tile = TileConfig(m=m_eff, L=min(tile.L, m_eff), threads=tile.threads, ctas_per_sm=tile.ctas_per_sm,
-                      max_gates=tile.max_gates, rot_layers=tile.rot_layers, max_work=tile.max_work)
+                      max_gates=tile.max_gates, rot_layers=tile.rot_layers, max_work=tile.max_work, balance=tile.balance)
     sched = schedule(gates, n, tile)
     if chain is None:
         chain = bool(getattr(gates, "chain_after_schedule", False))
