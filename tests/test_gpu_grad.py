@@ -139,6 +139,19 @@ def test_ucc_h2o_shape_energy_grad(cuda_device):
     assert abs(e4 - e3) < 1e-12 and np.abs(g4 - g3).max() < 1e-10
 
 
+def test_ucc_batched_replicas(cuda_device):
+    """energy_and_grad_batch: concurrent replicas (own buffers, stream, CUDA graph each) give the single-evaluation numbers."""
+    from tyxonq_b200 import ucc
+    n, nes, ex_ops, pids, i1, i2 = _ucc_problem(4, 4)
+    sv = ucc.UCCStatevector(n, nes, ex_ops, pids, ucc.hamiltonian_from_integral(i1, i2), device=cuda_device)
+    rng = np.random.default_rng(3)
+    P_ = rng.uniform(-0.5, 0.5, (11, max(pids) + 1))
+    es, gs = sv.energy_and_grad_batch(P_, replicas=4)
+    for b in (0, 3, 10):
+        e, g = sv.energy_and_grad(P_[b])
+        assert abs(es[b] - e) < 1e-12 and np.abs(gs[b] - g).max() < 1e-12
+
+
 def test_b200_backend_value_and_grad(cuda_device):
     """Seam B3: tq.set_backend(B200Backend()) style use -- arrays live on the device, value_and_grad runs the
     adjoint sweep (reference pytorch_backend.py:446-564 returns (float, ndarray))."""

@@ -25,3 +25,23 @@ for B in (148, 1024, 8192):
     for _ in range(5):
         t0 = time.perf_counter(); eb, gb = v.energy_and_grad_batch(pb); ts.append(time.perf_counter() - t0)
     print(f"resident, batch {B}: {B / np.median(ts):.0f} evals/s ({1e3 * np.median(ts):.2f} ms per launch incl. H2D/D2H)")
+
+# H2O-shaped UCCSD (config 2): one evaluation per call and concurrent replicas
+from tyxonq_b200 import ucc
+i1, i2 = ucc.random_integral(7, 2077)
+ex_ops, pids = ucc.uccsd_ex_ops(5, 2)
+sv = ucc.UCCStatevector(14, (5, 5), ex_ops, pids, ucc.hamiltonian_from_integral(i1, i2), device=dev)
+np.random.seed(2077)
+p = np.random.rand(75) - 0.5
+for _ in range(3): sv.energy_and_grad(p)
+ts = []
+for _ in range(5):
+    t0 = time.perf_counter()
+    for _ in range(20): e, g = sv.energy_and_grad(p)
+    ts.append((time.perf_counter() - t0) / 20)
+print(f"H2O-shaped UCCSD, one evaluation per call: {1 / np.median(ts):.0f} evals/s, E = {e:.12f}")
+pb = np.random.default_rng(5).uniform(-0.5, 0.5, (64, 75))
+for R in (4, 8, 9):
+    sv.energy_and_grad_batch(pb[:R], replicas=R)
+    t0 = time.perf_counter(); es, gs = sv.energy_and_grad_batch(pb, replicas=R); dt = time.perf_counter() - t0
+    print(f"H2O-shaped UCCSD, {R} concurrent replicas: {64 / dt:.0f} evals/s")

@@ -331,7 +331,7 @@ class UCCStatevector:
         self._out[0:1].copy_(self._e[0:1])
         self._out[1:1 + self.n_params].copy_(self._gout[: self.n_params])
 
-    def energy_and_grad(self, params: Sequence[float], *, graph: bool = True) -> Tuple[float, np.ndarray]:
+    def energy_and_grad(self, params: Sequence[float], *, graph: bool = True, _sync: bool = True) -> Tuple[float, np.ndarray]:
         """energy_and_grad_statevector (statevector_ops.py:203-244) with an analytic adjoint gradient.
         ``graph``: replay the evaluation as one CUDA graph (captured on the second call) instead of ~300
         separate launches; new parameters only rewrite the pinned matrix buffers."""
@@ -366,6 +366,40 @@ class UCCStatevector:
                 self._enqueue()
             self._calls += 1
             self._out_host.copy_(self._out, non_blocking=True)
+            if not _sync:
+                return None  # type: ignore[return-value]   (energy_and_grad_batch collects after every replica is launched)
             torch.cuda.current_stream().synchronize()
         out = self._out_host.numpy()
         return float(out[0]), out[1:1 + self.n_params].copy()
+
+    def energy_and_grad_batch(self, params: np.ndarray, *, replicas: int = 8) -> Tuple[np.ndarray, np.ndarray]:
+        """Many parameter vectors ([B, n_params] -> energies [B], gradients [B, n_params]).  An evaluation of a small
+        molecule is a chain of ~300 dependent steps on 16 CTAs (latency, not throughput), so ``replicas`` independent
+        evaluations run CONCURRENTLY: each replica has its own state buffers, stream and CUDA graph, the persistent sweep
+        kernels of different replicas share the device (16 of 148 SMs each)."""
+        p = np.asarray(params, dtype=np.float64).reshape(-1, max(self.n_params, 1))
+        B = p.shape[0]
+        R = max(1, min(int(replicas), B))
+        if not hasattr(self, "_replicas") or len(self._replicas) < R:
+            self._replicas = [self] + [UCCStatevector(self.n, self.n_elec_s, self.ex_ops, self.param_ids, self.ham, mode=self.mode,
+                                                     device=self.device, dtype=self.dtype, tile=self.tile) for _ in range(R - 1)]
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(R)]
+            for r, (rep, st) in enumerate(zip(self._replicas, self._streams)):   # warm up + capture each replica's graph on ITS stream
+                with torch.cuda.stream(st):
+                    rep.energy_and_grad(p[0])
+                    rep.energy_and_grad(p[0])
+        es = np.empty(B)
+        gs = np.empty((B, self.n_params))
+        with torch.cuda.device(self.device):
+            for b0 in range(0, B, R):
+                live = []
+                for r in range(min(R, B - b0)):
+                    with torch.cuda.stream(self._streams[r]):
+                        self._replicas[r].energy_and_grad(p[b0 + r], _sync=False)
+                    live.append(r)
+                for r in live:
+                    self._streams[r].synchronize()
+                    out = self._replicas[r]._out_host.numpy()
+                    es[b0 + r] = out[0]
+                    gs[b0 + r] = out[1:1 + self.n_params]
+        return es, gs
