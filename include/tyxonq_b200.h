@@ -226,6 +226,15 @@ int tqb_grad_pair(const void *bra, const void *ket, int n, int dtype, const tqb_
 int tqb_grad_dense(const void *bra, const void *ket, int n, int dtype, int k, const int *bits,
                    const double *gen_host, double scale, double *out_dev, int slot, void *stream);
 
+/* Single-qubit transition matrices of a (bra, ket) pair for up to 6 index bits in ONE read of both states:
+ * out_dev[8 i .. 8 i + 8) = (re, im) of T[0][0], T[0][1], T[1][0], T[1][1] for bit i of the call, T[a][b] = sum over the other
+ * bits of conj(bra[.., a, ..]) ket[.., b, ..].  <bra| A_q |ket> = sum_ab A[a][b] T_q[a][b] for any single-qubit operator A:
+ * one call gives the adjoint gradient of every single-qubit gate acting on those qubits in a layer (the reverse sweep of
+ * civector_ops.py:141-200 layer by layer instead of gate by gate).  The bits of interest must be tile bits: tile = the L
+ * lowest index bits + hb[] (m <= 12 bits in all), tile_bits[] = their tile-local positions.  out_dev is overwritten.   */
+int tqb_transition_1q(const void *bra, const void *ket, int n, int dtype, int m, int L, const int8_t *hb,
+                      const int8_t *tile_bits, int n_bits, double *out_dev, void *stream);
+
 /* Whole sweeps of PAIR rotations on a SMALL state (2^n amplitudes resident in L2) in ONE launch: a
  * persistent grid walks the steps with a grid-wide barrier between them instead of one launch per gate.
  * Step j rotates the pair (pattern A, pattern B) of its k target bits by [[c, -s], [s, c]] where the

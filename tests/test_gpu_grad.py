@@ -258,3 +258,45 @@ def test_resident_vqe_kernel(cuda_device):
     assert np.abs(g - O.central_fd_gradient(energy, th, 1e-6)).max() < 1e-7
     e2, g2 = ae.energy_and_grad(th, resident=False)
     assert abs(e - e2) < 1e-10 and np.abs(g - g2).max() < 1e-9
+
+
+def test_layered_adjoint_matches_per_gate_path(cuda_device):
+    """energy_and_grad_layered (tqb_transition_1q: all single-qubit gradients of a layer from one pair of states, fused
+    un-apply passes between layers) against the per-gate adjoint path and central differences of the oracle: the
+    hardware-efficient ansatz (rz.rx runs + cx ladder), the RY ansatz, a circuit with parametrised two-qubit gates and
+    scaled / shared parameters; complex128 at n = 14 (one tile) and n = 16 (streaming tiles), complex64."""
+    import torch
+    from tyxonq_b200.pauli import PauliSum
+    from tyxonq_b200.vqe import AdjointEnergy, Param
+    rng = np.random.default_rng(21)
+
+    def hea_template(n, layers):
+        ops = [("h", q) for q in range(n)]
+        k = 0
+        for _ in range(layers):
+            ops += [("cx", q, q + 1) for q in range(n - 1)]
+            for q in range(n):
+                ops.append(("rz", q, Param(k))); k += 1
+                ops.append(("rx", q, Param(k))); k += 1
+        return ops, k
+
+    for n, dt, tol in ((14, torch.complex128, 1e-9), (16, torch.complex128, 1e-9), (15, torch.complex64, 2e-4)):
+        tmpl, npar = hea_template(n, 2)
+        ham = PauliSum.from_pauli_list(n, [(0.8, [("Z", i), ("Z", i + 1)]) for i in range(n - 1)] + [(-0.6, [("X", i)]) for i in range(n)]
+                                       + [(0.3, [("Y", 0), ("Y", n - 1)])])
+        ae = AdjointEnergy(n, tmpl, ham, device=cuda_device, dtype=dt)
+        th = rng.uniform(-1.5, 1.5, npar)
+        e1, g1 = ae.energy_and_grad_layered(th)
+        e2, g2 = ae.energy_and_grad(th, resident=False) if n < AdjointEnergy.LAYERED_MIN_QUBITS else (e1, g1)
+        assert abs(e1 - e2) < tol * 10 and np.abs(g1 - g2).max() < tol * 10, (n, dt, abs(e1 - e2), np.abs(g1 - g2).max())
+        assert np.abs(g1).max() > 1e-3
+    # two-qubit parametrised gates, scaled and shared parameters, fixed gates in between
+    n = 12
+    tmpl = [("h", q) for q in range(n)] + [("rzz", q, q + 1, Param(0, 2.0)) for q in range(0, n - 1, 2)] + [("rx", q, Param(1)) for q in range(n)] + \
+           [("rxx", 1, 2, Param(2)), ("cx", 3, 4), ("ry", 4, Param(3)), ("rz", 4, Param(4, -1.0)), ("s", 5), ("rx", 5, Param(4)), ("ryy", 6, 9, Param(5))]
+    ham = PauliSum.from_pauli_list(n, [(1.0, [("Z", i), ("Z", (i + 3) % n)]) for i in range(n)] + [(0.5, [("X", 4)]), (0.25, [("Y", 5), ("Z", 6)])])
+    ae = AdjointEnergy(n, tmpl, ham, device=cuda_device)
+    th = rng.uniform(-1, 1, 6)
+    e1, g1 = ae.energy_and_grad_layered(th)
+    e2, g2 = ae.energy_and_grad(th, resident=False)
+    assert abs(e1 - e2) < 1e-10 and np.abs(g1 - g2).max() < 1e-9

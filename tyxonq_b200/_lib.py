@@ -83,6 +83,7 @@ SIGNATURES = {
     "tqb_expect_pauli_tiled": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "tqb_apply_pauli_sum": (_i, [_vp, _vp, _i, _i64, _i, _u64, _vp, _vp, _i, _vp, _vp, _vp]),
     "tqb_inner": (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp]),
+    "tqb_transition_1q": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "tqb_grad_pair": (_i, [_vp, _vp, _i, _i, _vp, _d, _vp, _i, _vp]),
     "tqb_grad_dense": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _d, _vp, _i, _vp]),
     "tqb_pair_sweep": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),

@@ -423,6 +423,91 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
   block_reduce<2>(acc, red, partial + (((size_t)blockIdx.y * pt.n_layouts + pt.layout) * gridDim.x + blockIdx.x) * 2);
 }
 
+// ---- single-qubit transition matrices of a (bra, ket) pair -------------------------------------------------------
+// T_q[a][b] = sum over the other bits of conj(bra[.., a, ..]) * ket[.., b, ..]  for up to 6 index bits q per launch: every
+// single-qubit operator A on qubit q has <bra| A_q |ket> = sum_ab A[a][b] T_q[a][b], so ONE evaluation of T_q yields the adjoint
+// gradient of every gate in a layer of single-qubit gates on q (generators conjugated through the later gates of the run on
+// the host) -- instead of one full read of both states per parameter (grad_dense_kernel).  Tile-staged like the Pauli sums:
+// both states' tiles in shared memory, the bits of interest are tile bits.
+struct Trans1q {
+  int n, m, L, h, nb;
+  int8_t hb[16];
+  int8_t tb[8];   // tile-local positions of the bits of interest
+};
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(RT, 2) transition_1q_kernel(const cplx<T> *__restrict__ bra, const cplx<T> *__restrict__ ket, Trans1q tq,
+                                                              double *out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[RT / 32][NB * 8];
+  const int m = tq.m, L = tq.L, h = tq.h;
+  const uint32_t nel = 1u << m;
+  cplx<T> *kt = reinterpret_cast<cplx<T> *>(smem_raw);
+  cplx<T> *bt = kt + nel;
+  uint64_t *roff = reinterpret_cast<uint64_t *>(bt + nel);
+  const int tid = threadIdx.x;
+  for (uint32_t j = tid; j < (1u << h); j += RT) {
+    uint64_t o = 0;
+    for (int i = 0; i < h; ++i) o |= (uint64_t)((j >> i) & 1u) << tq.hb[i];
+    roff[j] = o;
+  }
+  uint32_t pos[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) pos[k] = (uint32_t)tq.tb[k < tq.nb ? k : 0];
+  double acc[NB][8];
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[k][i] = 0.0;
+  const uint64_t ntiles = 1ull << (tq.n - m);
+  constexpr int V = 16 / (int)sizeof(cplx<T>);
+  for (uint64_t tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
+    uint64_t base = tt << L;
+    for (int j = 0; j < h; ++j) {
+      const uint32_t p = (uint32_t)tq.hb[j];
+      base = ((base >> p) << (p + 1u)) | (base & ((1ull << p) - 1ull));
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < nel / V; i += RT) {
+      const uint32_t e = i * V;
+      const uint64_t idx = base | roff[e >> L] | (uint64_t)(e & ((1u << L) - 1u));
+      *reinterpret_cast<cvec<T, V> *>(kt + e) = *reinterpret_cast<const cvec<T, V> *>(ket + idx);
+      *reinterpret_cast<cvec<T, V> *>(bt + e) = *reinterpret_cast<const cvec<T, V> *>(bra + idx);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      if (k >= tq.nb) break;
+      const uint32_t low = (1u << pos[k]) - 1u;
+      for (uint32_t c = tid; c < (nel >> 1); c += RT) {
+        const uint32_t e0 = ((c & ~low) << 1) | (c & low), e1 = e0 | (1u << pos[k]);
+        const cplx<T> b0 = bt[e0], b1 = bt[e1], k0 = kt[e0], k1 = kt[e1];
+        // conj(b) * k
+        acc[k][0] += (double)b0.x * k0.x + (double)b0.y * k0.y;  acc[k][1] += (double)b0.x * k0.y - (double)b0.y * k0.x;   // T00
+        acc[k][2] += (double)b0.x * k1.x + (double)b0.y * k1.y;  acc[k][3] += (double)b0.x * k1.y - (double)b0.y * k1.x;   // T01
+        acc[k][4] += (double)b1.x * k0.x + (double)b1.y * k0.y;  acc[k][5] += (double)b1.x * k0.y - (double)b1.y * k0.x;   // T10
+        acc[k][6] += (double)b1.x * k1.x + (double)b1.y * k1.y;  acc[k][7] += (double)b1.x * k1.y - (double)b1.y * k1.x;   // T11
+      }
+    }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < NB; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double x = acc[k][i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) red[warp][k * 8 + i] = x;
+    }
+  __syncthreads();
+  if (tid < tq.nb * 8) {
+    double s2 = 0.0;
+    for (int w = 0; w < RT / 32; ++w) s2 += red[w][tid];
+    atomicAdd(out + tid, s2);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(RT) inner_kernel(const cplx<T> *__restrict__ a, const cplx<T> *__restrict__ b, Seg sg,
                                                    double *partial) {
@@ -1001,6 +1086,47 @@ int tqb_apply_pauli_sum(const void *state, void *out, int n, int64_t batch, int 
                [&] { apply_pauli_kernel<float><<<grid, RT, 0, st>>>(CF(state), MF(out), n, global_base, group_x, group_ptr, n_groups, term_z, term_coef); }))
     return -1;
   TQB_CHECK_LAUNCH("apply_pauli_kernel");
+  return 0;
+}
+
+int tqb_transition_1q(const void *bra, const void *ket, int n, int dtype, int m, int L, const int8_t *hb, const int8_t *tile_bits,
+                      int n_bits, double *out_dev, void *stream) {
+  TQB_REQUIRE(bra && ket && hb && tile_bits && out_dev && n >= 1 && n < 48 && m >= 1 && m <= n && m <= 12 && L >= 0 && L <= m && m - L <= 16 &&
+                  n_bits >= 1 && n_bits <= 6, "tqb_transition_1q: bad arguments (m <= 12, at most 6 bits per call)");
+  TQB_REQUIRE(dtype == TQB_C128 || dtype == TQB_C64, "tqb_transition_1q: bad dtype");
+  Workspace *ws = workspace();
+  if (!ws) return -1;
+  Trans1q tq;
+  tq.n = n; tq.m = m; tq.L = L; tq.h = m - L; tq.nb = n_bits;
+  int prev = L - 1;
+  for (int i = 0; i < 16; ++i) {
+    tq.hb[i] = i < tq.h ? hb[i] : 0;
+    if (i < tq.h) {
+      TQB_REQUIRE(hb[i] > prev && hb[i] < n, "tqb_transition_1q: hb must be ascending, >= L and < n");
+      prev = hb[i];
+    }
+  }
+  for (int i = 0; i < 8; ++i) {
+    tq.tb[i] = i < n_bits ? tile_bits[i] : 0;
+    if (i < n_bits) TQB_REQUIRE(tile_bits[i] >= 0 && tile_bits[i] < m, "tqb_transition_1q: bit of interest outside the tile");
+  }
+  const int es = dtype == TQB_C128 ? 16 : 8;
+  const size_t smem = 2 * ((size_t)es << m) + ((size_t)8 << tq.h) + 16;
+  TQB_REQUIRE(smem + 4096 <= (size_t)ws->max_smem_optin, "tqb_transition_1q: tiles exceed shared memory");
+  cudaStream_t st = as_stream(stream);
+  TQB_CHECK_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)n_bits * 8 * sizeof(double), st));
+  const unsigned long long tiles = 1ull << (n - m);
+  unsigned long long grid = (unsigned long long)ws->sm_count * 2;
+  if (grid > tiles) grid = tiles;
+#define TQB_TR(T, PTR)                                                                                                              \
+  do {                                                                                                                              \
+    auto kern = transition_1q_kernel<T, 6>;                                                                                         \
+    TQB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->max_smem_optin - 4096));             \
+    kern<<<(unsigned)grid, RT, smem, st>>>(PTR(bra), PTR(ket), tq, out_dev);                                                        \
+  } while (0)
+  if (dtype == TQB_C128) TQB_TR(double, CD); else TQB_TR(float, CF);
+#undef TQB_TR
+  TQB_CHECK_LAUNCH("transition_1q_kernel");
   return 0;
 }
 
