@@ -63,6 +63,43 @@ def test_state_autograd_kat(cuda_device):
     assert abs(float(z) - np.cos(0.5)) < 1e-12 and abs(float(th.grad) + np.sin(0.5)) < 1e-10
 
 
+def test_state_autograd_layered_backward(cuda_device, monkeypatch):
+    """torch backward of Circuit.state at n = 13: the layer-by-layer sweep (autograd.layered_sweep, default from 12 qubits
+    on) gives the gradients of the per-gate sweep, and both agree with central differences of the oracle."""
+    import torch
+    from tyxonq_b200 import StatevectorEngine
+    from tyxonq_b200 import autograd as A
+    n = 13
+    rng = np.random.default_rng(5)
+    theta0 = rng.uniform(-1, 1, 8)
+    w = rng.normal(size=1 << n)
+    cvec = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+
+    def ops_of(t):
+        ops = [("h", q) for q in range(n)]
+        ops += [("rz", q, t[q % 4]) for q in range(n)] + [("rx", q, t[4 + q % 3] * 0.5) for q in range(n)]
+        ops += [("cx", q, q + 1) for q in range(n - 1)] + [("rzz", 0, n - 1, t[7])] + [("ry", q, t[(q + 1) % 8]) for q in range(0, n, 2)]
+        ops += [("s", 3), ("rz", 3, t[2]), ("rxx", 5, 11, t[6] * -1.5), ("x", 6), ("rx", 6, t[0])]
+        return ops
+
+    def loss_np(t):
+        psi, _ = O.evolve_ops(n, ops_of([float(x) for x in t]))
+        return float(np.sum(w * np.abs(psi) ** 2) + np.real(np.vdot(cvec, psi)))
+
+    grads = {}
+    for name, thr in (("layered", 12), ("per_gate", 64)):
+        monkeypatch.setattr(A, "LAYERED_MIN_QUBITS", thr)
+        theta = torch.tensor(theta0, dtype=torch.float64, requires_grad=True)
+        psi = StatevectorEngine("pytorch", device=cuda_device).state(FakeCircuit(n, ops_of(theta)))
+        loss = torch.sum(torch.from_numpy(w) * psi.abs() ** 2) + torch.real(torch.sum(torch.from_numpy(cvec).conj() * psi))
+        loss.backward()
+        assert abs(float(loss) - loss_np(theta0)) < 1e-9
+        grads[name] = theta.grad.numpy().copy()
+    assert np.abs(grads["layered"] - grads["per_gate"]).max() < 1e-10
+    fd = O.central_fd_gradient(loss_np, theta0, 1e-6)
+    assert np.abs(grads["layered"] - fd).max() < 1e-6 * max(1.0, np.abs(fd).max())
+
+
 def _ucc_problem(nao, ne):
     from tyxonq_b200 import ucc
     n = 2 * nao

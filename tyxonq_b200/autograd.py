@@ -26,6 +26,9 @@ from .gates import CHAIN, DENSE, DIAG, GEN, MUX, PAIR, SWAP, LGate, lower_op, _t
 from .planner import compile_program, default_tile
 
 
+LAYERED_MIN_QUBITS = 12   # from here on the backward pass sweeps layer by layer (layered_sweep)
+
+
 def has_grad_params(circuit: Any) -> bool:
     for op in getattr(circuit, "ops", []):
         if isinstance(op, (list, tuple)):
@@ -61,6 +64,123 @@ def grad_dense(bra: torch.Tensor, ket: torch.Tensor, bits: Sequence[int], gen: n
     with torch.cuda.device(bra.device):
         _lib.check(_lib.load().tqb_grad_dense(ptr_b, ptr_k, n, dt, k, C.cast(b_arr, C.c_void_p), g.ctypes.data,
                                               float(scale), out.data_ptr(), int(slot), stream))
+
+
+# ---- layered reverse sweep ---------------------------------------------------------------------------------------
+def _mat1q(g: LGate) -> np.ndarray:
+    d = np.asarray(g.data, dtype=np.complex128)
+    if g.kind == DENSE:
+        return d.reshape(2, 2)
+    if g.kind == DIAG:
+        return np.diag(d.reshape(2))
+    if g.kind == SWAP:
+        return np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    raise NotImplementedError("single-qubit gate kind")
+
+
+def transition_1q(kb: torch.Tensor, bits: Sequence[int]) -> dict:
+    """{index bit: T (2x2 complex)} with T[a][b] = sum_rest conj(bra[a, rest]) ket[b, rest] for kb = [ket, bra]:
+    tqb_transition_1q, up to 6 bits per read of both states (tile = low bits + the bits of interest)."""
+    ptr, n, _, dt, stream = P._prep(kb[0])
+    itemsize = kb.element_size()
+    m = min(n, 11 if itemsize == 16 else 12)
+    L = m if m == n else min(m, 5 if itemsize == 16 else 6)
+    lib = _lib.load()
+    todo = sorted(set(int(b) for b in bits))
+    low = [b for b in todo if b < L]
+    high = [b for b in todo if b >= L]
+    calls = []
+    while low or high:
+        take_h = high[: min(6, m - L)]
+        high = high[len(take_h):]
+        take_l = low[: 6 - len(take_h)]
+        low = low[len(take_l):]
+        hb = list(take_h)
+        f = L
+        while len(hb) < m - L:        # fill the tile with the lowest unused high bits
+            if f not in hb:
+                hb.append(f)
+            f += 1
+        hb.sort()
+        pos = {b: L + j for j, b in enumerate(hb)}
+        calls.append((hb, take_l + take_h, [b if b < L else pos[b] for b in take_l + take_h]))
+    res = torch.zeros((max(len(calls), 1), 48), dtype=torch.float64, device=kb.device)
+    with torch.cuda.device(kb.device):
+        for ci, (hb, _, tpos) in enumerate(calls):
+            hb_a = (C.c_int8 * 16)(*(hb + [0] * (16 - len(hb))))
+            tb_a = (C.c_int8 * 8)(*(tpos + [0] * (8 - len(tpos))))
+            _lib.check(lib.tqb_transition_1q(kb[1].data_ptr(), kb[0].data_ptr(), n, dt, m, L, C.cast(hb_a, C.c_void_p),
+                                             C.cast(tb_a, C.c_void_p), len(tpos), res[ci].data_ptr(), stream))
+    host = res.cpu().numpy()
+    out: dict = {}
+    for ci, (_, bs, _) in enumerate(calls):
+        for j, b in enumerate(bs):
+            v = host[ci, 8 * j:8 * j + 8]
+            out[b] = np.array([[v[0] + 1j * v[1], v[2] + 1j * v[3]], [v[4] + 1j * v[5], v[6] + 1j * v[7]]])
+    return out
+
+
+def layered_sweep(kb: torch.Tensor, gates: Sequence[LGate], slots: Sequence[Optional[Tuple[int, float]]], grad: np.ndarray) -> None:
+    """Reverse sweep over kb = [ket, bra] (the states AFTER all gates), layer by layer:
+    grad[slot] += weight * Re <bra| D_k |ket_k> for every gate k with slots[k] = (slot, weight), D_k = (dU_k/dtheta) U_k^+.
+
+    The gate list is cut, from the end, into blocks in which any two gates act on different qubits or are both single-qubit
+    gates on the same qubit.  Inside a block the generator of a gate, conjugated through the LATER single-qubit gates of its
+    own qubit, is still a single-qubit operator A and commutes with everything else in the block, so
+    <bra| D |ket> = sum_ab A[a][b] T_q[a][b] with the transition matrices T_q of the pair AFTER the block (transition_1q).
+    Between blocks both states are un-applied by fused passes on the 2-member batch.  Multi-qubit parametrised gates keep
+    the per-gate reduction (grad_dense)."""
+    from .fuse import fuse
+    ptr, n, _, dt, stream = P._prep(kb[0])
+    itemsize = kb.element_size()
+    blocks: List[List[int]] = []
+    cur: List[int] = []
+    one_q_bits = 0     # bits of single-qubit gates in the current block
+    other_bits = 0     # bits of everything else in it
+    for idx in range(len(gates) - 1, -1, -1):
+        g = gates[idx]
+        is1q = len(g.bits) == 1
+        ok = not (g.mask & other_bits) if is1q else not (g.mask & (other_bits | one_q_bits))
+        if not ok:
+            blocks.append(cur)
+            cur, one_q_bits, other_bits = [], 0, 0
+        cur.append(idx)
+        if is1q:
+            one_q_bits |= g.mask
+        else:
+            other_bits |= g.mask
+    if cur:
+        blocks.append(cur)
+    first_param = min((i for i, r in enumerate(slots) if r is not None), default=len(gates))
+    pending: List[LGate] = []
+    tile2 = default_tile(n, itemsize, 2)
+    for blk in blocks:                      # blk: gate indices in REVERSE order
+        par = [i for i in blk if slots[i] is not None]
+        if par:
+            if pending:                     # un-apply everything after this block: both states are then "after the block"
+                prog2 = compile_program(fuse(list(pending)), n, tile2, itemsize=itemsize)
+                P.DeviceProgram(prog2, kb.device, kb.dtype).run(kb)
+                pending = []
+            need = sorted({int(gates[i].bits[0]) for i in par if len(gates[i].bits) == 1})
+            T = transition_1q(kb, need) if need else {}
+            later: dict = {}                # bit -> product of the later single-qubit gates of that bit
+            for i in blk:                   # reverse order: later gates first
+                g = gates[i]
+                if len(g.bits) == 1:
+                    b = int(g.bits[0])
+                    W = later.get(b, np.eye(2, dtype=np.complex128))
+                    if slots[i] is not None:
+                        D = np.asarray(GEN[g.name], dtype=np.complex128).reshape(2, 2)
+                        A = W @ D @ W.conj().T
+                        grad[slots[i][0]] += slots[i][1] * float(np.real(np.sum(A * T[b])))
+                    later[b] = W @ _mat1q(g)
+                elif slots[i] is not None:  # a parametrised multi-qubit gate, alone on its qubits in the block
+                    out1 = torch.zeros(1, dtype=torch.float64, device=kb.device)
+                    grad_dense(kb[1], kb[0], g.bits, GEN[g.name], slots[i][1], out1, 0)
+                    grad[slots[i][0]] += float(out1.cpu()[0])
+        if min(blk) <= first_param:
+            break                           # nothing left to differentiate
+        pending.extend(dagger(gates[i]) for i in blk)
 
 
 def lower_circuit(circuit: Any, mode: str) -> Tuple[List[LGate], List[torch.Tensor]]:
@@ -139,11 +259,17 @@ class _CircuitState(torch.autograd.Function):
                 P.DeviceProgram(compile_program(pending, n, tile, itemsize=kb.element_size()), dev, dtype).run(kb)
                 pending.clear()
 
-        for g in reversed(gates):
-            if g.param is not None:
-                flush()
-                grad_dense(kb[1], kb[0], _gen_bits(g), GEN[g.name], 1.0, gout, g.param)
-            pending.append(dagger(g))
+        if n >= LAYERED_MIN_QUBITS:
+            # layer by layer: all single-qubit gradients of a layer from one pair of states (layered_sweep)
+            acc = np.zeros(max(nparam, 1))
+            layered_sweep(kb, gates, [None if g.param is None else (g.param, 1.0) for g in gates], acc)
+            gout += torch.from_numpy(acc).to(dev)
+        else:
+            for g in reversed(gates):
+                if g.param is not None:
+                    flush()
+                    grad_dense(kb[1], kb[0], _gen_bits(g), GEN[g.name], 1.0, gout, g.param)
+                pending.append(dagger(g))
         # the remaining un-applies are not needed for the gradient
         res = gout.cpu()
         grads = []

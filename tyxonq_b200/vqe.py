@@ -144,72 +144,12 @@ class AdjointEnergy:
         self._out[1:1 + self.n_params].copy_(self._gout[: self.n_params])
 
     # ---- layered adjoint sweep (large registers) ----------------------------------------------------------------
-    @staticmethod
-    def _mat1q(g: LGate) -> np.ndarray:
-        from .gates import DENSE, DIAG, SWAP
-        d = np.asarray(g.data, dtype=np.complex128)
-        if g.kind == DENSE:
-            return d.reshape(2, 2)
-        if g.kind == DIAG:
-            return np.diag(d.reshape(2))
-        if g.kind == SWAP:
-            return np.array([[0, 1], [1, 0]], dtype=np.complex128)
-        raise NotImplementedError("single-qubit gate kind")
-
-    def _transition_1q(self, bits: Sequence[int]) -> dict:
-        """{index bit: T (2x2 complex)} with T[a][b] = sum_rest conj(bra[a, rest]) ket[b, rest]: tqb_transition_1q, up to 6
-        bits per read of both states (tile = low bits + the bits of interest)."""
-        n = self.n
-        m = min(n, 11 if self.itemsize == 16 else 12)
-        L = min(m, 5 if self.itemsize == 16 else 6)
-        if m == n:
-            L = m
-        lib = _lib.load()
-        kb = self._kb
-        _, _, _, dt, stream = P._prep(kb[0])
-        out: dict = {}
-        todo = sorted(set(int(b) for b in bits))
-        low = [b for b in todo if b < L]
-        high = [b for b in todo if b >= L]
-        calls = []
-        while low or high:
-            take_h = high[: min(6, m - L)]
-            high = high[len(take_h):]
-            take_l = low[: 6 - len(take_h)]
-            low = low[len(take_l):]
-            hb = list(take_h)
-            f = L
-            while len(hb) < m - L:        # fill the tile with the lowest unused high bits
-                if f not in hb:
-                    hb.append(f)
-                f += 1
-            hb.sort()
-            pos = {b: L + j for j, b in enumerate(hb)}
-            calls.append((hb, take_l + take_h, [b if b < L else pos[b] for b in take_l + take_h]))
-        res = torch.zeros((len(calls), 48), dtype=torch.float64, device=self.device)
-        for ci, (hb, _, tpos) in enumerate(calls):
-            hb_a = (C.c_int8 * 16)(*(hb + [0] * (16 - len(hb))))
-            tb_a = (C.c_int8 * 8)(*(tpos + [0] * (8 - len(tpos))))
-            _lib.check(lib.tqb_transition_1q(kb[1].data_ptr(), kb[0].data_ptr(), n, dt, m, L, C.cast(hb_a, C.c_void_p),
-                                             C.cast(tb_a, C.c_void_p), len(tpos), res[ci].data_ptr(), stream))
-        host = res.cpu().numpy()
-        for ci, (_, bs, _) in enumerate(calls):
-            for j, b in enumerate(bs):
-                v = host[ci, 8 * j:8 * j + 8]
-                out[b] = np.array([[v[0] + 1j * v[1], v[2] + 1j * v[3]], [v[4] + 1j * v[5], v[6] + 1j * v[7]]])
-        return out
-
     def energy_and_grad_layered(self, params: Sequence[float]) -> Tuple[float, np.ndarray]:
-        """Adjoint gradient LAYER BY LAYER for large registers.  The gate list is cut (from the end) into blocks in which
-        every two gates act on different qubits or are both single-qubit gates on the same qubit; inside such a block the
-        generator of a gate, conjugated through the later single-qubit gates of its own qubit, is still a single-qubit
-        operator A and commutes with everything else in the block, so dE/dtheta = 2 scale Re sum_ab A[a][b] T_q[a][b] with the
-        transition matrices T_q of the (bra, ket) pair AFTER the block (tqb_transition_1q: up to 6 qubits per read of both
-        states).  Between blocks both states are un-applied by ordinary fused passes on the 2-member batch [ket, bra].  A
-        hardware-efficient layer (n rz + n rx + the cx ladder) costs ~5 reads for its 2n gradients and ~2 passes for the
-        un-apply, instead of one read + one pass PER PARAMETER (civector_ops.py:141-200 gate by gate)."""
+        """Energy and adjoint gradient with the LAYERED reverse sweep (autograd.layered_sweep): every single-qubit gradient
+        of a layer from one pair of states (tqb_transition_1q), fused un-apply passes between layers -- instead of one read of
+        both states and one pass PER PARAMETER (civector_ops.py:141-200 gate by gate)."""
+        from .autograd import layered_sweep
         from .fuse import fuse
-        from .gates import DIAG
         p = np.asarray(params, dtype=np.float64)
         shape = p.shape
         gates, refs = self._lower(p.reshape(-1))
@@ -225,60 +165,8 @@ class AdjointEnergy:
                 P.DeviceProgram(prog, self.device, self.dtype).run(kb[0])
             self.ham.apply(kb[0], kb[1])
             e = float(P.inner(kb[0], kb[1])[0].real.cpu())
-            # blocks, from the end
-            blocks: List[List[int]] = []
-            cur: List[int] = []
-            one_q_bits = 0     # bits of single-qubit gates in the current block
-            other_bits = 0     # bits of everything else in it
-            for idx in range(len(gates) - 1, -1, -1):
-                g = gates[idx]
-                is1q = len(g.bits) == 1
-                ok = not (g.mask & other_bits) if is1q else not (g.mask & (other_bits | one_q_bits))
-                if not ok:
-                    blocks.append(cur)
-                    cur, one_q_bits, other_bits = [], 0, 0
-                cur.append(idx)
-                if is1q:
-                    one_q_bits |= g.mask
-                else:
-                    other_bits |= g.mask
-            if cur:
-                blocks.append(cur)
-            first_param = min((i for i, r in enumerate(refs) if r is not None), default=len(gates))
-            pending: List[LGate] = []
-            tile2 = default_tile(n, self.itemsize, 2)
-
-            def unapply() -> None:
-                if pending:
-                    prog2 = compile_program(fuse(list(pending)), n, tile2, itemsize=self.itemsize)
-                    P.DeviceProgram(prog2, self.device, self.dtype).run(kb)
-                    pending.clear()
-
-            for blk in blocks:                      # blk: gate indices in REVERSE order
-                par = [i for i in blk if refs[i] is not None]
-                if par:
-                    unapply()                       # both states are now "after this block"
-                    need = sorted({int(gates[i].bits[0]) for i in par if len(gates[i].bits) == 1})
-                    T = self._transition_1q(need) if need else {}
-                    later: dict = {}                # bit -> product of the later single-qubit gates of that bit (W)
-                    for i in blk:                   # reverse order: later gates first
-                        g = gates[i]
-                        if len(g.bits) == 1:
-                            b = int(g.bits[0])
-                            W = later.get(b, np.eye(2, dtype=np.complex128))
-                            if refs[i] is not None:
-                                D = np.asarray(GEN[g.name], dtype=np.complex128).reshape(2, 2)
-                                A = W @ D @ W.conj().T
-                                grad[refs[i].index] += 2.0 * refs[i].scale * float(np.real(np.sum(A * T[b])))
-                            later[b] = W @ self._mat1q(g)
-                        elif refs[i] is not None:   # a parametrised multi-qubit gate, alone on its qubits in the block
-                            from .autograd import grad_dense
-                            out1 = torch.zeros(1, dtype=torch.float64, device=self.device)
-                            grad_dense(kb[1], kb[0], g.bits, GEN[g.name], 2.0 * refs[i].scale, out1, 0)
-                            grad[refs[i].index] += float(out1.cpu()[0])
-                if min(blk) <= first_param:
-                    break                           # nothing left to differentiate
-                pending.extend(dagger(gates[i]) for i in blk)
+            slots = [None if r is None else (r.index, 2.0 * r.scale) for r in refs]
+            layered_sweep(kb, gates, slots, grad)
         return e, grad[: self.n_params].reshape(shape).copy()
 
     def energy_and_grad_batch(self, params: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
