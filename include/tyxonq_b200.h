@@ -54,6 +54,12 @@ extern "C" {
                          /* layer i > 0 by the value of bit bits[i-1] after layer i-1.  Matrices: */
                          /* layer i at mat_off + 8i (selector 0) and + 8i + 4 (selector 1).      */
                          /* sbits[] = ascending positions of the targets (+ a tile-local control) */
+                         /* Rotation form (off_a = 4 + 2*type + muxed, R <= 4): the data are a    */
+                         /* phase table and one coefficient per layer (tqb_core.cuh              */
+                         /* gate_chain_rot); off_b = extras (bits 0..1) | unit table (bit 7) |    */
+                         /* bit 8+i-1: scaled layer i runs in the c form | bit 11: bits 8..10 are  */
+                         /* valid (they repeat the imaginary parts of the coefficients, which the */
+                         /* generic kernels read; the specialised kernels compile them in)        */
 
 #define TQB_MAX_DENSE_K 4
 #define TQB_MAX_GATE_BITS 8
@@ -141,7 +147,10 @@ int tqb_run_passes2(void *state, int n, int64_t batch, int dtype, uint64_t globa
  * profiling switches of the specialised kernels (1 = skip gates, 2 = skip bulk loads, 4 = skip bulk stores; results
  * are WRONG with any flag set).  512 + v: tile staging of the specialised kernels, v = 1 (default) one tensor copy
  * per tile (cp.async.bulk.tensor through a CUtensorMap of the state, unpadded layouts), v = 0 one bulk copy per
- * contiguous run.  Returns the old mode.                                                                   */
+ * contiguous run.  1024 + v: code shape of the specialised kernels, v = 0 unrolled (one copy of the code per gate,
+ * every bit position an immediate), v = 1 looped (gates of one class share a body, positions from a constant table:
+ * small enough for the instruction caches), v = 2 (default) looped for complex64, unrolled for complex128.
+ * Returns the old mode.                                                                                       */
 int tqb_set_jit(int mode);
 /* Directory of the on-disk cubin cache (NULL or "" = none).                                              */
 int tqb_set_jit_cache(const char *dir);

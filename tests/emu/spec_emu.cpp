@@ -24,7 +24,8 @@ template <int GI>
 static void run_gate(char *tile, const amp *sm, unsigned tid, unsigned extv) {
   if (!fuse_in(GI))
     for (int s = 0; s < D; ++s) g_v[s] = amp{(T)1e300, (T)-1e300};   // poison: a gate that is not fused must load
-  apply_gate<GI>(tile, sm, tid, extv, g_v, NoSync());
+  if constexpr (LOOPED != 0) apply_gate_looped<GI>(tile, sm, tid, extv, NoSync());
+  else apply_gate<GI>(tile, sm, tid, extv, g_v, NoSync());
 }
 
 extern "C" int spec_emu_run(void *state_v, int n, long long batch, unsigned long long global_base, const signed char *hb,

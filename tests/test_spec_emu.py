@@ -54,6 +54,33 @@ def test_spec_passes_match_oracle(name, n, layers, m, L, dtype):
     assert np.abs(out - ref).max() < (1e-12 if dtype == np.complex128 else 3e-5)
 
 
+@pytest.mark.parametrize("dtype,m,L", [(np.complex128, 11, 5), (np.complex64, 12, 6)])
+def test_spec_scaled_layer_forms(dtype, m, L):
+    """Angles at and next to pi: scaled rotation layers in the c form (compiled in: tqb_gate.off_b bits 8..11 -> GateC.inv)
+    and in the t form with |t| up to gates.ROT_T_MAX."""
+    from tyxonq_b200 import gates as G
+    n = 14
+    rng = np.random.default_rng(77)
+    special = [np.pi, -np.pi, np.pi - 1e-9, np.pi - 1.0 / 600, np.pi - 1.0 / 400, 0.0, np.pi / 2, 3.0]
+    th = rng.choice(special, size=2 * 3 * n)
+    ops = hea_ops(n, 3, th)
+    ref, _ = O.evolve_ops(n, ops, mode="run")
+    prog = _compile(ops, n, m, L, np.dtype(dtype).itemsize)
+    chains = prog.gates[(prog.gates["kind"] == 5) & (prog.gates["off_a"] >= 4)]
+    forms = {int(g["off_b"]) >> 8 for g in chains}
+    assert all(f & 8 for f in forms) and any(f & 7 for f in forms) and any(not (f & 7) for f in forms), forms
+    code = 1 if dtype == np.complex128 else 0
+    hdrs = "".join(spec_header(np.ascontiguousarray(prog.passes), i, np.ascontiguousarray(prog.gates), code) for i in range(prog.n_passes))
+    rot = re.findall(r"^  \{6, .*\}, (-?\d+)\},$", hdrs, flags=re.M)    # GateC.inv of the rotation-form chains
+    assert rot and all(int(v) >= 0 for v in rot) and any(int(v) > 0 for v in rot), rot
+    psi0 = np.zeros(1 << n, dtype=dtype)
+    psi0[0] = 1
+    out, n_spec = run_program_spec_emulated(prog, psi0)
+    assert n_spec == prog.n_passes
+    assert np.abs(out - ref).max() < (1e-12 if dtype == np.complex128 else 3e-5)
+    assert G.ROT_T_MAX >= 512
+
+
 def test_spec_sharded_base_and_batch():
     """global_base feeds outside-the-tile controls / table bits; the batch index is just more tile index bits."""
     n, g = 13, 2

@@ -145,6 +145,8 @@ def load() -> C.CDLL:
         lib.tqb_set_jit(int(os.environ["TQB_JIT"]))
     if os.environ.get("TQB_TENSOR_TMA"):   # 0 = stage tiles with one bulk copy per run instead of one tensor copy per tile
         lib.tqb_set_jit(512 + int(os.environ["TQB_TENSOR_TMA"]))
+    if os.environ.get("TQB_SPEC_LOOP"):    # code shape of the specialised kernels: 0 unrolled, 1 looped, 2 by dtype (default)
+        lib.tqb_set_jit(1024 + int(os.environ["TQB_SPEC_LOOP"]))
     import atexit
     atexit.register(lib.tqb_jit_shutdown)   # before interpreter teardown: no compilation thread outlives the process
     _lib = lib

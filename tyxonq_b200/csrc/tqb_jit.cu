@@ -52,6 +52,7 @@ enum { K_DENSE1 = 0, K_DIAG = 1, K_MUX = 4, K_CHAIN = 5, K_ROT = 6 };
 
 struct SpecGate {
   int kind = 0, R = 0, type = 0, muxed = 0, unit_p = 0, E = 0, ctrl = -1, mat = 0, sync = 0;
+  int inv = -1;           // rotation-form chains: bit i-1 = layer i runs in the c form (tqb_gate.off_b bits 8..10); -1 = decided at run time
   int xb[2] = {-1, -1};
   int dbits[6] = {-1, -1, -1, -1, -1, -1};
   int rb[5] = {-1, -1, -1, -1, -1};
@@ -62,6 +63,7 @@ struct SpecGate {
 
 struct SpecPlan {
   int dtype = 0, m = 0, L = 0, padL = 0, next = 0, mat_count = 0, rbits = 0;
+  int looped = 0;   // code shape: 0 = one unrolled copy of the code per gate, 1 = one body per gate class (tqb_spec.cuh)
   int ext[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<SpecGate> g;
 };
@@ -70,9 +72,10 @@ static inline int popc(uint32_t v) { return __builtin_popcount(v); }
 
 // exact bank-conflict count of the gate's tile accesses for warp 0: sum over the sampled register indices and the
 // phases of a warp-wide access of the largest number of lanes that need DIFFERENT 128-byte rows of the same bank group
-static int conflict_cost(const SpecGate &s, int rbits, int es, int padL) {
+// unit: bytes of one access -- es, or 16 for complex64 gates that keep tile bit 0 in registers (tqb_spec.cuh pair_reg)
+static int conflict_cost(const SpecGate &s, int rbits, int es, int padL, int unit) {
   auto pbyte = [&](uint32_t e) -> uint32_t { return e * (uint32_t)es + (padL ? ((e >> padL) << 4) : 0u); };
-  const int lanes_per_phase = 128 / es;
+  const int lanes_per_phase = 128 / unit;
   const int D = 1 << rbits;
   int cost = 0;
   const int samples[3] = {0, D - 1, D / 2 - 1 > 0 ? D / 2 - 1 : 0};
@@ -80,6 +83,7 @@ static int conflict_cost(const SpecGate &s, int rbits, int es, int padL) {
     uint32_t so = 0;
     for (int i = 0; i < rbits; ++i)
       if ((samples[si] >> i) & 1) so |= 1u << s.rb[i];
+    if (unit > es) so &= ~1u;   // the pair's first element
     for (int ph = 0; ph < 32 / lanes_per_phase; ++ph) {
       uint32_t rows[16][16];
       int cnt[16];
@@ -89,7 +93,7 @@ static int conflict_cost(const SpecGate &s, int rbits, int es, int padL) {
         uint32_t e = so;
         for (int j = 0; j < 5; ++j) e |= ((tid >> j) & 1u) << s.tb[j];
         const uint32_t a = pbyte(e);
-        const int chunk = (int)((a / (uint32_t)es) % (uint32_t)lanes_per_phase);
+        const int chunk = (int)((a / (uint32_t)unit) % (uint32_t)lanes_per_phase);
         const uint32_t row = a / 128u;
         bool seen = false;
         for (int k = 0; k < cnt[chunk]; ++k) seen = seen || rows[chunk][k] == row;
@@ -109,6 +113,11 @@ static int map_gate(SpecGate &s, int m, int rbits, int es, int padL, uint32_t W)
   const uint32_t free_bits = all & ~s.targets & ~W;
   const int nf = rbits - popc(s.targets);
   const uint32_t fill_cand = free_bits & ~s.reserved;
+  // complex64: tile bit 0 in registers makes every access of the gate a 16-byte one (a forced filler unless a layer
+  // targets it); impossible when bit 0 is a warp bit or carries a control / table bit of the gate
+  const bool pair_forced = es == 8 && !(s.targets & 1u) && (fill_cand & 1u) && nf >= 1;
+  const bool pair = es == 8 && ((s.targets & 1u) || pair_forced);
+  const int unit = pair ? 16 : es;
   std::vector<int> cand;
   for (int b = 0; b < m; ++b)
     if ((fill_cand >> b) & 1u) cand.push_back(b);
@@ -119,10 +128,11 @@ static int map_gate(SpecGate &s, int m, int rbits, int es, int padL, uint32_t W)
   int tried = 0;
   for (uint32_t sub = (1u << nc); sub-- > 0;) {
     if (popc(sub) != nf) continue;
-    if (++tried > 24) break;
     uint32_t fillers = 0;
     for (int i = 0; i < nc; ++i)
       if ((sub >> i) & 1u) fillers |= 1u << cand[i];
+    if (pair_forced && !(fillers & 1u)) continue;
+    if (++tried > 24) break;
     SpecGate t = s;
     {
       int r = s.R;
@@ -136,7 +146,7 @@ static int map_gate(SpecGate &s, int m, int rbits, int es, int padL, uint32_t W)
       if ((lane_bits >> b) & 1u) lb.push_back(b);
     if ((int)lb.size() != 5) continue;
     // which lane bits take the low lane positions: enumerate orderings by choosing the subset for lanes 0..nl-1
-    const int nl = es == 16 ? 3 : 4;
+    const int nl = unit == 16 ? 3 : 4;
     for (uint32_t lo = 0; lo < 32u; ++lo) {
       if (popc(lo) != nl) continue;
       int j = 0;
@@ -147,7 +157,8 @@ static int map_gate(SpecGate &s, int m, int rbits, int es, int padL, uint32_t W)
       int w = 5;
       for (int b = 0; b < m; ++b)
         if ((W >> b) & 1u) t.tb[w++] = b;
-      int c = conflict_cost(t, rbits, es, padL) * 1000;
+      // (per byte moved: an 8-byte access has half the phases of a 16-byte one)
+      int c = conflict_cost(t, rbits, es, padL, unit) * (unit > es || es == 16 ? 1000 : 2000);
       // preferences: control / extra bits outside the low lanes (table loads stay one broadcast per phase),
       // fillers on high bits
       for (int i = 0; i < nl; ++i)
@@ -164,6 +175,10 @@ static int map_gate(SpecGate &s, int m, int rbits, int es, int padL, uint32_t W)
   return best;
 }
 
+// code shape of the generated kernels: 0 = unrolled (one copy of the code per gate), 1 = looped (one body per gate class),
+// 2 = by dtype: complex64 looped (its unrolled kernels are instruction-fetch bound), complex128 unrolled
+static std::atomic<int> g_spec_loop{2};
+
 // cheap half: the pass in normalised form (outside-the-tile bits as slots, matrix offsets relative to the pass)
 static bool spec_parse(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPlan &P, std::string &why) {
   const int m = ps.m, L = ps.L, h = ps.m - ps.L;
@@ -174,6 +189,10 @@ static bool spec_parse(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPl
   P.L = L;
   P.rbits = m - 7;
   P.mat_count = ps.mat_count;
+  {
+    const int lm = g_spec_loop.load();
+    P.looped = lm == 2 ? (dtype == TQB_C128 ? 0 : 1) : (lm ? 1 : 0);
+  }
   if (dtype == TQB_C128 ? P.rbits != 4 : (P.rbits != 4 && P.rbits != 5)) return why = "tile size", false;
   if (ps.max_dense_k >= 0) return why = "not a lean pass", false;
   if (ps.mat_count <= 0 || ps.mat_count > 2048) return why = "matrices not staged", false;
@@ -243,6 +262,7 @@ static bool spec_parse(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPl
           s.muxed = (int)(q.off_a & 1u);
           s.E = (int)(q.off_b & 3u);
           s.unit_p = (q.off_b & 128u) ? 1 : 0;
+          s.inv = (q.off_b & 2048u) ? (int)((q.off_b >> 8) & 7u) : -1;
           if (s.E > 2 || q.k + 1 + s.E > TQB_MAX_GATE_BITS) return why = "extra bits", false;
           for (int j = 0; j < s.E; ++j) {
             s.xb[j] = code(q.bits[q.k + 1 + j], ok);
@@ -278,9 +298,9 @@ static bool spec_parse(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPl
 static std::string shape_key(const SpecPlan &P) {
   std::string k;
   auto put = [&](int v) { k.append(reinterpret_cast<const char *>(&v), sizeof v); };
-  put(P.dtype); put(P.m); put(P.L); put(P.mat_count); put(P.next); put((int)P.g.size());
+  put(P.dtype); put(P.m); put(P.L); put(P.mat_count); put(P.next); put((int)P.g.size()); put(P.looped);
   for (const SpecGate &s : P.g) {
-    put(s.kind); put(s.R); put(s.type); put(s.muxed); put(s.unit_p); put(s.E); put(s.ctrl); put(s.mat);
+    put(s.kind); put(s.R); put(s.type); put(s.muxed); put(s.unit_p); put(s.E); put(s.ctrl); put(s.mat); put(s.inv);
     put(s.xb[0]); put(s.xb[1]);
     for (int j = 0; j < 6; ++j) put(s.dbits[j]);
     for (int j = 0; j < 5; ++j) put(s.kind == K_DIAG ? -1 : (j < s.R ? s.rb[j] : -1));
@@ -442,17 +462,17 @@ static std::string spec_header(const SpecPlan &P) {
   char buf[512];
   o += "namespace tqbs {\n";
   o += P.dtype == TQB_C128 ? "typedef double T;\n" : "typedef float T;\n";
-  snprintf(buf, sizeof buf, "constexpr int M = %d, L = %d, PADL = %d, NG = %d, NEXT = %d, MAT_COUNT = %d, RBITS = %d;\n", P.m, P.L,
-           P.padL, (int)P.g.size(), P.next, P.mat_count, P.rbits);
+  snprintf(buf, sizeof buf, "constexpr int M = %d, L = %d, PADL = %d, NG = %d, NEXT = %d, MAT_COUNT = %d, RBITS = %d, LOOPED = %d;\n",
+           P.m, P.L, P.padL, (int)P.g.size(), P.next, P.mat_count, P.rbits, P.looped);
   o += buf;
-  o += "struct GateC { int kind, R, type, muxed, unit_p, E, ctrl, mat, sync; int xb[2]; int dbits[6]; int rb[5]; int tb[7]; };\n";
+  o += "struct GateC { int kind, R, type, muxed, unit_p, E, ctrl, mat, sync; int xb[2]; int dbits[6]; int rb[5]; int tb[7]; int inv; };\n";
   o += "constexpr GateC G[NG] = {\n";
   for (const SpecGate &s : P.g) {
     snprintf(buf, sizeof buf,
-             "  {%d, %d, %d, %d, %d, %d, %d, %d, %d, {%d, %d}, {%d, %d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d, %d, %d}},\n",
+             "  {%d, %d, %d, %d, %d, %d, %d, %d, %d, {%d, %d}, {%d, %d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d, %d, %d}, %d},\n",
              s.kind, s.R, s.type, s.muxed, s.unit_p, s.E, s.ctrl, s.mat, s.sync, s.xb[0], s.xb[1], s.dbits[0], s.dbits[1],
              s.dbits[2], s.dbits[3], s.dbits[4], s.dbits[5], s.rb[0], s.rb[1], s.rb[2], s.rb[3], s.rb[4], s.tb[0], s.tb[1],
-             s.tb[2], s.tb[3], s.tb[4], s.tb[5], s.tb[6]);
+             s.tb[2], s.tb[3], s.tb[4], s.tb[5], s.tb[6], s.inv);
     o += buf;
   }
   o += "};\n}\n";
@@ -879,6 +899,11 @@ using namespace tqb;
 extern "C" {
 
 int tqb_set_jit(int mode) {
+  if (mode >= 1024) {   // 1024 + v: code shape of the generated kernels (see g_spec_loop)
+    const int v = mode - 1024;
+    g_spec_loop.store(v < 0 || v > 2 ? 2 : v);
+    return g_jit_mode.load();
+  }
   if (mode >= 512) {   // 512 + v: tensor-map staging (cp.async.bulk.tensor) on / off
     g_tensor_tma.store(mode - 512 ? 1 : 0);
     return g_jit_mode.load();

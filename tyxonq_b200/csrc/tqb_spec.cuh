@@ -37,7 +37,7 @@ namespace tqbs {
 
 // ---- generated before this point ------------------------------------------------------------------
 //   typedef double T;                       amplitude component type
-//   constexpr int M, L, PADL, NG, NEXT, MAT_COUNT, RBITS;
+//   constexpr int M, L, PADL, NG, NEXT, MAT_COUNT, RBITS, LOOPED;
 //   struct GateC;  constexpr GateC G[NG];
 // (struct GateC is declared by the generated block so that both sides agree on the field order.)
 
@@ -96,6 +96,45 @@ SPEC_HD int reg_index(int p) {
   return -1;
 }
 
+// complex64: when tile bit 0 is a register bit of the gate (the generator arranges that: a filler when no layer targets
+// it), the two amplitudes that differ in it are one aligned 16-byte shared-memory access -- 8 lanes per wavefront, the
+// same bank picture as complex128 -- instead of two 8-byte ones.  pair_reg: that register bit's index, or -1.
+template <int GI>
+SPEC_HD int pair_reg() {
+  return ES == 8 ? reg_index<GI>(0) : -1;
+}
+struct alignas(4 * sizeof(T)) amp2 {
+  cplx<T> a, b;
+};
+// v[s] <- element at addr(s) for every register index s; J0 >= 0: s and s | (1 << J0) are adjacent (one access)
+template <int N, int J0, class AddrF>
+SPEC_DEV void load_amps(amp (&v)[N], AddrF addr) {
+  static_for<N>([&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    if constexpr (J0 < 0) {
+      v[s] = *reinterpret_cast<const amp *>(addr(sc));
+    } else if constexpr (!((s >> (J0 < 0 ? 0 : J0)) & 1)) {
+      const amp2 p = *reinterpret_cast<const amp2 *>(addr(sc));
+      v[s] = p.a;
+      v[s | (1 << (J0 < 0 ? 0 : J0))] = p.b;
+    }
+  });
+}
+template <int N, int J0, class AddrF>
+SPEC_DEV void store_amps(const amp (&v)[N], AddrF addr) {
+  static_for<N>([&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    if constexpr (J0 < 0) {
+      *reinterpret_cast<amp *>(addr(sc)) = v[s];
+    } else if constexpr (!((s >> (J0 < 0 ? 0 : J0)) & 1)) {
+      amp2 p;
+      p.a = v[s];
+      p.b = v[s | (1 << (J0 < 0 ? 0 : J0))];
+      *reinterpret_cast<amp2 *>(addr(sc)) = p;
+    }
+  });
+}
+
 // DIAG: the part of the table index that comes from register bits, for register index s
 template <int GI>
 SPEC_HD unsigned diag_tvar(int s) {
@@ -145,15 +184,15 @@ SPEC_DEV unsigned bit_value(unsigned base, unsigned extv) {
 
 // ---- arithmetic on the register block ------------------------------------------------------------------
 // dense 2x2 on register bit I; SELBIT >= 0: pairs whose register bit SELBIT is 1 use (b..) instead of (a..)
-template <int I, int SELBIT>
-SPEC_DEV void layer_dense(amp (&v)[D], const amp *Ma, const amp *Mb) {
+template <int I, int SELBIT, int N>
+SPEC_DEV void layer_dense(amp (&v)[N], const amp *Ma, const amp *Mb) {
   const amp a00 = Ma[0], a01 = Ma[1], a10 = Ma[2], a11 = Ma[3];
   amp b00 = a00, b01 = a01, b10 = a10, b11 = a11;
   if constexpr (SELBIT >= 0) {
     b00 = Mb[0]; b01 = Mb[1]; b10 = Mb[2]; b11 = Mb[3];
   }
 #pragma unroll
-  for (int s = 0; s < D; ++s) {
+  for (int s = 0; s < N; ++s) {
     if (s & (1 << I)) continue;
     const bool sel = SELBIT >= 0 && ((s >> (SELBIT >= 0 ? SELBIT : 0)) & 1);
     const amp m00 = sel ? b00 : a00, m01 = sel ? b01 : a01, m10 = sel ? b10 : a10, m11 = sel ? b11 : a11;
@@ -171,10 +210,10 @@ SPEC_DEV void layer_dense(amp (&v)[D], const amp *Ma, const amp *Mb) {
 
 // rotation-form layers (tqb_core.cuh rot_layer / rot_layer_scaled): M = [[a, i r], [i r, a]] (TYPE 0) or
 // [[a, -r], [r, a]] (TYPE 1); MUXED: the pair's inputs are renamed when register bit I-1 is 1 (the fused cx)
-template <int I, int TYPE, bool MUXED>
-SPEC_DEV void rot_layer(amp (&v)[D], const T a, const T r) {
+template <int I, int TYPE, bool MUXED, int N>
+SPEC_DEV void rot_layer(amp (&v)[N], const T a, const T r) {
 #pragma unroll
-  for (int s = 0; s < D; ++s) {
+  for (int s = 0; s < N; ++s) {
     if (s & (1 << I)) continue;
     const bool sel = MUXED && I > 0 && ((s >> (I > 0 ? I - 1 : 0)) & 1);
     const int lo = s, hi = s | (1 << I);
@@ -197,11 +236,14 @@ SPEC_DEV void rot_layer(amp (&v)[D], const T a, const T r) {
   }
 }
 
-template <int I, int TYPE, bool MUXED>
-SPEC_DEV void rot_layer_scaled(amp (&v)[D], const T k, const bool inv) {
+// INVC: 0 / 1 = the form is known when the kernel is generated (tqb_gate.off_b bits 8..11: no run-time branch, one copy of the
+// layer's code), -1 = read from the coefficient at run time
+template <int I, int TYPE, bool MUXED, int INVC, int N>
+SPEC_DEV void rot_layer_scaled(amp (&v)[N], const T k, const bool inv_rt) {
+  const bool inv = INVC < 0 ? inv_rt : (INVC != 0);
   if (!inv) {
 #pragma unroll
-    for (int s = 0; s < D; ++s) {
+    for (int s = 0; s < N; ++s) {
       if (s & (1 << I)) continue;
       const bool sel = MUXED && ((s >> (I > 0 ? I - 1 : 0)) & 1);
       const int lo = s, hi = s | (1 << I);
@@ -228,7 +270,7 @@ SPEC_DEV void rot_layer_scaled(amp (&v)[D], const T k, const bool inv) {
     }
   } else {
 #pragma unroll
-    for (int s = 0; s < D; ++s) {
+    for (int s = 0; s < N; ++s) {
       if (s & (1 << I)) continue;
       const bool sel = MUXED && ((s >> (I > 0 ? I - 1 : 0)) & 1);
       const int lo = s, hi = s | (1 << I);
@@ -282,14 +324,11 @@ SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv,
       v[s] = t[s];
     });
   }
+  constexpr int J0 = pair_reg<GI>();
+  auto elem = [&](auto sc) { return tb0 + pbyte(soff<GI>(decltype(sc)::value)); };
   // plain load of the block (element s -> register s)
   auto load_block = [&]() {
-    if constexpr (!FIN) {
-      static_for<D>([&](auto sc) {
-        constexpr int s = decltype(sc)::value;
-        v[s] = *reinterpret_cast<const amp *>(tb0 + pbyte(soff<GI>(s)));
-      });
-    }
+    if constexpr (!FIN) load_amps<D, J0>(v, elem);
   };
 
   if constexpr (KIND == K_ROT) {
@@ -325,23 +364,29 @@ SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv,
       if (i < R) {
         const amp c = coef[i];
         kk[i] = c.x;
-        inv[i] = c.y != (T)0;
+        if constexpr (G[GI].inv < 0) inv[i] = c.y != (T)0;
       }
     }
     sync();
-    static_for<D>([&](auto sc) {
-      constexpr int s = decltype(sc)::value;
-      constexpr unsigned o = pbyte(soff<GI>(s & ~1));
-      amp in;
-      if constexpr (FIN) in = v[s];
-      else in = *reinterpret_cast<const amp *>(((s & 1) ? pb : pa) + o);
-      if constexpr (G[GI].unit_p != 0) v[s] = in;
-      else v[s] = cmul(in, ((s & 1) ? Po : Pe)[s & ((1 << R) - 1)]);
-    });
+    if constexpr (!FIN) {
+      // a run-time control swaps the two halves of a pair that sits on layer 0's bit: single accesses then
+      constexpr int JL = (HAS_CTRL && J0 == 0) ? -1 : J0;
+      load_amps<D, JL>(v, [&](auto sc) {
+        constexpr int s = decltype(sc)::value;
+        return ((s & 1) ? pb : pa) + pbyte(soff<GI>(s & ~1));
+      });
+    }
+    if constexpr (G[GI].unit_p == 0) {
+      static_for<D>([&](auto sc) {
+        constexpr int s = decltype(sc)::value;
+        v[s] = cmul(v[s], ((s & 1) ? Po : Pe)[s & ((1 << R) - 1)]);
+      });
+    }
     rot_layer<0, TYPE, false>(v, a0, r0);
-    if constexpr (R > 1) rot_layer_scaled<(R > 1 ? 1 : 0), TYPE, MUXED>(v, kk[1], inv[1]);
-    if constexpr (R > 2) rot_layer_scaled<(R > 2 ? 2 : 0), TYPE, MUXED>(v, kk[2], inv[2]);
-    if constexpr (R > 3) rot_layer_scaled<(R > 3 ? 3 : 0), TYPE, MUXED>(v, kk[3], inv[3]);
+    constexpr int IV = G[GI].inv;
+    if constexpr (R > 1) rot_layer_scaled<(R > 1 ? 1 : 0), TYPE, MUXED, (IV < 0 ? -1 : (IV & 1))>(v, kk[1], inv[1]);
+    if constexpr (R > 2) rot_layer_scaled<(R > 2 ? 2 : 0), TYPE, MUXED, (IV < 0 ? -1 : ((IV >> 1) & 1))>(v, kk[2], inv[2]);
+    if constexpr (R > 3) rot_layer_scaled<(R > 3 ? 3 : 0), TYPE, MUXED, (IV < 0 ? -1 : ((IV >> 2) & 1))>(v, kk[3], inv[3]);
   } else if constexpr (KIND == K_CHAIN) {
     // general chain: layer i -> Mg[8i .. 8i+4) (selector 0), Mg[8i+4 .. 8i+8) (selector 1); layer 0 is selected by the
     // control, layer i > 0 by register bit i-1 after layer i-1
@@ -368,20 +413,206 @@ SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv,
     });
     const amp *const tab = Mg + tfix;
     sync();
+    load_block();
     static_for<D>([&](auto sc) {
       constexpr int s = decltype(sc)::value;
       constexpr unsigned tvar = diag_tvar<GI>(s);
-      amp in;
-      if constexpr (FIN) in = v[s];
-      else in = *reinterpret_cast<const amp *>(tb0 + pbyte(soff<GI>(s)));
-      v[s] = cmul(in, tab[tvar]);
+      v[s] = cmul(v[s], tab[tvar]);
     });
   }
-  if constexpr (!FOUT) {
+  if constexpr (!FOUT) store_amps<D, J0>(v, elem);
+}
+
+// ---- the looped variant (LOOPED != 0) ---------------------------------------------------------------------------
+// The unrolled form above spends ~600 instructions per complex64 gate and thread; a pass of 16 gates is 160 KB of
+// straight-line code that every warp streams through once per tile, far beyond the instruction caches, and the kernel
+// becomes instruction-fetch bound (profiles/r02_trotter_pass4_ncu.txt: stall no_instruction on top, issue slots 38 % busy).
+// Here gates of the same CLASS (kind, chain length and type, table / control present, forms of the scaled layers) share
+// ONE body, a real (not inlined) function: the call site of a gate still folds the gate's bit positions into immediates
+// -- thread base, control / table bits, matrix offsets, the synchronisation -- and passes the byte strides of the
+// register bits as arguments; the body forms the thread's 2^RBITS addresses with one add each.  A pass then is a few
+// bodies of 5-10 KB plus ~40 instructions per gate and runs from the instruction cache.  No register fusion in this form: a gate marked sync == -1 round-trips through shared memory
+// (same thread, same amplitudes: no barrier).
+#ifdef TQB_SPEC_EMU
+#define SPEC_BODY static
+static char *g_emu_tile = nullptr;   // the bodies address the tile by 32-bit offsets from here
+SPEC_DEV char *smem_at(unsigned off) { return g_emu_tile + off; }
+#else
+#define SPEC_BODY __device__ __noinline__
+extern __shared__ __align__(128) unsigned char smem_raw[];
+// 32-bit offsets into the CTA's shared memory: address arithmetic in the bodies stays 32-bit (one IADD per amplitude)
+SPEC_DEV char *smem_at(unsigned off) { return reinterpret_cast<char *>(smem_raw) + off; }
+#endif
+
+SPEC_HD int pair_reg_of(int gi) {
+  if (ES != 8) return -1;
+  for (int i = 0; i < RBITS; ++i)
+    if (G[gi].rb[i] == 0) return i;
+  return -1;
+}
+SPEC_HD bool same_class(int i, int j) {
+  if (G[i].kind != G[j].kind || pair_reg_of(i) != pair_reg_of(j)) return false;
+  if (G[i].kind == K_DIAG) return true;
+  if (G[i].R != G[j].R) return false;
+  if (G[i].kind == K_ROT)
+    return G[i].type == G[j].type && G[i].muxed == G[j].muxed && G[i].unit_p == G[j].unit_p &&
+           (G[i].ctrl >= 0) == (G[j].ctrl >= 0) && G[i].inv == G[j].inv;
+  return true;
+}
+SPEC_HD int class_of(int gi) {
+  for (int j = 0; j < gi; ++j)
+    if (same_class(j, gi)) return j;
+  return gi;
+}
+SPEC_HD int ctz_c(int s) {
+  int k = 0;
+  while (!((s >> k) & 1)) ++k;
+  return k;
+}
+struct Strides {
+  unsigned d[5];   // byte offset (padded layout) of register bit j
+};
+SPEC_DEV void block_addresses(const Strides &st, unsigned a0, unsigned (&a)[D]) {
+  a[0] = a0;
+  static_for<D>([&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    if constexpr (s > 0) a[s] = a[s & (s - 1)] + st.d[ctz_c(s)];
+  });
+}
+
+// rotation-form chain of class REP; tb: the thread's block (register bits zero), P: table (already offset by the extra
+// bits), coef: the layer coefficients, cv: value of the control bit
+template <int REP>
+SPEC_BODY void rot_body(unsigned tb, const amp *P, const amp *coef, unsigned cv, Strides st) {
+  constexpr int R = G[REP].R;
+  constexpr int TYPE = G[REP].type;
+  constexpr bool MUXED = G[REP].muxed != 0;
+  constexpr bool HAS_CTRL = G[REP].ctrl >= 0;
+  constexpr int J0 = pair_reg_of(REP);
+  const amp *const Pe = P + cv;
+  const amp *const Po = P - cv;
+  const T a0 = coef[0].x;
+  T r0 = coef[0].y;
+  if (TYPE == 1 && cv) r0 = -r0;
+  T kk[4];
+  bool inv[4];
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+    kk[i] = (T)0;
+    inv[i] = false;
+    if (i < R) {
+      const amp c = coef[i];
+      kk[i] = c.x;
+      if constexpr (G[REP].inv < 0) inv[i] = c.y != (T)0;
+    }
+  }
+  const unsigned dcv = cv ? st.d[0] : 0u, dncv = cv ? 0u : st.d[0];
+  unsigned a[D];
+  block_addresses(st, tb, a);
+  amp v[D];
+  // register s holds INPUT element s ^ cv (the fused cx on layer 0)
+  constexpr int JL = (HAS_CTRL && J0 == 0) ? -1 : J0;
+  load_amps<D, JL>(v, [&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    if constexpr (HAS_CTRL) return smem_at(a[s & ~1] + ((s & 1) ? dncv : dcv));
+    else return smem_at(a[s]);
+  });
+  if constexpr (G[REP].unit_p == 0) {
     static_for<D>([&](auto sc) {
       constexpr int s = decltype(sc)::value;
-      *reinterpret_cast<amp *>(tb0 + pbyte(soff<GI>(s))) = v[s];
+      v[s] = cmul(v[s], ((s & 1) ? Po : Pe)[s & ((1 << R) - 1)]);
     });
+  }
+  rot_layer<0, TYPE, false>(v, a0, r0);
+  constexpr int IV = G[REP].inv;
+  if constexpr (R > 1) rot_layer_scaled<(R > 1 ? 1 : 0), TYPE, MUXED, (IV < 0 ? -1 : (IV & 1))>(v, kk[1], inv[1]);
+  if constexpr (R > 2) rot_layer_scaled<(R > 2 ? 2 : 0), TYPE, MUXED, (IV < 0 ? -1 : ((IV >> 1) & 1))>(v, kk[2], inv[2]);
+  if constexpr (R > 3) rot_layer_scaled<(R > 3 ? 3 : 0), TYPE, MUXED, (IV < 0 ? -1 : ((IV >> 2) & 1))>(v, kk[3], inv[3]);
+  store_amps<D, J0>(v, [&](auto sc) { return smem_at(a[decltype(sc)::value]); });
+}
+
+// diagonal gate of class REP: tab = table + the index bits that are not register bits; dw.d[j] = table-index weight of
+// register bit j
+template <int REP>
+SPEC_BODY void diag_body(unsigned tb, const amp *tab, Strides st, Strides dw) {
+  constexpr int J0 = pair_reg_of(REP);
+  unsigned a[D], t[D];
+  block_addresses(st, tb, a);
+  block_addresses(dw, 0u, t);
+  amp v[D];
+  load_amps<D, J0>(v, [&](auto sc) { return smem_at(a[decltype(sc)::value]); });
+  static_for<D>([&](auto sc) {
+    constexpr int s = decltype(sc)::value;
+    v[s] = cmul(v[s], tab[t[s]]);
+  });
+  store_amps<D, J0>(v, [&](auto sc) { return smem_at(a[decltype(sc)::value]); });
+}
+
+// K_CHAIN (general), K_MUX, K_DENSE1 of class REP: dense 2x2 layers; M0: layer 0's matrix (control applied), Mg: the gate's
+template <int REP>
+SPEC_BODY void dense_body(unsigned tb, const amp *M0, const amp *Mg, Strides st) {
+  constexpr int KIND = G[REP].kind;
+  constexpr int R = G[REP].R;
+  constexpr int J0 = pair_reg_of(REP);
+  unsigned a[D];
+  block_addresses(st, tb, a);
+  amp v[D];
+  load_amps<D, J0>(v, [&](auto sc) { return smem_at(a[decltype(sc)::value]); });
+  layer_dense<0, -1>(v, M0, Mg);
+  if constexpr (KIND == K_CHAIN && R > 1) layer_dense<(R > 1 ? 1 : 0), 0>(v, Mg + 8, Mg + 12);
+  if constexpr (KIND == K_CHAIN && R > 2) layer_dense<(R > 2 ? 2 : 0), 1>(v, Mg + 16, Mg + 20);
+  store_amps<D, J0>(v, [&](auto sc) { return smem_at(a[decltype(sc)::value]); });
+}
+
+// the call site of gate GI: everything about the gate is an immediate here; sync() as in apply_gate
+template <int GI, class Sync>
+SPEC_DEV void apply_gate_looped(char *tile, const amp *sm, unsigned tid, unsigned extv, Sync sync) {
+  constexpr int KIND = G[GI].kind;
+  constexpr int R = G[GI].R;
+  constexpr int REP = class_of(GI);
+  const unsigned base = thread_base<GI>(tid);
+#ifdef TQB_SPEC_EMU
+  g_emu_tile = tile;
+  const unsigned tb = pbyte(base);
+#else
+  const unsigned tb = (unsigned)(tile - reinterpret_cast<char *>(smem_raw)) + pbyte(base);
+#endif
+  const amp *const Mg = sm + G[GI].mat;
+  Strides st;
+  static_for<5>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    constexpr unsigned dj = j < RBITS ? pbyte(1u << G[GI].rb[j < RBITS ? j : 0]) : 0u;
+    st.d[j] = dj;
+  });
+  if constexpr (KIND == K_ROT) {
+    constexpr int E = G[GI].E;
+    constexpr unsigned TAB = 1u << (R + E);
+    const unsigned cv = bit_value<GI, G[GI].ctrl>(base, extv);
+    unsigned x = 0;
+    if constexpr (E > 0) x |= bit_value<GI, G[GI].xb[0]>(base, extv);
+    if constexpr (E > 1) x |= bit_value<GI, G[GI].xb[1]>(base, extv) << 1;
+    sync();
+    rot_body<REP>(tb, Mg + (x << R), Mg + (G[GI].ctrl >= 0 ? 2u * TAB : TAB), cv, st);
+  } else if constexpr (KIND == K_DIAG) {
+    unsigned tfix = 0;
+    Strides dw;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) dw.d[j] = 0u;
+    static_for<6>([&](auto jc) {
+      constexpr int j = decltype(jc)::value;
+      if constexpr (j < R) {
+        constexpr int code = G[GI].dbits[j];
+        if constexpr (code >= 64 || !is_reg_bit<GI>(code)) tfix |= bit_value<GI, code>(base, extv) << j;
+        else dw.d[reg_index<GI>(code)] = 1u << j;
+      }
+    });
+    sync();
+    diag_body<REP>(tb, Mg + tfix, st, dw);
+  } else {
+    unsigned cv = 0;
+    if constexpr (KIND != K_DENSE1) cv = bit_value<GI, G[GI].ctrl>(base, extv);
+    sync();
+    dense_body<REP>(tb, Mg + 4u * cv, Mg, st);
   }
 }
 
@@ -412,6 +643,23 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+// the producer warp's wait: sleeps between polls, so that its polling does not take issue slots from the consumer warps
+// that share its scheduler (compute-bound passes: the polls were 20 % of all executed instructions)
+__device__ __forceinline__ void mbar_wait_relaxed(u64 *bar, u32 parity) {
+  const u32 addr = smem_u32(bar);
+  u32 done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
 }
 __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -478,7 +726,6 @@ constexpr u32 SMEM_TOTAL = SMEM_ROFF + 8u * NRUNS;
 
 extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const SpecParams prm,
                                                                         const __grid_constant__ TensorMap tmap) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
   u64 *full = reinterpret_cast<u64 *>(smem_raw + SMEM_BARS);
   u64 *done = full + 4;
   amp *smats = reinterpret_cast<amp *>(smem_raw + SMEM_MATS);
@@ -556,7 +803,7 @@ extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const Spe
         }
         for (u64 it = 0; it < count; ++it) {
           const int b = (int)(it % NB);
-          mbar_wait(&done[b], (u32)((it / NB) & 1));
+          mbar_wait_relaxed(&done[b], (u32)((it / NB) & 1));
           coords(it, c);
           tensor_store(&tmap, c, smem_raw + b * TILE_STRIDE);
           bulk_commit();
@@ -576,7 +823,7 @@ extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const Spe
     for (u64 it = 0; it < (u64)NB && it < count; ++it) issue_load(it);
     for (u64 it = 0; it < count; ++it) {
       const int b = (int)(it % NB);
-      mbar_wait(&done[b], (u32)((it / NB) & 1));
+      mbar_wait_relaxed(&done[b], (u32)((it / NB) & 1));
       const u64 nxt = it + NB;
       const bool refill = nxt < count;
       amp *dstg = tile_ptr(it);
@@ -625,6 +872,16 @@ extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const Spe
     }
     if (prm.dbg & 1) {
       mbar_wait(&full[b], parity);
+    } else if constexpr (LOOPED != 0) {
+      static_for<NG>([&](auto gc) {
+        constexpr int GI = decltype(gc)::value;
+        apply_gate_looped<GI>(tile, smats, (unsigned)tid, extv, [&]() {
+          constexpr int S = G[GI].sync;
+          if constexpr (S == 0) mbar_wait(&full[b], parity);
+          else if constexpr (S == 1) __syncwarp();
+          else if constexpr (S == 2) consumer_sync();
+        });
+      });
     } else {
       amp v[D];
       static_for<NG>([&](auto gc) {

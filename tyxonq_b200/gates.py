@@ -201,6 +201,13 @@ def mux_gate(u0: np.ndarray, u1: np.ndarray, target_bit: int, control_bit: int, 
     return LGate(MUX, (int(target_bit), int(control_bit)), np.ascontiguousarray(d), pat_b=int(structure), batched=True, **kw)
 
 
+# A scaled rotation layer runs as x + t.(i x') with t = r / a as long as |t| <= ROT_T_MAX, else as c.x + i x' with c = a / r
+# (tqb_core.cuh rot_layer_scaled).  The product of the divided-out factors multiplies layer 0, so the rounding errors stay
+# relative to |a x| + |r x'| in either form; the t form is preferred far beyond |t| = 1 because the specialised kernels
+# compile the form in (tqb_gate.off_b bits 8..11) and circuits whose angles move (VQE) should keep their kernel shapes.
+ROT_T_MAX = 1024.0
+
+
 def rot_decompose(u: np.ndarray) -> Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]]:
     """U = M.diag(d0, d1) with M = [[a, i r], [i r, a]] (type 0: rz.rx products) or M = [[a, -r], [r, a]] (type 1: ry, h),
     a and r real, for every member of u [B, 2, 2].  Returns {type: (a, r, d0, d1)} for the types that reproduce U to
@@ -285,6 +292,7 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
     E = len(extra_bits)
     assert E <= 2
     unit = False
+    inv_bits = 0   # bit i-1: layer i runs in the c form; bit 3: the bits are valid (unbatched chains)
     if rot is not None:
         typ, muxed, dec = rot
         if B == 1:   # plain Python complex arithmetic: the planner builds one of these per chain
@@ -309,12 +317,14 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
             coef, scale = [], 1.0
             for i in range(1, R):   # scaled layers: (t, 0) with t = r / a, or (c, 1) with c = a / r; the factor goes to layer 0
                 ai, ri = float(dec[i][0][0]), float(dec[i][1][0])
-                if abs(ai) >= abs(ri):
+                if abs(ai) * ROT_T_MAX >= abs(ri):
                     coef.append(complex(ri / ai, 0.0))
                     scale *= ai
                 else:
                     coef.append(complex(ai / ri, 1.0))
                     scale *= ri
+                    inv_bits |= 1 << (i - 1)
+            inv_bits |= 8     # the forms are the same for every state of the batch: the specialised kernels compile them in
             tab += [complex(float(dec[0][0][0]) * scale, float(dec[0][1][0]) * scale)] + coef
             data = np.array(tab, dtype=C128).reshape(1, -1)
         else:
@@ -325,17 +335,20 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
             unit = bool(np.abs(P - 1.0).max() < 1e-15)   # plain rotations (ry, rx layers): the kernel skips the table multiply
             if control_bit is not None:
                 P = np.concatenate([P, P[:, np.arange(1 << R) ^ 1]], axis=1)
-            cols, scale = [], np.ones(B)
+            cols, scale, all_t = [], np.ones(B), True
             for i in range(1, R):   # scaled layers, per batch member (see the B == 1 branch)
                 ai, ri = np.broadcast_to(dec[i][0], (B,)), np.broadcast_to(dec[i][1], (B,))
-                big = np.abs(ai) >= np.abs(ri)
+                big = np.abs(ai) * ROT_T_MAX >= np.abs(ri)
+                all_t = all_t and bool(np.all(big))
                 with np.errstate(all="ignore"):
                     cols.append(np.where(big, ri / ai, ai / ri) + 1j * np.where(big, 0.0, 1.0))
                 scale = scale * np.where(big, ai, ri)
+            if all_t:
+                inv_bits = 8   # every member runs every scaled layer in the t form
             cols.insert(0, (np.broadcast_to(dec[0][0], (B,)) + 1j * np.broadcast_to(dec[0][1], (B,))) * scale)
             coef = np.stack(cols, axis=1)
             data = np.ascontiguousarray(np.concatenate([P, coef], axis=1))
-        kw["pat_b"] = (4 + 2 * typ + muxed) | (E << 4) | (128 if unit else 0)
+        kw["pat_b"] = (4 + 2 * typ + muxed) | (E << 4) | (128 if unit else 0) | (inv_bits << 8)
     else:
         blocks = []
         for _, a, b in layers:
