@@ -31,7 +31,8 @@ static void run_gate(char *tile, const amp *sm, unsigned tid, unsigned extv) {
 extern "C" int spec_emu_run(void *state_v, int n, long long batch, unsigned long long global_base, const signed char *hb,
                             const signed char *ext, const void *mats_v) {
   amp *state = reinterpret_cast<amp *>(state_v);
-  const amp *mats = reinterpret_cast<const amp *>(mats_v);
+  const amp *mats_all = reinterpret_cast<const amp *>(mats_v);
+  std::vector<amp> staged(MAT_COUNT + 1);
   gate_fn fn[NG];
   static_for<NG>([&](auto gc) {
     constexpr int GI = decltype(gc)::value;
@@ -55,6 +56,10 @@ extern "C" int spec_emu_run(void *state_v, int n, long long batch, unsigned long
       return o;
     };
     for (unsigned e = 0; e < nel; ++e) memcpy(tile.data() + pbyte(e), &sb[gidx(e)], sizeof(amp));
+    // the kernel's staged copy of the matrices: gate by gate, the data of batch member bm
+    for (int gi = 0; gi < NG; ++gi)
+      for (int i = 0; i < G[gi].mlen; ++i) staged[G[gi].mat + i] = mats_all[G[gi].msrc + bm * (unsigned long long)G[gi].mbs + i];
+    const amp *mats = staged.data();
     unsigned extv = 0;
     for (int j = 0; j < NEXT; ++j) extv |= (unsigned)(((global_base | x) >> ext[j]) & 1ull) << j;
     // segments: [lo, hi) with G[lo].sync in {0, 2}; runs inside a segment start at sync == 1

@@ -374,7 +374,23 @@ def test_specialised_kernels_match_oracle(cuda_device):
         P.DeviceProgram(prog, cuda_device, torch.complex128).run(st)
         assert _lib.jit_stats()["spec_launches"] - before == prog.n_passes
         assert np.abs(st.cpu().numpy() - ref[None, :]).max() < TOL128
+        # one matrix set per batch member (config 5's batched ansatz): the kernel re-stages the matrices member by member;
+        # both code shapes (unrolled / one body per gate class) for both dtypes
+        from tyxonq_b200.batched import BatchedAnsatz
+        nq, layers, B = 15, 3, 24
+        params = rng.uniform(-np.pi, np.pi, (B, (layers + 1) * nq))
+        refs = np.stack([O.evolve_ops(nq, O.hwe_ry_ops(nq, layers, params[b]))[0] for b in range(B)])
+        for td, tol in ((torch.complex64, TOL64), (torch.complex128, TOL128)):
+            for shape in (0, 1):
+                lib.tqb_set_jit(1024 + shape)
+                ba = BatchedAnsatz(nq, layers, B, device=cuda_device, dtype=td,
+                                   tile=TileConfig(m=12 if td == torch.complex64 else 11, L=6 if td == torch.complex64 else 5, threads=128))
+                before = _lib.jit_stats()["spec_launches"]
+                out = ba.run(params).cpu().numpy()
+                assert _lib.jit_stats()["spec_launches"] - before == ba.passes, "per-member passes must run specialised kernels"
+                assert np.abs(out - refs).max() < tol, (td, shape, np.abs(out - refs).max())
     finally:
+        lib.tqb_set_jit(1024 + 2)
         lib.tqb_set_jit(512 + 1)
         lib.tqb_set_jit(old)
 

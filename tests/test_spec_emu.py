@@ -71,7 +71,7 @@ def test_spec_scaled_layer_forms(dtype, m, L):
     assert all(f & 8 for f in forms) and any(f & 7 for f in forms) and any(not (f & 7) for f in forms), forms
     code = 1 if dtype == np.complex128 else 0
     hdrs = "".join(spec_header(np.ascontiguousarray(prog.passes), i, np.ascontiguousarray(prog.gates), code) for i in range(prog.n_passes))
-    rot = re.findall(r"^  \{6, .*\}, (-?\d+)\},$", hdrs, flags=re.M)    # GateC.inv of the rotation-form chains
+    rot = re.findall(r"^  \{6, .*\}, (-?\d+), \d+, \d+, \d+\},$", hdrs, flags=re.M)    # GateC.inv of the rotation-form chains
     assert rot and all(int(v) >= 0 for v in rot) and any(int(v) > 0 for v in rot), rot
     psi0 = np.zeros(1 << n, dtype=dtype)
     psi0[0] = 1
@@ -97,6 +97,26 @@ def test_spec_sharded_base_and_batch():
     out, n_spec = run_program_spec_emulated(prog, psi0.reshape(-1), batch=3)
     assert n_spec == prog.n_passes
     assert np.abs(out.reshape(3, -1) - refn[None, :]).max() < 1e-12
+
+
+@pytest.mark.parametrize("dtype,m,L", [(np.complex64, 12, 6), (np.complex128, 11, 5)])
+def test_spec_per_member_matrices(dtype, m, L):
+    """One matrix set per batch member (tqb_gate.mat_bstride != 0, the batched ansatz of config 5): the specialised
+    kernel stages the member's matrices gate by gate and re-stages them when its tile range reaches the next member."""
+    from tyxonq_b200.batched import hwe_ry_gates
+    n, layers, B = 14, 2, 3
+    rng = np.random.default_rng(11)
+    params = rng.uniform(-np.pi, np.pi, (B, (layers + 1) * n))
+    prog = compile_program(fuse(hwe_ry_gates(n, layers, params)), n, TileConfig(m=m, L=L, threads=128), batch_mats=B,
+                           itemsize=np.dtype(dtype).itemsize)
+    assert (prog.gates["mat_bstride"] != 0).any()
+    psi0 = np.zeros((B, 1 << n), dtype=dtype)
+    psi0[:, 0] = 1
+    out, n_spec = run_program_spec_emulated(prog, psi0.reshape(-1), batch=B)
+    assert n_spec == prog.n_passes
+    for b in range(B):
+        ref, _ = O.evolve_ops(n, hwe_ry_ops(n, layers, params[b]), mode="run")
+        assert np.abs(out.reshape(B, -1)[b] - ref).max() < (1e-12 if dtype == np.complex128 else 3e-5), b
 
 
 def test_generator_invariants():

@@ -1,7 +1,7 @@
 """Compile the specialised pass kernels of the standard workloads into the on-disk cubin cache (tyxonq_b200/jit_cache/)
 with NVRTC -- needs no GPU.  The cache is git-ignored but ships to the GPU box with the snapshot, so the first step of a
 bench or smoke run finds its kernels ready instead of compiling them in the background.
-usage: python tools/prewarm_jit.py [hea30] [hea30c64] [qaoa30] [smoke] [trotter]"""
+usage: python tools/prewarm_jit.py [hea30] [hea30c64] [qaoa30] [smoke] [trotter] [hwe20b]"""
 from __future__ import annotations
 
 import sys
@@ -31,6 +31,18 @@ def shapes(name: str):
     raise SystemExit(f"unknown workload {name}")
 
 
+def batched_program(name: str):
+    """Programs with one matrix set per batch member (config 5: 1024 parameter sets of the 20-qubit HWE-RY ansatz)."""
+    from tyxonq_b200.batched import hwe_ry_gates
+    from tyxonq_b200.fuse import fuse
+    from tyxonq_b200.planner import compile_program, default_tile
+    if name == "hwe20b":
+        nq, L, Bn, itemsize = 20, 4, 1024, 8
+        params = np.random.default_rng(7).random((Bn, (L + 1) * nq))
+        return compile_program(fuse(hwe_ry_gates(nq, L, params)), nq, default_tile(nq, itemsize, Bn), batch_mats=Bn, itemsize=itemsize), itemsize
+    return None
+
+
 def prewarm(names) -> int:
     from tyxonq_b200 import _lib
     from tyxonq_b200.fuse import fuse
@@ -39,9 +51,13 @@ def prewarm(names) -> int:
     lib = _lib.load()
     done = 0
     for name in names:
-        n, ops, itemsize = shapes(name)
-        lg = fuse([g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None])
-        prog = compile_program(lg, n, default_tile(n, itemsize), itemsize=itemsize)
+        bp = batched_program(name)
+        if bp is not None:
+            prog, itemsize = bp
+        else:
+            n, ops, itemsize = shapes(name)
+            lg = fuse([g for g in (lower_op(o, n, mode="run") for o in ops) if g is not None])
+            prog = compile_program(lg, n, default_tile(n, itemsize), itemsize=itemsize)
         passes, gates = np.ascontiguousarray(prog.passes), np.ascontiguousarray(prog.gates)
         t0 = time.time()
         ok = bad = 0

@@ -52,6 +52,7 @@ enum { K_DENSE1 = 0, K_DIAG = 1, K_MUX = 4, K_CHAIN = 5, K_ROT = 6 };
 
 struct SpecGate {
   int kind = 0, R = 0, type = 0, muxed = 0, unit_p = 0, E = 0, ctrl = -1, mat = 0, sync = 0;
+  int msrc = 0, mlen = 0, mbs = 0;   // matrices: offset of member 0's data from the pass's first matrix, length, per-member stride
   int inv = -1;           // rotation-form chains: bit i-1 = layer i runs in the c form (tqb_gate.off_b bits 8..10); -1 = decided at run time
   int xb[2] = {-1, -1};
   int dbits[6] = {-1, -1, -1, -1, -1, -1};
@@ -63,6 +64,7 @@ struct SpecGate {
 
 struct SpecPlan {
   int dtype = 0, m = 0, L = 0, padL = 0, next = 0, mat_count = 0, rbits = 0;
+  int batched = 0;  // some gate carries one matrix set per batch member (tqb_gate.mat_bstride)
   int looped = 0;   // code shape: 0 = one unrolled copy of the code per gate, 1 = one body per gate class (tqb_spec.cuh)
   int ext[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<SpecGate> g;
@@ -188,14 +190,13 @@ static bool spec_parse(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPl
   P.m = m;
   P.L = L;
   P.rbits = m - 7;
-  P.mat_count = ps.mat_count;
+  P.mat_count = 0;   // the staged (per-member) length: filled in gate by gate below
   {
     const int lm = g_spec_loop.load();
     P.looped = lm == 2 ? (dtype == TQB_C128 ? 0 : 1) : (lm ? 1 : 0);
   }
   if (dtype == TQB_C128 ? P.rbits != 4 : (P.rbits != 4 && P.rbits != 5)) return why = "tile size", false;
   if (ps.max_dense_k >= 0) return why = "not a lean pass", false;
-  if (ps.mat_count <= 0 || ps.mat_count > 2048) return why = "matrices not staged", false;
   if (((size_t)es << L) < 128 || h < 1 || h > 6) return why = "run length", false;
   if (ps.n_gates < 1 || ps.n_gates > 64) return why = "gate count", false;
   auto code = [&](int8_t b, bool &ok) -> int {
@@ -219,9 +220,11 @@ static bool spec_parse(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPl
     const tqb_gate &q = gh[ps.gate_begin + gi];
     SpecGate s;
     bool ok = true;
-    if (q.mat_bstride != 0) return why = "per-member matrices", false;
-    s.mat = (int)q.mat_off - ps.mat_begin;
-    if (s.mat < 0 || s.mat >= ps.mat_count) return why = "matrix range", false;
+    s.msrc = (int)q.mat_off - ps.mat_begin;
+    s.mbs = (int)q.mat_bstride;
+    s.mat = P.mat_count;   // where the gate's (member's) data sit in the staged copy
+    if (s.msrc < 0) return why = "matrix range", false;
+    if (s.mbs != 0) P.batched = 1;
     auto target = [&](int i, int8_t b) {
       if (b < 0 || b >= m || ((s.targets >> b) & 1u)) ok = false;
       else {
@@ -289,8 +292,18 @@ static bool spec_parse(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPl
         return why = "gate kind", false;
     }
     if (!ok) return why = "bad gate bits", false;
+    switch (s.kind) {   // length of the gate's data (complex elements)
+      case K_DENSE1: s.mlen = 4; break;
+      case K_MUX: s.mlen = 8; break;
+      case K_CHAIN: s.mlen = 8 * s.R; break;
+      case K_DIAG: s.mlen = 1 << s.R; break;
+      default: s.mlen = ((1 << (s.R + s.E)) << (s.ctrl >= 0 ? 1 : 0)) + s.R; break;   // K_ROT: table(s) + one coefficient per layer
+    }
+    if (s.mbs != 0 && s.mbs != s.mlen) return why = "per-member stride", false;
+    P.mat_count += s.mlen;
     P.g.push_back(s);
   }
+  if (P.mat_count <= 0 || P.mat_count > 2048) return why = "matrices not staged", false;
   return true;
 }
 
@@ -300,7 +313,7 @@ static std::string shape_key(const SpecPlan &P) {
   auto put = [&](int v) { k.append(reinterpret_cast<const char *>(&v), sizeof v); };
   put(P.dtype); put(P.m); put(P.L); put(P.mat_count); put(P.next); put((int)P.g.size()); put(P.looped);
   for (const SpecGate &s : P.g) {
-    put(s.kind); put(s.R); put(s.type); put(s.muxed); put(s.unit_p); put(s.E); put(s.ctrl); put(s.mat); put(s.inv);
+    put(s.kind); put(s.R); put(s.type); put(s.muxed); put(s.unit_p); put(s.E); put(s.ctrl); put(s.mat); put(s.inv); put(s.msrc); put(s.mbs);
     put(s.xb[0]); put(s.xb[1]);
     for (int j = 0; j < 6; ++j) put(s.dbits[j]);
     for (int j = 0; j < 5; ++j) put(s.kind == K_DIAG ? -1 : (j < s.R ? s.rb[j] : -1));
@@ -462,17 +475,17 @@ static std::string spec_header(const SpecPlan &P) {
   char buf[512];
   o += "namespace tqbs {\n";
   o += P.dtype == TQB_C128 ? "typedef double T;\n" : "typedef float T;\n";
-  snprintf(buf, sizeof buf, "constexpr int M = %d, L = %d, PADL = %d, NG = %d, NEXT = %d, MAT_COUNT = %d, RBITS = %d, LOOPED = %d;\n",
-           P.m, P.L, P.padL, (int)P.g.size(), P.next, P.mat_count, P.rbits, P.looped);
+  snprintf(buf, sizeof buf, "constexpr int M = %d, L = %d, PADL = %d, NG = %d, NEXT = %d, MAT_COUNT = %d, RBITS = %d, LOOPED = %d, BATCHED = %d;\n",
+           P.m, P.L, P.padL, (int)P.g.size(), P.next, P.mat_count, P.rbits, P.looped, P.batched);
   o += buf;
-  o += "struct GateC { int kind, R, type, muxed, unit_p, E, ctrl, mat, sync; int xb[2]; int dbits[6]; int rb[5]; int tb[7]; int inv; };\n";
+  o += "struct GateC { int kind, R, type, muxed, unit_p, E, ctrl, mat, sync; int xb[2]; int dbits[6]; int rb[5]; int tb[7]; int inv, msrc, mlen, mbs; };\n";
   o += "constexpr GateC G[NG] = {\n";
   for (const SpecGate &s : P.g) {
     snprintf(buf, sizeof buf,
-             "  {%d, %d, %d, %d, %d, %d, %d, %d, %d, {%d, %d}, {%d, %d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d, %d, %d}, %d},\n",
+             "  {%d, %d, %d, %d, %d, %d, %d, %d, %d, {%d, %d}, {%d, %d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d, %d, %d}, %d, %d, %d, %d},\n",
              s.kind, s.R, s.type, s.muxed, s.unit_p, s.E, s.ctrl, s.mat, s.sync, s.xb[0], s.xb[1], s.dbits[0], s.dbits[1],
              s.dbits[2], s.dbits[3], s.dbits[4], s.dbits[5], s.rb[0], s.rb[1], s.rb[2], s.rb[3], s.rb[4], s.tb[0], s.tb[1],
-             s.tb[2], s.tb[3], s.tb[4], s.tb[5], s.tb[6], s.inv);
+             s.tb[2], s.tb[3], s.tb[4], s.tb[5], s.tb[6], s.inv, s.msrc, s.mlen, s.mbs);
     o += buf;
   }
   o += "};\n}\n";
@@ -849,7 +862,7 @@ int spec_try_launch(void *state, int n, int64_t batch, int dtype, uint64_t globa
   const int es = dtype == TQB_C128 ? 16 : 8;
   const int h = ps.m - ps.L;
   const size_t run_stride = ((size_t)es << ps.L) + (plan.padL ? 16 : 0);
-  const size_t smem = 2 * (run_stride << h) + 64 + (size_t)((ps.mat_count + 1) & ~1) * es + ((size_t)8 << h);
+  const size_t smem = 2 * (run_stride << h) + 64 + (size_t)((parsed.mat_count + 1) & ~1) * es + ((size_t)8 << h);
   if (smem > (size_t)ws.max_smem_optin) return 0;
   const void *fn = reinterpret_cast<const void *>(k->kern);
   if (!k->configured) {

@@ -37,7 +37,7 @@ namespace tqbs {
 
 // ---- generated before this point ------------------------------------------------------------------
 //   typedef double T;                       amplitude component type
-//   constexpr int M, L, PADL, NG, NEXT, MAT_COUNT, RBITS, LOOPED;
+//   constexpr int M, L, PADL, NG, NEXT, MAT_COUNT, RBITS, LOOPED, BATCHED;
 //   struct GateC;  constexpr GateC G[NG];
 // (struct GateC is declared by the generated block so that both sides agree on the field order.)
 
@@ -740,10 +740,31 @@ extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const Spe
     for (int i = 0; i < H; ++i) o |= (u64)((j >> i) & 1u) << prm.hb[i];
     roff[j] = o;
   }
-  {
-    const amp *src = reinterpret_cast<const amp *>(prm.mats);
-    for (int i = tid; i < MAT_COUNT; i += CT + 32) smats[i] = src[i];
+  const int tbits = prm.n - M;
+  const u64 total = (u64)prm.batch << tbits;
+  // tiles of this CTA: first + it * stride, it < count.  Interleaved over the grid, except when gates carry one matrix
+  // set per batch member (BATCHED): then every CTA takes a contiguous range of tiles, so that it stays with one member
+  // for hundreds of tiles and re-stages the matrices only when the member changes.
+  u64 first = blockIdx.x, stride = gridDim.x;
+  u64 count = first < total ? (total - first + stride - 1) / stride : 0;
+  if constexpr (BATCHED != 0) {
+    const u64 per = (total + gridDim.x - 1) / gridDim.x;
+    first = (u64)blockIdx.x * per;
+    stride = 1;
+    count = first < total ? (total - first < per ? total - first : per) : 0;
   }
+  // the pass's matrices, gate by gate (a gate's data of batch member bm start at msrc + bm * mbs); consumers only
+  const amp *const mats = reinterpret_cast<const amp *>(prm.mats);
+  auto stage_mats = [&](u64 bm, bool all) {
+    static_for<NG>([&](auto gc) {
+      constexpr int GI = decltype(gc)::value;
+      if (all || G[GI].mbs != 0) {
+        const amp *src = mats + G[GI].msrc + bm * (u64)G[GI].mbs;
+        for (int i = tid; i < G[GI].mlen; i += CT) smats[G[GI].mat + i] = src[i];
+      }
+    });
+  };
+  if (!producer && count > 0) stage_mats(first >> tbits, true);
   if (tid == 0) {
     for (int i = 0; i < NB; ++i) {
       mbar_init(&full[i], 1);
@@ -753,10 +774,6 @@ extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const Spe
   }
   __syncthreads();
 
-  const int tbits = prm.n - M;
-  const u64 total = (u64)prm.batch << tbits;
-  const u64 first = blockIdx.x, stride = gridDim.x;
-  const u64 count = first < total ? (total - first + stride - 1) / stride : 0;
   auto tile_index = [&](u64 tt) -> u64 {   // element index (within the batch member) of tile tt's first amplitude
     u64 x = (tt & ((1ull << tbits) - 1ull)) << L;
 #pragma unroll
@@ -859,11 +876,21 @@ extern "C" __global__ void __launch_bounds__(CT + 32, 3) tqb_spec_pass(const Spe
     return;
   }
 
+  u64 member = first >> tbits;
 #pragma unroll 1
   for (u64 it = 0; it < count; ++it) {
     const int b = (int)(it % NB);
     const u32 parity = (u32)((it / NB) & 1);
     char *tile = reinterpret_cast<char *>(smem_raw + b * TILE_STRIDE);
+    if constexpr (BATCHED != 0) {
+      const u64 bm = (first + it * stride) >> tbits;
+      if (bm != member) {   // next batch member: its matrices replace the staged ones (all consumers are between tiles)
+        member = bm;
+        consumer_sync();
+        stage_mats(bm, false);
+        consumer_sync();
+      }
+    }
     u32 extv = 0;
     if constexpr (NEXT > 0) {
       const u64 gidx = prm.global_base | tile_index(first + it * stride);

@@ -220,7 +220,10 @@ def rot_decompose(u: np.ndarray) -> Dict[int, Tuple[np.ndarray, np.ndarray, np.n
     big = av >= rv
     sa, sr = np.where(av > 0, av, 1.0), np.where(rv > 0, rv, 1.0)
     out: Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = {}
+    first = _rot_decompose_scalar(*[complex(x) for x in u[0].reshape(4)])   # a type that fails on member 0 fails on the batch
     for typ, f10, f01 in ((0, 1j, 1j), (1, 1.0, -1.0)):      # M10 = f10 * r, M01 = f01 * r
+        if typ not in first:
+            continue
         d0 = np.where(big, u00 / sa, u10 / (f10 * sr))
         d1 = np.where(big, u11 / sa, u01 / (f01 * sr))
         with np.errstate(all="ignore"):                       # a zero d0 fails the |d| = 1 check below
@@ -329,9 +332,10 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
             data = np.array(tab, dtype=C128).reshape(1, -1)
         else:
             P = np.ones((B, 1 << R), dtype=C128)
-            for s in range(1 << R):
-                for i in range(R):
-                    P[:, s] *= dec[i][3] if (s >> i) & 1 else dec[i][2]
+            if not all(np.all(dec[i][2] == 1.0) and np.all(dec[i][3] == 1.0) for i in range(R)):   # (ry layers: all ones)
+                for s in range(1 << R):
+                    for i in range(R):
+                        P[:, s] *= dec[i][3] if (s >> i) & 1 else dec[i][2]
             unit = bool(np.abs(P - 1.0).max() < 1e-15)   # plain rotations (ry, rx layers): the kernel skips the table multiply
             if control_bit is not None:
                 P = np.concatenate([P, P[:, np.arange(1 << R) ^ 1]], axis=1)
