@@ -271,6 +271,41 @@ def test_pauli_sum_tiled_kernel(cuda_device):
             assert abs(old[b] - ref) < tol
 
 
+def test_pauli_sum_tiled_many_terms_per_group(cuda_device):
+    """Groups of many terms with one x-mask (sign-sum tables of the tiled kernel: low-bit table, high-bit table, straddling
+    terms): Z-only strings of 1..6 random qubits plus a few X/Y patterns that each carry many Z decorations, real and
+    complex weights, one-tile (n = 12) and streaming (n = 16, 17) layouts, complex64."""
+    import torch
+    from tyxonq_b200 import PauliSum
+    rng = np.random.default_rng(29)
+    for n, dt, tol, herm in ((16, torch.complex128, TOL128, True), (17, torch.complex64, 2e-5, True), (12, torch.complex128, TOL128, False),
+                             (16, torch.complex128, TOL128, False)):
+        terms = []
+        for _ in range(40):     # diagonal group
+            t = [0] * n
+            for q in rng.choice(n, size=int(rng.integers(1, 7)), replace=False):
+                t[int(q)] = 3
+            terms.append(t)
+        for xs in ((0, 1), (3, n - 1), (5,), (2, 7, 11)):   # four off-diagonal groups with 12 terms each
+            for _ in range(12):
+                t = [0] * n
+                for q in rng.choice(n, size=int(rng.integers(0, 5)), replace=False):
+                    t[int(q)] = 3
+                for q in xs:
+                    t[q] = int(rng.integers(1, 3)) if t[q] == 0 else 2
+                terms.append(t)
+        w = rng.normal(size=len(terms)) + (0 if herm else 1j * rng.normal(size=len(terms)))
+        ham = PauliSum.from_codes(terms, w.tolist())
+        B = 2
+        st = rng.normal(size=(B, 1 << n)) + 1j * rng.normal(size=(B, 1 << n))
+        st /= np.linalg.norm(st, axis=1, keepdims=True)
+        d = torch.from_numpy(st).to(cuda_device).to(dt)
+        got = ham.expectation(d, tiled=True).cpu().numpy()
+        for b in range(B):
+            ref = complex(np.vdot(st[b], O.apply_pauli_sum(st[b], terms, w.tolist())))
+            assert abs(got[b] - ref) < tol * 4, (n, dt, herm, b, got[b], ref)
+
+
 def test_tfim_vqe_energy(cuda_device):
     """examples/vqetfim_benchmark.py exact_energy on the device vs the oracle restatement."""
     from tyxonq_b200.vqe import TFIMVqe

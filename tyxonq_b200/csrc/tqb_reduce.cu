@@ -338,6 +338,12 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
   uint32_t *szl = reinterpret_cast<uint32_t *>(sc + nt);
   uint32_t *sgx = szl + nt;               // per group: xmask (tile-local) ...
   int *sgp = reinterpret_cast<int *>(sgx + pt.ng);   // ... and term range (relative), ng + 1 entries
+  // groups of more than two terms: the sign sum S(e) = sum_t c_t (-1)^popc(e & z_t) splits into a table over the low LB tile
+  // bits, a table over the high ones and the few terms whose z-mask straddles the split (listed in sst)
+  constexpr int LB = 7;
+  int *sst = sgp + pt.ng + 2;
+  Pair2<R> *sd = reinterpret_cast<Pair2<R> *>((reinterpret_cast<uintptr_t>(sst + nt) + 15u) & ~(uintptr_t)15u);   // [0, 128): low table, [128, 256): high
+  __shared__ int sst_n;
   const int tid = threadIdx.x;
   for (uint32_t j = tid; j < (1u << h); j += RT) {
     uint64_t o = 0;
@@ -394,17 +400,53 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
           if (!HERM) si += (b.x * a.y - b.y * a.x) * pr;
         }
       } else {
+        // tables of the sign sum for this tile (the signs of the outside-the-tile bits are already in sc[])
+        const uint32_t lowmask = m > LB ? (1u << LB) - 1u : nel - 1u;
+        const uint32_t nhigh = m > LB ? 1u << (m - LB) : 1u;
+        __syncthreads();   // (the previous group's tables are no longer read)
+        for (uint32_t j = tid; j < 128u + nhigh; j += RT) {
+          const bool low = j < 128u;
+          const uint32_t idx = low ? j : (j - 128u) << LB;
+          R pr = 0, pi = 0;
+          for (int t = a0; t < a1; ++t) {
+            const uint32_t z = szl[t];
+            // low table: masks inside the low bits (and the constant terms); high table: masks inside the high bits
+            const bool mine = low ? (z & ~lowmask) == 0u : ((z & lowmask) == 0u && z != 0u);
+            if (mine) {
+              const Pair2<R> c = sc[t];
+              pr += flip_sign(c.x, idx & z);
+              if (!REALC) pi += flip_sign(c.y, idx & z);
+            }
+          }
+          sd[j] = Pair2<R>{pr, pi};
+        }
+        if (tid < 32) {   // the straddling terms, in order
+          int cnt = 0;
+          for (int tb = a0; tb < a1; tb += 32) {
+            const int t = tb + tid;
+            const bool strad = t < a1 && (szl[t < a1 ? t : a0] & lowmask) != 0u && (szl[t < a1 ? t : a0] & ~lowmask) != 0u;
+            const unsigned bal = __ballot_sync(0xffffffffu, strad);
+            if (strad) sst[cnt + __popc(bal & ((1u << tid) - 1u))] = t;
+            cnt += __popc(bal);
+          }
+          if (tid == 0) sst_n = cnt;
+        }
+        __syncthreads();
+        const int nst = sst_n;
+        const bool diag = xl == 0u;
 #pragma unroll 2
         for (uint32_t k = tid; k < count; k += RT) {
           const uint32_t e = paired ? (((k & ~plow) << 1) | (k & plow)) : k;
-          R pr = 0, pi = 0;
-          for (int t = a0; t < a1; ++t) {
+          const Pair2<R> dl = sd[e & lowmask], dh = sd[128u + (m > LB ? e >> LB : 0u)];
+          R pr = dl.x + dh.x, pi = dl.y + dh.y;
+          for (int i = 0; i < nst; ++i) {
+            const int t = sst[i];
             const Pair2<R> c = sc[t];
             const uint32_t v = e & szl[t];
             pr += flip_sign(c.x, v);
             if (!REALC) pi += flip_sign(c.y, v);
           }
-          const cplx<T> a = tile[e], b = tile[e ^ xl];
+          const cplx<T> a = tile[e], b = diag ? a : tile[e ^ xl];
           const R qr = b.x * a.x + b.y * a.y, qi = b.x * a.y - b.y * a.x;   // conj(b) * a
           if (REALC) {
             sr += qr * pr;
@@ -1042,7 +1084,8 @@ int tqb_expect_pauli_tiled(const void *state, int n, int64_t batch, int dtype, u
         prev = lay.hb[i];
       }
     }
-    const size_t smem = ((size_t)es << lay.m) + 8 * ((((size_t)1 << pt.h) + 1) & ~(size_t)1) + (size_t)lay.n_terms * 20 + (size_t)lay.n_groups * 8 + 32;
+    const size_t smem = ((size_t)es << lay.m) + 8 * ((((size_t)1 << pt.h) + 1) & ~(size_t)1) + (size_t)lay.n_terms * 24 + (size_t)lay.n_groups * 8 +
+                        256 * (size_t)es + 64;   // tile | run offsets | sc, szl, sst per term | sgx, sgp per group | sign-sum tables
     TQB_REQUIRE(smem + 1024 <= (size_t)ws->max_smem_optin, "tqb_expect_pauli_tiled: tile + terms exceed shared memory");
 #define TQB_PT(T, HERM, REALC, PTR)                                                                                              \
   do {                                                                                                                            \
