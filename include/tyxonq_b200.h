@@ -59,7 +59,8 @@ extern "C" {
                          /* gate_chain_rot); off_b = extras (bits 0..1) | unit table (bit 7) |    */
                          /* bit 8+i-1: scaled layer i runs in the c form | bit 11: bits 8..10 are  */
                          /* valid (they repeat the imaginary parts of the coefficients, which the */
-                         /* generic kernels read; the specialised kernels compile them in)        */
+                         /* generic kernels read; the specialised kernels compile them in) | bit   */
+                         /* 12: layer 0 runs in the t form too, its factor is in the table         */
 
 #define TQB_MAX_DENSE_K 4
 #define TQB_MAX_GATE_BITS 8

@@ -578,7 +578,7 @@ TQB_HD RotDesc rot_decode(const tqb_gate &g, int m, int padL = 0) {   // padL: s
   for (int j = 0; j < 5; ++j) r.lm[j] = j < nz ? (1u << (uint32_t)g.sbits[j]) - 1u : 0xffffffffu;
   r.flags = (ctrl_local ? 1u : 0u) | (has_ctrl ? 2u : 0u) | ((g.off_b & 128u) ? 4u : 0u) | ((g.off_b & 3u) << 3) |
             ((g.off_a & 3u) << 5) | ((cb & 63u) << 8) | ((uint32_t)(m - nz) << 16) | ((uint32_t)padL << 21) | ((uint32_t)m << 24) |
-            ((uint32_t)(R - 1) << 29);
+            ((uint32_t)(R - 1) << 29) | ((g.off_b & 4096u) ? 0x80000000u : 0u);   // bit 31: layer 0 in the t form (its factor is in the table)
   r.xb = (uint32_t)(uint8_t)g.bits[R + 1] | ((uint32_t)(uint8_t)g.bits[R + 2] << 8) | (g.mat_bstride << 16);  // (stride <= 2^7 + 4)
   r.mat = g.mat_off;
   return r;
@@ -678,7 +678,8 @@ TQB_HD void chain_rot_sweep(cplx<T> *tile, uint64_t gbase, const RotDesc &rd, co
     if (!(f & (1u << 7)))
 #endif
     {
-      rot_layer<T, R, 0, TYPE, false>(v, a0, (TYPE == 1 && cv) ? -r0 : r0);
+      if (f >> 31) rot_layer_scaled<T, R, 0, TYPE, false>(v, (TYPE == 1 && cv) ? -a0 : a0, false);   // coef[0] = (t0, 0)
+      else rot_layer<T, R, 0, TYPE, false>(v, a0, (TYPE == 1 && cv) ? -r0 : r0);
       rot_layer_scaled<T, R, 1, TYPE, MUXED>(v, kk[1], inv[1]);
       if (R > 2) rot_layer_scaled<T, R, (R > 2 ? 2 : 1), TYPE, MUXED>(v, kk[R > 2 ? 2 : 1], inv[R > 2 ? 2 : 1]);
       if (R > 3) rot_layer_scaled<T, R, (R > 3 ? 3 : 1), TYPE, MUXED>(v, kk[R > 3 ? 3 : 1], inv[R > 3 ? 3 : 1]);

@@ -53,7 +53,8 @@ enum { K_DENSE1 = 0, K_DIAG = 1, K_MUX = 4, K_CHAIN = 5, K_ROT = 6 };
 struct SpecGate {
   int kind = 0, R = 0, type = 0, muxed = 0, unit_p = 0, E = 0, ctrl = -1, mat = 0, sync = 0;
   int msrc = 0, mlen = 0, mbs = 0;   // matrices: offset of member 0's data from the pass's first matrix, length, per-member stride
-  int inv = -1;           // rotation-form chains: bit i-1 = layer i runs in the c form (tqb_gate.off_b bits 8..10); -1 = decided at run time
+  int inv = -1;           // rotation-form chains: bit i-1 = layer i runs in the c form, bit 3 = layer 0 runs in the t form with its factor
+                          // in the table (tqb_gate.off_b bits 8..10, 12); -1 = decided at run time (bit 11 clear)
   int xb[2] = {-1, -1};
   int dbits[6] = {-1, -1, -1, -1, -1, -1};
   int rb[5] = {-1, -1, -1, -1, -1};
@@ -265,7 +266,8 @@ static bool spec_parse(const tqb_pass &ps, const tqb_gate *gh, int dtype, SpecPl
           s.muxed = (int)(q.off_a & 1u);
           s.E = (int)(q.off_b & 3u);
           s.unit_p = (q.off_b & 128u) ? 1 : 0;
-          s.inv = (q.off_b & 2048u) ? (int)((q.off_b >> 8) & 7u) : -1;
+          s.inv = (q.off_b & 2048u) ? (int)(((q.off_b >> 8) & 7u) | ((q.off_b & 4096u) ? 8u : 0u)) : -1;
+          if ((q.off_b & 4096u) && !(q.off_b & 2048u)) return why = "chain form bits", false;
           if (s.E > 2 || q.k + 1 + s.E > TQB_MAX_GATE_BITS) return why = "extra bits", false;
           for (int j = 0; j < s.E; ++j) {
             s.xb[j] = code(q.bits[q.k + 1 + j], ok);

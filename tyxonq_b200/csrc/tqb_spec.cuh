@@ -382,8 +382,9 @@ SPEC_DEV void apply_gate(char *tile, const amp *sm, unsigned tid, unsigned extv,
         v[s] = cmul(v[s], ((s & 1) ? Po : Pe)[s & ((1 << R) - 1)]);
       });
     }
-    rot_layer<0, TYPE, false>(v, a0, r0);
     constexpr int IV = G[GI].inv;
+    if constexpr (IV >= 0 && (IV & 8) != 0) rot_layer_scaled<0, TYPE, false, 0>(v, (TYPE == 1 && cv) ? -a0 : a0, false);   // coef[0] = (t0, 0)
+    else rot_layer<0, TYPE, false>(v, a0, r0);
     if constexpr (R > 1) rot_layer_scaled<(R > 1 ? 1 : 0), TYPE, MUXED, (IV < 0 ? -1 : (IV & 1))>(v, kk[1], inv[1]);
     if constexpr (R > 2) rot_layer_scaled<(R > 2 ? 2 : 0), TYPE, MUXED, (IV < 0 ? -1 : ((IV >> 1) & 1))>(v, kk[2], inv[2]);
     if constexpr (R > 3) rot_layer_scaled<(R > 3 ? 3 : 0), TYPE, MUXED, (IV < 0 ? -1 : ((IV >> 2) & 1))>(v, kk[3], inv[3]);
@@ -523,8 +524,9 @@ SPEC_BODY void rot_body(unsigned tb, const amp *P, const amp *coef, unsigned cv,
       v[s] = cmul(v[s], ((s & 1) ? Po : Pe)[s & ((1 << R) - 1)]);
     });
   }
-  rot_layer<0, TYPE, false>(v, a0, r0);
   constexpr int IV = G[REP].inv;
+  if constexpr (IV >= 0 && (IV & 8) != 0) rot_layer_scaled<0, TYPE, false, 0>(v, (TYPE == 1 && cv) ? -a0 : a0, false);   // coef[0] = (t0, 0)
+  else rot_layer<0, TYPE, false>(v, a0, r0);
   if constexpr (R > 1) rot_layer_scaled<(R > 1 ? 1 : 0), TYPE, MUXED, (IV < 0 ? -1 : (IV & 1))>(v, kk[1], inv[1]);
   if constexpr (R > 2) rot_layer_scaled<(R > 2 ? 2 : 0), TYPE, MUXED, (IV < 0 ? -1 : ((IV >> 1) & 1))>(v, kk[2], inv[2]);
   if constexpr (R > 3) rot_layer_scaled<(R > 3 ? 3 : 0), TYPE, MUXED, (IV < 0 ? -1 : ((IV >> 2) & 1))>(v, kk[3], inv[3]);

@@ -295,7 +295,7 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
     E = len(extra_bits)
     assert E <= 2
     unit = False
-    inv_bits = 0   # bit i-1: layer i runs in the c form; bit 3: the bits are valid (unbatched chains)
+    inv_bits = 0   # bit i-1: layer i runs in the c form; bit 3: the bits are valid; bit 4: layer 0 is scaled too (factor in the table)
     if rot is not None:
         typ, muxed, dec = rot
         if B == 1:   # plain Python complex arithmetic: the planner builds one of these per chain
@@ -328,7 +328,15 @@ def chain_gate(layers: Sequence[Tuple[int, np.ndarray, np.ndarray]], control_bit
                     scale *= ri
                     inv_bits |= 1 << (i - 1)
             inv_bits |= 8     # the forms are the same for every state of the batch: the specialised kernels compile them in
-            tab += [complex(float(dec[0][0][0]) * scale, float(dec[0][1][0]) * scale)] + coef
+            a0, r0 = float(dec[0][0][0]), float(dec[0][1][0])
+            if not unit and a0 != 0.0 and abs(a0) * ROT_T_MAX >= abs(r0):
+                # the table is multiplied in anyway: it takes layer 0's factor as well, and layer 0 runs in the t form
+                # (2 multiply-adds per amplitude instead of 4)
+                tab = [p * (a0 * scale) for p in tab]
+                tab += [complex(r0 / a0, 0.0)] + coef
+                inv_bits |= 16
+            else:
+                tab += [complex(a0 * scale, r0 * scale)] + coef
             data = np.array(tab, dtype=C128).reshape(1, -1)
         else:
             P = np.ones((B, 1 << R), dtype=C128)

@@ -335,7 +335,7 @@ def _pack(gates: Sequence[LGate], sched, n: int, tile: TileConfig, batch_mats: i
                     if r + 1 + j < 8:
                         e["bits"][r + 1 + j] = enc(g.bits[r + has_c + j]) if j < E else 127
                 e["off_a"] = g.pat_b & 15          # 0 = two matrices per layer; 4..7 = rotation form (tqb_core.cuh gate_chain_rot)
-                e["off_b"] = (E & 3) | (g.pat_b & 128) | (g.pat_b & 0xF00)   # extras, unit table, forms of the scaled layers
+                e["off_b"] = (E & 3) | (g.pat_b & 128) | (g.pat_b & 0x1F00)   # extras, unit table, forms of the scaled layers
                 zs = sorted(loc + ([ctrl] if ctrl < 64 else []))
                 for j, b in enumerate(zs):
                     e["sbits"][j] = b
