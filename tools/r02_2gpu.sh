@@ -2,7 +2,7 @@
 # 2 GPUs: sharded == unsharded check, reference arm under torchrun, bench line with config 4 extra
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533"
-echo skip check
+timeout 300 $TR tools/sharded_check.py 26 4 > gpurun_out/r02_sharded_check2.log 2>&1; echo "check rc=$?"; tail -4 gpurun_out/r02_sharded_check2.log
 echo skip ref
 timeout 900 $TR bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r02_bench2.json 2> gpurun_out/r02_bench2.err; echo "bench rc=$?"; tail -3 gpurun_out/r02_bench2.err
 python - <<'PY'
