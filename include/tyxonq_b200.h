@@ -110,6 +110,10 @@ const char *tqb_last_error(void);
 /* Allocates the per-device reduction workspace (call once per device before anything else). */
 int tqb_init(int device);
 int tqb_shutdown(int device);
+/* Reductions write partial sums into the device's workspace.  Calls that run concurrently on different streams
+ * (independent evaluations) must use different slices of it: the calling host thread selects slot `slot` of
+ * `n_slots` (<= 64) equal slices for everything it enqueues afterwards, graph captures included.  (0, 1) = whole. */
+int tqb_workspace_slot(int slot, int n_slots);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches).         */
 int64_t tqb_launch_count(void);
 /* max dynamic shared memory per CTA (bytes) and SM count of `device`.                        */

@@ -187,6 +187,18 @@ def test_ucc_batched_replicas(cuda_device):
     for b in (0, 3, 10):
         e, g = sv.energy_and_grad(P_[b])
         assert abs(es[b] - e) < 1e-12 and np.abs(gs[b] - g).max() < 1e-12
+    # the H2O-shaped problem, every member checked, for several replica counts (the energy is a two-stage reduction through
+    # the library's workspace: concurrent replicas must reduce into their own slices, tqb_workspace_slot)
+    i1, i2 = ucc.random_integral(7, 2077)
+    ex_ops, pids = ucc.uccsd_ex_ops(5, 2)
+    sv = ucc.UCCStatevector(14, (5, 5), ex_ops, pids, ucc.hamiltonian_from_integral(i1, i2), device=cuda_device)
+    P_ = rng.uniform(-0.5, 0.5, (48, 75))
+    ref = [sv.energy_and_grad(P_[b]) for b in range(48)]
+    for R in (4, 12, 16):
+        for _ in range(2):
+            es, gs = sv.energy_and_grad_batch(P_, replicas=R)
+            assert max(abs(es[b] - ref[b][0]) for b in range(48)) < 1e-12, R
+            assert max(np.abs(gs[b] - ref[b][1]).max() for b in range(48)) < 1e-12, R
 
 
 def test_b200_backend_value_and_grad(cuda_device):

@@ -68,6 +68,7 @@ SIGNATURES = {
     "tqb_init_basis": (_i, [_vp, _i, _i64, _i, _u64, _u64, _vp]),
     "tqb_run_passes": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "tqb_run_passes2": (_i, [_vp, _i, _i64, _i, _u64, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "tqb_workspace_slot": (_i, [_i, _i]),
     "tqb_set_jit": (_i, [_i]),
     "tqb_set_jit_cache": (_i, [C.c_char_p]),
     "tqb_jit_wait": (_i, []),

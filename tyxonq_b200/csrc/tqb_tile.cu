@@ -29,13 +29,24 @@ int fail(const std::string &msg) {
   t_err = msg;
   return -1;
 }
+// The reduction kernels write their partial sums into the device's workspace; calls that run CONCURRENTLY on different
+// streams (independent evaluations, e.g. the replicas of ucc.energy_and_grad_batch) must not share it.  A host thread
+// selects slot k of K equal slices (tqb_workspace_slot); everything it enqueues afterwards -- CUDA-graph captures
+// included, the pointers are baked in -- uses that slice.
+static thread_local int t_ws_slot = 0, t_ws_slots = 1;
 Workspace *workspace() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || g_ws[dev].ptr == nullptr) {
     set_error("tqb_init(device) has not been called for the current device");
     return nullptr;
   }
-  return &g_ws[dev];
+  if (t_ws_slots <= 1) return &g_ws[dev];
+  static thread_local Workspace view;
+  view = g_ws[dev];
+  const size_t slice = (view.bytes / (size_t)t_ws_slots) & ~(size_t)255;
+  view.ptr = static_cast<char *>(view.ptr) + slice * (size_t)t_ws_slot;
+  view.bytes = slice;
+  return &view;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -575,6 +586,13 @@ int tqb_init(int device) {
   TQB_CHECK_CUDA(cudaMalloc(&w.ptr, w.bytes));
   g_ws[device] = w;
   TQB_CHECK_CUDA(cudaSetDevice(cur));
+  return 0;
+}
+
+int tqb_workspace_slot(int slot, int n_slots) {
+  TQB_REQUIRE(n_slots >= 1 && n_slots <= 64 && slot >= 0 && slot < n_slots, "tqb_workspace_slot: bad arguments (1 <= n_slots <= 64)");
+  t_ws_slot = slot;
+  t_ws_slots = n_slots;
   return 0;
 }
 

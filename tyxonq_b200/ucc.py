@@ -353,17 +353,24 @@ class UCCStatevector:
         elif self._proto:
             self._fwd_dev.fill_host(self._fill(self._fwd, params, False))
             self._rev_dev.fill_host(self._fill(self._rev, params, True))
+        slot, n_slots = getattr(self, "_ws_slot", (0, 1))
+        lib = _lib.load()
         with torch.cuda.device(self.device):
-            if graph and self._graph is None and self._calls >= 1:
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+            # concurrent replicas (energy_and_grad_batch) reduce into their own slices of the library's workspace
+            _lib.check(lib.tqb_workspace_slot(slot, n_slots))
+            try:
+                if graph and self._graph is None and self._calls >= 1:
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._enqueue()
+                    self._graph = g
+                if graph and self._graph is not None:
+                    self._graph.replay()
+                else:
                     self._enqueue()
-                self._graph = g
-            if graph and self._graph is not None:
-                self._graph.replay()
-            else:
-                self._enqueue()
+            finally:
+                lib.tqb_workspace_slot(0, 1)
             self._calls += 1
             self._out_host.copy_(self._out, non_blocking=True)
             if not _sync:
@@ -372,18 +379,27 @@ class UCCStatevector:
         out = self._out_host.numpy()
         return float(out[0]), out[1:1 + self.n_params].copy()
 
-    def energy_and_grad_batch(self, params: np.ndarray, *, replicas: int = 8) -> Tuple[np.ndarray, np.ndarray]:
+    MAX_REPLICAS = 32   # slices of the reduction workspace (tqb_workspace_slot)
+
+    def energy_and_grad_batch(self, params: np.ndarray, *, replicas: int = 16) -> Tuple[np.ndarray, np.ndarray]:
         """Many parameter vectors ([B, n_params] -> energies [B], gradients [B, n_params]).  An evaluation of a small
         molecule is a chain of ~300 dependent steps on 16 CTAs (latency, not throughput), so ``replicas`` independent
         evaluations run CONCURRENTLY: each replica has its own state buffers, stream and CUDA graph, the persistent sweep
-        kernels of different replicas share the device (16 of 148 SMs each)."""
+        kernels of different replicas share the device (16 CTAs each), and every replica reduces into its own slice of the
+        library's workspace (tqb_workspace_slot: the partial sums of <ket|bra> must not be shared between streams)."""
         p = np.asarray(params, dtype=np.float64).reshape(-1, max(self.n_params, 1))
         B = p.shape[0]
-        R = max(1, min(int(replicas), B))
+        R = max(1, min(int(replicas), B, self.MAX_REPLICAS))
         if not hasattr(self, "_replicas") or len(self._replicas) < R:
             self._replicas = [self] + [UCCStatevector(self.n, self.n_elec_s, self.ex_ops, self.param_ids, self.ham, mode=self.mode,
                                                      device=self.device, dtype=self.dtype, tile=self.tile) for _ in range(R - 1)]
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(R)]
+            for r, rep in enumerate(self._replicas):
+                if getattr(rep, "_ws_slot", None) != (r, self.MAX_REPLICAS):   # (graphs bake the slice in: re-capture on change)
+                    rep._ws_slot = (r, self.MAX_REPLICAS)
+                    rep._graph = None
+                    if hasattr(rep, "_calls"):
+                        rep._calls = 0
             for r, (rep, st) in enumerate(zip(self._replicas, self._streams)):   # warm up + capture each replica's graph on ITS stream
                 with torch.cuda.stream(st):
                     rep.energy_and_grad(p[0])
