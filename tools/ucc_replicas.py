@@ -11,7 +11,7 @@ ex_ops, pids = ucc.uccsd_ex_ops(5, 2)
 sv = ucc.UCCStatevector(14, (5, 5), ex_ops, pids, ucc.hamiltonian_from_integral(i1, i2), device=dev)
 p = np.random.default_rng(5).uniform(-0.5, 0.5, (96, 75))
 ref = None
-for R in (1, 4, 8, 12, 16):
+for R in (1, 8, 16, 24, 32):
     sv.energy_and_grad_batch(p[:R], replicas=R)
     t0 = time.perf_counter()
     es, gs = sv.energy_and_grad_batch(p, replicas=R)

@@ -275,13 +275,18 @@ __global__ void __launch_bounds__(RT) apply_pauli_kernel(const cplx<T> *__restri
                                                          uint64_t global_base, const uint64_t *__restrict__ group_x,
                                                          const int *__restrict__ group_ptr, int n_groups,
                                                          const uint64_t *__restrict__ term_z,
-                                                         const double *__restrict__ term_coef) {
+                                                         const double *__restrict__ term_coef, int groups_per_slice) {
+  // groups_per_slice > 0 (small states: too few amplitudes to fill the device): blockIdx.z takes a slice of the x-mask
+  // groups and ADDS its part into `out` (zeroed by the host) -- 554 groups of a molecular Hamiltonian on 2^14 amplitudes
+  // were one serial loop per thread on 64 CTAs
   const cplx<T> *sb = state + ((size_t)blockIdx.y << n);
   cplx<T> *ob = out + ((size_t)blockIdx.y << n);
   const size_t dim = (size_t)1 << n;
+  const int g0 = groups_per_slice > 0 ? (int)blockIdx.z * groups_per_slice : 0;
+  const int g1 = groups_per_slice > 0 ? (g0 + groups_per_slice < n_groups ? g0 + groups_per_slice : n_groups) : n_groups;
   for (size_t j = (size_t)blockIdx.x * RT + threadIdx.x; j < dim; j += (size_t)gridDim.x * RT) {
     double hr = 0.0, hi = 0.0;
-    for (int g = 0; g < n_groups; ++g) {
+    for (int g = g0; g < g1; ++g) {
       const uint64_t src = j ^ group_x[g];
       double pr, pi;
       group_phase(term_z, term_coef, group_ptr[g], group_ptr[g + 1], global_base | src, pr, pi);
@@ -290,7 +295,12 @@ __global__ void __launch_bounds__(RT) apply_pauli_kernel(const cplx<T> *__restri
       hr += br * pr - bi * pi;
       hi += br * pi + bi * pr;
     }
-    ob[j] = cplx<T>{(T)hr, (T)hi};
+    if (groups_per_slice > 0) {
+      atomicAdd(&ob[j].x, (T)hr);
+      atomicAdd(&ob[j].y, (T)hi);
+    } else {
+      ob[j] = cplx<T>{(T)hr, (T)hi};
+    }
   }
 }
 
@@ -710,6 +720,60 @@ __global__ void __launch_bounds__(RT) pair_sweep_kernel(cplx<T> *ket, cplx<T> *b
   }
 }
 
+// The same sweep for registers of <= 15 qubits in ONE CTA of 1024 threads: a step has at most 2^13 independent groups (8 per
+// thread), so the barrier between two dependent steps is a __syncthreads() (tens of cycles) instead of a grid barrier
+// through global atomics (~2 us), the next step's descriptor is fetched while the current one computes, and an evaluation
+// occupies one SM -- many independent evaluations run side by side (ucc.energy_and_grad_batch).
+constexpr int SWEEP_CTA = 1024;
+template <typename T>
+__global__ void __launch_bounds__(SWEEP_CTA, 1) pair_sweep_cta_kernel(cplx<T> *ket, cplx<T> *bra, int n, const tqb_pair_step *__restrict__ steps,
+                                                                     int n_steps, int mode, double *out) {
+  __shared__ double sm[2][SWEEP_CTA / 32];   // per-warp partial sums, double-buffered over the steps
+  __shared__ tqb_pair_step st2[2];
+  const int tid = threadIdx.x;
+  constexpr int WORDS = (int)(sizeof(tqb_pair_step) / 4);
+  if (tid < WORDS) reinterpret_cast<uint32_t *>(&st2[0])[tid] = reinterpret_cast<const uint32_t *>(steps)[tid];
+  __syncthreads();
+  for (int j = 0; j < n_steps; ++j) {
+    const tqb_pair_step &st = st2[j & 1];
+    if (j + 1 < n_steps && tid < WORDS)   // (slot (j + 1) & 1 was last read in step j - 1, before the barrier that ended it)
+      reinterpret_cast<uint32_t *>(&st2[(j + 1) & 1])[tid] = reinterpret_cast<const uint32_t *>(steps + j + 1)[tid];
+    const int k = st.k;
+    const uint32_t ngroups = 1u << (n - k);
+    const double c = st.c, s = st.s;
+    double v = 0.0;
+    for (uint32_t g = tid; g < ngroups; g += SWEEP_CTA) {
+      const uint64_t base = insert_zeros64(g, st.sbits, k);
+      const uint64_t ia = base + st.off_a, ib = base + st.off_b;
+      const bool odd = __popcll(base & st.zmask) & 1;
+      const double sg = odd ? -s : s;
+      cplx<T> ka = ket[ia], kb = ket[ib];
+      if (mode == 1) {
+        cplx<T> ba = bra[ia], bb = bra[ib];
+        double r = ((double)ba.x * kb.x + (double)ba.y * kb.y) - ((double)bb.x * ka.x + (double)bb.y * ka.y);
+        v += odd ? -r : r;
+        bra[ia] = cplx<T>{(T)(c * ba.x - sg * bb.x), (T)(c * ba.y - sg * bb.y)};
+        bra[ib] = cplx<T>{(T)(sg * ba.x + c * bb.x), (T)(sg * ba.y + c * bb.y)};
+      }
+      ket[ia] = cplx<T>{(T)(c * ka.x - sg * kb.x), (T)(c * ka.y - sg * kb.y)};
+      ket[ib] = cplx<T>{(T)(sg * ka.x + c * kb.x), (T)(sg * ka.y + c * kb.y)};
+    }
+    if (mode == 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0) sm[j & 1][tid >> 5] = v;
+    }
+    __syncthreads();   // the step's writes (global memory and sm[]) are visible to the CTA; st2[(j + 1) & 1] is loaded
+    if (mode == 1 && tid < 32) {
+      double t = sm[j & 1][tid];   // (rewritten in step j + 2, after the barrier of step j + 1 that this warp takes part in)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      if (tid == 0 && t != 0.0) out[st.slot] += st.scale * t;   // (one CTA owns `out` during the sweep)
+    }
+  }
+}
+
+
 // ---- projection / scaling / probabilities ----------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(RT) project_kernel(cplx<T> *state, Seg sg, int bit, int keep, double *partial) {
@@ -1122,11 +1186,25 @@ int tqb_apply_pauli_sum(const void *state, void *out, int n, int64_t batch, int 
   size_t bx = (dim + RT - 1) / RT;
   const size_t cap = (size_t)ws->sm_count * 16;
   if (bx > cap) bx = cap;
-  dim3 grid((unsigned)bx, (unsigned)batch);
   cudaStream_t st = as_stream(stream);
+  // small states: slices of the groups on blockIdx.z until ~4 CTAs per SM are in flight
+  int slices = 1, gps = 0;
+  const size_t ctas = bx * (size_t)batch, want = (size_t)ws->sm_count * 4;
+  if (ctas < want && n_groups >= 8) {
+    slices = (int)((want + ctas - 1) / ctas);
+    if (slices > 32) slices = 32;
+    if (slices > n_groups / 4) slices = n_groups / 4;
+    if (slices > 1) {
+      gps = (n_groups + slices - 1) / slices;
+      slices = (n_groups + gps - 1) / gps;
+      TQB_CHECK_CUDA(cudaMemsetAsync(out, 0, ((size_t)batch << n) * (dtype == TQB_C128 ? 16 : 8), st));
+    }
+  }
+  dim3 grid((unsigned)bx, (unsigned)batch, (unsigned)(slices > 1 ? slices : 1));
+  if (slices <= 1) gps = 0;
   if (by_dtype(dtype,
-               [&] { apply_pauli_kernel<double><<<grid, RT, 0, st>>>(CD(state), MD(out), n, global_base, group_x, group_ptr, n_groups, term_z, term_coef); },
-               [&] { apply_pauli_kernel<float><<<grid, RT, 0, st>>>(CF(state), MF(out), n, global_base, group_x, group_ptr, n_groups, term_z, term_coef); }))
+               [&] { apply_pauli_kernel<double><<<grid, RT, 0, st>>>(CD(state), MD(out), n, global_base, group_x, group_ptr, n_groups, term_z, term_coef, gps); },
+               [&] { apply_pauli_kernel<float><<<grid, RT, 0, st>>>(CF(state), MF(out), n, global_base, group_x, group_ptr, n_groups, term_z, term_coef, gps); }))
     return -1;
   TQB_CHECK_LAUNCH("apply_pauli_kernel");
   return 0;
@@ -1266,6 +1344,14 @@ int tqb_pair_sweep(void *ket, void *bra, int n, int dtype, const tqb_pair_step *
   Workspace *ws = workspace();
   if (!ws) return -1;
   cudaStream_t st = as_stream(stream);
+  if (n <= 15) {   // one CTA: barriers are __syncthreads()
+    if (by_dtype(dtype,
+                 [&] { pair_sweep_cta_kernel<double><<<1, SWEEP_CTA, 0, st>>>(MD(ket), MD(bra), n, steps_dev, n_steps, mode, out_dev); },
+                 [&] { pair_sweep_cta_kernel<float><<<1, SWEEP_CTA, 0, st>>>(MF(ket), MF(bra), n, steps_dev, n_steps, mode, out_dev); }))
+      return -1;
+    TQB_CHECK_LAUNCH("pair_sweep_cta_kernel");
+    return 0;
+  }
   TQB_CHECK_CUDA(cudaMemsetAsync(sync_dev, 0, sizeof(unsigned long long), st));
   // all CTAs must be co-resident for the grid barrier: one CTA per SM at most
   uint64_t want = ((1ull << (n > 2 ? n - 2 : 0)) + RT - 1) / RT;

@@ -381,11 +381,12 @@ class UCCStatevector:
 
     MAX_REPLICAS = 32   # slices of the reduction workspace (tqb_workspace_slot)
 
-    def energy_and_grad_batch(self, params: np.ndarray, *, replicas: int = 16) -> Tuple[np.ndarray, np.ndarray]:
+    def energy_and_grad_batch(self, params: np.ndarray, *, replicas: int = 32) -> Tuple[np.ndarray, np.ndarray]:
         """Many parameter vectors ([B, n_params] -> energies [B], gradients [B, n_params]).  An evaluation of a small
-        molecule is a chain of ~300 dependent steps on 16 CTAs (latency, not throughput), so ``replicas`` independent
+        molecule is a chain of ~300 dependent steps (latency, not throughput: the sweeps of a register of <= 15 qubits run in ONE
+        CTA whose barrier is __syncthreads, pair_sweep_cta_kernel), so ``replicas`` independent
         evaluations run CONCURRENTLY: each replica has its own state buffers, stream and CUDA graph, the persistent sweep
-        kernels of different replicas share the device (16 CTAs each), and every replica reduces into its own slice of the
+        kernels of different replicas share the device, and every replica reduces into its own slice of the
         library's workspace (tqb_workspace_slot: the partial sums of <ket|bra> must not be shared between streams)."""
         p = np.asarray(params, dtype=np.float64).reshape(-1, max(self.n_params, 1))
         B = p.shape[0]
