@@ -589,7 +589,6 @@ def extras(dev, quick: bool = False) -> dict:
     dt = float(np.median(ts))
     # bytes an evaluation must move if the 256 KiB ket / bra stayed on chip: none -- the bound is the latency of 2 x 140
     # dependent pair rotations + H|psi>; reported as time per dependent step
-    pbatch = np.random.default_rng(5).uniform(-0.5, 0.5, (64, 75))
     pbatch = np.random.default_rng(5).uniform(-0.5, 0.5, (128, 75))
     sv.energy_and_grad_batch(pbatch[:32], replicas=32)
     t0 = time.perf_counter()
