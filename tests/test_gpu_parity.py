@@ -424,6 +424,17 @@ def test_specialised_kernels_match_oracle(cuda_device):
                 out = ba.run(params).cpu().numpy()
                 assert _lib.jit_stats()["spec_launches"] - before == ba.passes, "per-member passes must run specialised kernels"
                 assert np.abs(out - refs).max() < tol, (td, shape, np.abs(out - refs).max())
+                if shape == 1:   # later calls rewrite the matrix buffer of the resident program (batched.HweRyRefill)
+                    params2 = rng.uniform(-3.0, 3.0, params.shape)
+                    refs2 = np.stack([O.evolve_ops(nq, O.hwe_ry_ops(nq, layers, params2[b]))[0] for b in range(B)])
+                    for pp, rr in ((params2, refs2), (params, refs), (params2, refs2)):
+                        assert np.abs(ba.run(pp).cpu().numpy() - rr).max() < tol
+                    assert ba.fast_calls == 3, ba.fast_calls
+                    params3 = params2.copy()
+                    params3[3, :] = np.pi - 1e-7    # a member outside the recipe's domain: that call is lowered generically
+                    refs3 = np.stack([O.evolve_ops(nq, O.hwe_ry_ops(nq, layers, params3[b]))[0] for b in range(B)])
+                    assert np.abs(ba.run(params3).cpu().numpy() - refs3).max() < tol * 10 and ba.fast_calls == 3
+                    assert np.abs(ba.run(params2).cpu().numpy() - refs2).max() < tol and ba.fast_calls == 4
     finally:
         lib.tqb_set_jit(1024 + 2)
         lib.tqb_set_jit(512 + 1)

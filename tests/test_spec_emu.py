@@ -119,6 +119,34 @@ def test_spec_per_member_matrices(dtype, m, L):
         assert np.abs(out.reshape(B, -1)[b] - ref).max() < (1e-12 if dtype == np.complex128 else 3e-5), b
 
 
+def test_batched_ansatz_refill_equals_generic_lowering():
+    """batched.HweRyRefill (the matrix buffer of the batched HWE-RY program written directly from the parameters, recipe
+    derived by probing the generic pipeline) against the generic lowering: equal buffers for angles all over (-3, 3), in
+    place into a complex64 staging buffer, and a refusal when a scaled layer needs the c form."""
+    from tyxonq_b200.batched import HweRyRefill, hwe_ry_gates
+    from tyxonq_b200.planner import default_tile
+    for n, layers, B, itemsize in ((14, 2, 5, 16), (20, 4, 16, 8)):
+        tile = default_tile(n, itemsize, B)
+        rng = np.random.default_rng(n)
+        p0 = rng.random((B, (layers + 1) * n))
+        prog = compile_program(fuse(hwe_ry_gates(n, layers, p0)), n, tile, batch_mats=B, itemsize=itemsize)
+        rf = HweRyRefill(n, layers, prog, B, tile, itemsize)
+        assert rf.ok
+        buf = rf.mats(p0).astype(np.complex64 if itemsize == 8 else np.complex128)
+        assert np.abs(rf.mats(p0) - prog.mats).max() < 1e-13
+        for _ in range(3):
+            p = rng.uniform(-3.0, 3.0, p0.shape)
+            ref = compile_program(fuse(hwe_ry_gates(n, layers, p)), n, tile, batch_mats=B, itemsize=itemsize)
+            assert np.array_equal(ref.gates, prog.gates) and np.array_equal(ref.passes, prog.passes), "the plan must not depend on the angles"
+            assert np.abs(rf.mats(p) - ref.mats).max() < 1e-13
+            assert rf.mats(p, out=buf) is buf
+            assert np.abs(buf - ref.mats.astype(buf.dtype)).max() < (1e-6 if itemsize == 8 else 1e-13)
+        p = rng.uniform(-3.0, 3.0, p0.shape)
+        p[B - 1, :] = np.pi - 1e-7              # |tan(theta / 2)| > gates.ROT_T_MAX in every scaled layer of one member
+        before = buf.copy()
+        assert rf.mats(p, out=buf) is None and np.array_equal(before, buf), "a refused call must leave the buffer alone"
+
+
 def test_generator_invariants():
     """Register bits and thread bits partition the tile; a warp-level sync is only used between gates that share the
     warp bits; 'no sync' only between gates with the same mapping; the first gate waits for the tile."""

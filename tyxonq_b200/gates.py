@@ -226,6 +226,8 @@ def rot_decompose(u: np.ndarray) -> Dict[int, Tuple[np.ndarray, np.ndarray, np.n
             continue
         d0 = np.where(big, u00 / sa, u10 / (f10 * sr))
         d1 = np.where(big, u11 / sa, u01 / (f01 * sr))
+        neg = (np.abs(d0 + 1.0) < 1e-14) & (np.abs(d1 + 1.0) < 1e-14)   # M.(-1) = (-M).1: keep the table a unit table
+        d0, d1 = np.where(neg, 1.0 + 0.0j, d0), np.where(neg, 1.0 + 0.0j, d1)
         with np.errstate(all="ignore"):                       # a zero d0 fails the |d| = 1 check below
             a = (u00 / d0).real
             r = (u10 / (f10 * d0)).real
@@ -249,6 +251,8 @@ def _rot_decompose_scalar(u00: complex, u01: complex, u10: complex, u11: complex
             d0, d1 = u10 / (f10 * rv), u01 / (f01 * rv)
         if abs(abs(d0) - 1) > 1e-13 or abs(abs(d1) - 1) > 1e-13:
             continue
+        if abs(d0 + 1.0) < 1e-14 and abs(d1 + 1.0) < 1e-14:   # M.(-1) = (-M).1: keep the table a unit table
+            d0 = d1 = 1.0 + 0.0j
         a = (u00 / d0).real
         r = (u10 / (f10 * d0)).real
         if max(abs(a * d0 - u00), abs(f01 * r * d1 - u01), abs(f10 * r * d0 - u10), abs(a * d1 - u11)) < 1e-13:
