@@ -306,6 +306,52 @@ def test_pauli_sum_tiled_many_terms_per_group(cuda_device):
             assert abs(got[b] - ref) < tol * 4, (n, dt, herm, b, got[b], ref)
 
 
+def test_pauli_sum_tiled_vanishing_half(cuda_device):
+    """Two-term groups whose sign sum vanishes on half of the pairs (XX + YY and XX - YY bonds, hopping terms X Z..Z X +
+    Y Z..Z Y, and pairs whose Z decorations reach OUTSIDE the tile so that the vanishing half changes from tile to tile),
+    next to pairs with unequal weights that must take the general loop."""
+    import torch
+    from tyxonq_b200 import PauliSum
+    rng = np.random.default_rng(31)
+    for n, dt, tol in ((12, torch.complex128, TOL128), (17, torch.complex128, TOL128), (18, torch.complex64, 2e-5)):
+        terms, w = [], []
+
+        def add(ops, c):
+            t = [0] * n
+            for q, p in ops:
+                t[q] = p
+            terms.append(t)
+            w.append(c)
+
+        for i in range(n - 1):                       # Heisenberg-like bonds, equal and opposite weights
+            c = float(rng.normal())
+            add([(i, 1), (i + 1, 1)], c)
+            add([(i, 2), (i + 1, 2)], c if i % 3 else -c)
+        for i, j in ((0, 3), (2, n - 1), (5, 9), (1, n - 2)):   # hopping terms with a Z string in between
+            c = float(rng.normal())
+            zs = [(q, 3) for q in range(i + 1, j)]
+            add([(i, 1), (j, 1)] + zs, c)
+            add([(i, 2), (j, 2)] + zs, c)
+        for i, j, k in ((0, 1, n - 1), (3, 4, n - 2), (6, 2, n - 1)):   # the two terms differ by a Z far away (outside most tiles)
+            c = float(rng.normal())
+            add([(i, 1), (j, 1), (k, 3)], c)
+            add([(i, 2), (j, 2)], c)
+        for i in range(0, n - 1, 2):                 # unequal weights: nothing vanishes
+            add([(i, 1), (i + 1, 2)], float(rng.normal()))
+            add([(i, 2), (i + 1, 1)], float(rng.normal()))
+        ham = PauliSum.from_codes(terms, w)
+        B = 2
+        st = rng.normal(size=(B, 1 << n)) + 1j * rng.normal(size=(B, 1 << n))
+        st /= np.linalg.norm(st, axis=1, keepdims=True)
+        d = torch.from_numpy(st).to(cuda_device).to(dt)
+        got = ham.expectation(d, tiled=True).cpu().numpy()
+        old = ham.expectation(d, tiled=False).cpu().numpy()
+        for b in range(B):
+            ref = O.expect_pauli_sum(st[b], terms, w)
+            assert abs(got[b] - ref) < tol * 4, (n, dt, b, got[b], ref)
+            assert abs(old[b] - ref) < tol * 4
+
+
 def test_tfim_vqe_energy(cuda_device):
     """examples/vqetfim_benchmark.py exact_energy on the device vs the oracle restatement."""
     from tyxonq_b200.vqe import TFIMVqe

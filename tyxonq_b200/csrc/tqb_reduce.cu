@@ -329,6 +329,29 @@ __device__ __forceinline__ double flip_sign(double c, uint32_t v) {
 
 template <typename R> struct Pair2 { R x, y; };
 
+// Enumeration of the tile indices whose bits `holes` are clear: thread t visits the (t + i * RT)-th such index for
+// i = 0 .. iters - 1.  The first index is computed by zero insertion, every next one by ONE add that carries across the
+// holes: e' = ((e | holes) + step) & ~holes with step = the image of RT (RT is a power of two, so the thread part of the
+// counter never changes).  body(e) gets the index; the trip count is uniform over the CTA.
+__device__ __forceinline__ uint32_t insert_holes(uint32_t x, uint32_t holes) {
+  while (holes) {
+    const uint32_t p = (uint32_t)(__ffs((int)holes) - 1);
+    x = ((x >> p) << (p + 1u)) | (x & ((1u << p) - 1u));
+    holes &= holes - 1u;
+  }
+  return x;
+}
+template <class Body>
+__device__ __forceinline__ void for_indices(uint32_t holes, uint32_t iters, Body body) {
+  uint32_t e = insert_holes(threadIdx.x, holes);
+  const uint32_t step = insert_holes((uint32_t)RT, holes);
+#pragma unroll 4
+  for (uint32_t i = 0; i < iters; ++i) {
+    body(e);
+    e = ((e | holes) + step) & ~holes;
+  }
+}
+
 // Arithmetic type R = the state's component type (complex64 states: float products and float partial sums over the few
 // iterations a thread spends on one group of one tile, added to the float64 accumulator once per group and tile).
 template <typename T, bool HERM, bool REALC>   // REALC: every coefficient (i^#Y folded in) is real
@@ -352,7 +375,9 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
   // bits, a table over the high ones and the few terms whose z-mask straddles the split (listed in sst)
   constexpr int LB = 7;
   int *sst = sgp + pt.ng + 2;
-  Pair2<R> *sd = reinterpret_cast<Pair2<R> *>((reinterpret_cast<uintptr_t>(sst + nt) + 15u) & ~(uintptr_t)15u);   // [0, 128): low table, [128, 256): high
+  // [0, 128): low table, [128, 256): high table; 16-byte aligned by OFFSET arithmetic (the address space stays known: LDS)
+  const uint32_t sd_off = (uint32_t)((reinterpret_cast<unsigned char *>(sst + nt) - smem_raw) + 15) & ~15u;
+  Pair2<R> *sd = reinterpret_cast<Pair2<R> *>(smem_raw + sd_off);
   __shared__ int sst_n;
   const int tid = threadIdx.x;
   for (uint32_t j = tid; j < (1u << h); j += RT) {
@@ -394,21 +419,65 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
       const bool paired = HERM && xl != 0u;
       // a Hermitian group visits each pair (e, e ^ x) once: e runs over the indices with the lowest xmask bit clear
       const uint32_t pbit = paired ? (uint32_t)(__ffs((int)xl) - 1) : 0u;
-      const uint32_t plow = (1u << pbit) - 1u;
+      const uint32_t phole = paired ? 1u << pbit : 0u;
       const uint32_t count = paired ? nel >> 1 : nel;
       R sr = 0, si = 0;
-      if (REALC && a1 - a0 <= 2) {
+      // visit the `nitems` tile indices whose `holes` bits are clear (for_indices: one add per index, uniform trip count;
+      // tiles smaller than 4 * RT amplitudes take the plain loop)
+      auto visit = [&](uint32_t holes, uint32_t nitems, auto body) {
+        if (nel >= 4u * RT) {
+          for_indices(holes, nitems / RT, body);
+        } else {
+          for (uint32_t k = tid; k < nitems; k += RT) body(insert_holes(k, holes));
+        }
+      };
+      // Two real terms whose z-masks differ in ONE tile bit j (XX + YY of a bond, hopping terms X Z..Z X + Y Z..Z Y): the
+      // sign sum is (cn + cj (-1)^e_j) (-1)^popc(e & zc).  With |cn| = |cj| it vanishes on half of the pairs -- those are not
+      // visited at all, and the other half shares one coefficient.  (Decided per tile: the signs of the outside-the-tile
+      // bits are in sc[].)
+      bool half_done = false;
+      if (REALC && HERM && paired && a1 - a0 == 2) {
+        const uint32_t pm = ~(1u << pbit);
+        const uint32_t za = szl[a0] & pm, zb = szl[a0 + 1] & pm, dz = za ^ zb;
+        if (__popc(dz) == 1) {
+          const uint32_t jb = (uint32_t)(__ffs((int)dz) - 1);
+          const bool a_has = (za >> jb) & 1u;
+          const R cj = a_has ? sc[a0].x : sc[a0 + 1].x, cn = a_has ? sc[a0 + 1].x : sc[a0].x;
+          const R v0 = cn + cj, v1 = cn - cj;
+          if (v0 == (R)0 || v1 == (R)0) {
+            const uint32_t fix = v0 == (R)0 ? 1u << jb : 0u;   // bit j of the pairs that contribute
+            const R C = v0 == (R)0 ? v1 : v0;
+            const uint32_t zc = za & zb;
+            const uint32_t holes = phole | (1u << jb);
+            if (zc == 0u) {
+              visit(holes, nel >> 2, [&](uint32_t e0) {
+                const uint32_t e = e0 | fix;
+                const cplx<T> a = tile[e], b = tile[e ^ xl];
+                sr += b.x * a.x + b.y * a.y;
+              });
+            } else {
+              visit(holes, nel >> 2, [&](uint32_t e0) {
+                const uint32_t e = e0 | fix;
+                const cplx<T> a = tile[e], b = tile[e ^ xl];
+                sr += flip_sign(b.x * a.x + b.y * a.y, e & zc);
+              });
+            }
+            sr *= C;
+            half_done = true;
+          }
+        }
+      }
+      if (half_done) {
+      } else if (REALC && a1 - a0 <= 2) {
         // one or two real terms (XX + YY of a Heisenberg bond, a single string): everything in registers
         const R c0 = sc[a0].x, c1 = a1 - a0 == 2 ? sc[a0 + 1].x : (R)0;
         const uint32_t z0 = szl[a0], z1 = a1 - a0 == 2 ? szl[a0 + 1] : 0u;
-#pragma unroll 4
-        for (uint32_t k = tid; k < count; k += RT) {
-          const uint32_t e = paired ? (((k & ~plow) << 1) | (k & plow)) : k;
+        visit(phole, count, [&](uint32_t e) {
           const R pr = flip_sign(c0, e & z0) + flip_sign(c1, e & z1);
           const cplx<T> a = tile[e], b = tile[e ^ xl];
           sr += (b.x * a.x + b.y * a.y) * pr;
           if (!HERM) si += (b.x * a.y - b.y * a.x) * pr;
-        }
+        });
       } else {
         // tables of the sign sum for this tile (the signs of the outside-the-tile bits are already in sc[])
         const uint32_t lowmask = m > LB ? (1u << LB) - 1u : nel - 1u;
@@ -444,12 +513,14 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
         __syncthreads();
         const int nst = sst_n;
         const bool diag = xl == 0u;
-#pragma unroll 2
-        for (uint32_t k = tid; k < count; k += RT) {
-          const uint32_t e = paired ? (((k & ~plow) << 1) | (k & plow)) : k;
+        // the first two straddling terms live in registers (a nearest-neighbour chain has one), the rest in a loop
+        const Pair2<R> s0c = nst > 0 ? sc[sst[0]] : Pair2<R>{(R)0, (R)0}, s1c = nst > 1 ? sc[sst[1]] : Pair2<R>{(R)0, (R)0};
+        const uint32_t s0z = nst > 0 ? szl[sst[0]] : 0u, s1z = nst > 1 ? szl[sst[1]] : 0u;
+        visit(phole, count, [&](uint32_t e) {
           const Pair2<R> dl = sd[e & lowmask], dh = sd[128u + (m > LB ? e >> LB : 0u)];
-          R pr = dl.x + dh.x, pi = dl.y + dh.y;
-          for (int i = 0; i < nst; ++i) {
+          R pr = dl.x + dh.x + flip_sign(s0c.x, e & s0z) + flip_sign(s1c.x, e & s1z), pi = dl.y + dh.y;
+          if (!REALC) pi += flip_sign(s0c.y, e & s0z) + flip_sign(s1c.y, e & s1z);
+          for (int i = 2; i < nst; ++i) {
             const int t = sst[i];
             const Pair2<R> c = sc[t];
             const uint32_t v = e & szl[t];
@@ -465,7 +536,7 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
             sr += qr * pr - qi * pi;
             if (!HERM) si += qr * pi + qi * pr;
           }
-        }
+        });
       }
       const double w = paired ? 2.0 : 1.0;
       acc[0] += w * (double)sr;
