@@ -9,6 +9,7 @@
 //   apply_op (densified sparse H)           applications/chem/chem_libs/hamiltonians_chem_library/hamiltonian_builders.py:283-318
 //   _project_z                              devices/simulators/statevector/engine.py:1075-1087
 //   sampling (Generator.choice + bincount)  devices/simulators/statevector/engine.py:377-418
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
 #include <string>
@@ -399,17 +400,21 @@ __global__ void __launch_bounds__(RT) expect_pauli_tiled_kernel(const cplx<T> *_
       base = ((base >> p) << (p + 1u)) | (base & ((1ull << p) - 1ull));
     }
     __syncthreads();   // the previous tile is done with tile[] / sc[]
+    // the tile: 16-byte asynchronous copies global -> shared (LDGSTS), all of a thread's copies in flight at once -- the
+    // staged loop through registers kept ~4 loads per thread in flight and paid four memory round trips per tile
     for (uint32_t i = tid; i < nel / V; i += RT) {
       const uint32_t e = i * V;
       const uint64_t idx = base | roff[e >> L] | (uint64_t)(e & ((1u << L) - 1u));
-      *reinterpret_cast<cvec<T, V> *>(tile + e) = *reinterpret_cast<const cvec<T, V> *>(sb + idx);
+      __pipeline_memcpy_async(tile + e, sb + idx, 16);
     }
+    __pipeline_commit();
     const uint64_t gidx = global_base | base;
     for (int t = tid; t < nt; t += RT) {
       const bool odd = __popcll(gidx & zout[t0 + t]) & 1;
       const double cr = coef[2 * (t0 + t)], ci = coef[2 * (t0 + t) + 1];
       sc[t] = odd ? Pair2<R>{(R)-cr, (R)-ci} : Pair2<R>{(R)cr, (R)ci};
     }
+    __pipeline_wait_prior(0);
     __syncthreads();
     // groups outside, the thread's amplitudes inside: a group's metadata is read once, nothing is carried from one
     // amplitude to the next but the running sums, and the inner iterations are independent (instruction-level overlap)
@@ -591,12 +596,14 @@ __global__ void __launch_bounds__(RT, 2) transition_1q_kernel(const cplx<T> *__r
       base = ((base >> p) << (p + 1u)) | (base & ((1ull << p) - 1ull));
     }
     __syncthreads();
-    for (uint32_t i = tid; i < nel / V; i += RT) {
+    for (uint32_t i = tid; i < nel / V; i += RT) {   // asynchronous 16-byte copies: all of them in flight at once
       const uint32_t e = i * V;
       const uint64_t idx = base | roff[e >> L] | (uint64_t)(e & ((1u << L) - 1u));
-      *reinterpret_cast<cvec<T, V> *>(kt + e) = *reinterpret_cast<const cvec<T, V> *>(ket + idx);
-      *reinterpret_cast<cvec<T, V> *>(bt + e) = *reinterpret_cast<const cvec<T, V> *>(bra + idx);
+      __pipeline_memcpy_async(kt + e, ket + idx, 16);
+      __pipeline_memcpy_async(bt + e, bra + idx, 16);
     }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
